@@ -1,0 +1,1292 @@
+// cge_api.cu — implementation of the C ABI in include/cge.h: scene flattening + upload, kernel dispatch,
+// known-answer entry points, and the multi-GPU tile gather.  No CPU fallback exists anywhere in this file: every
+// compute entry point launches CUDA kernels or returns CGE_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "bvh_build.h"
+#include "cge.h"
+#include "dev_scene.h"
+#include "nccl_min.h"
+#include "render_kernels.cuh"
+
+using namespace cge;
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CGE_CUDA(call)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return fail(CGE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t upload(const std::vector<T>& h)
+    {
+        release();
+        n = h.size();
+        if (n == 0) {
+            // keep a valid non-null pointer so kernels can form addresses
+            cudaError_t e = cudaMalloc(&p, sizeof(T) > 16 ? sizeof(T) : 16);
+            return e;
+        }
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess)
+            return e;
+        return cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Scratch {
+    float* rgb = nullptr;
+    int* ids = nullptr;
+    size_t pixels = 0;
+    unsigned* tileCounter = nullptr; // [0] tile counter
+    Counters* counters = nullptr;
+    float* gatherRgb = nullptr; // rank 0 only: receive staging for the other ranks' packed tiles
+    int* gatherIds = nullptr;
+    size_t gatherPixels = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool busy = false;
+};
+} // namespace
+
+struct cge_scene {
+    int device = 0;
+    int sm_count = 0;
+    DevScene dev {};
+    DevBuf<float4> nodes, tris, shade, materials;
+    DevBuf<int4> textures;
+    DevBuf<float> texels, lights;
+    HostBvh bvh;
+    uint32_t n_triangles = 0, n_spheres = 0;
+    uint32_t accel_root_ref = 0, accel_root_count = 0;
+    bool any_transparent = false;
+    std::vector<cge_light_desc> host_lights;
+    std::mutex mu;
+    std::vector<Scratch*> pool;
+};
+
+struct cge_comm {
+    int rank = 0, n_ranks = 1, device = 0;
+    void* nccl = nullptr; // ncclComm_t
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline float4 f4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+inline float bitsf(uint32_t u)
+{
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+void light_counts(const std::vector<cge_light_desc>& lights, const cge_params& p, uint32_t& draws, uint32_t& shadows)
+{
+    draws = 0;
+    shadows = 0;
+    if (!(p.features & CGE_FEAT_SHADING))
+        return;
+    const bool hard = p.features & CGE_FEAT_HARD_SHADOW, soft = p.features & CGE_FEAT_SOFT_SHADOW;
+    for (const auto& l : lights) {
+        if (l.type == CGE_LIGHT_POINT) {
+            if (hard)
+                shadows += 1;
+        } else if (l.type == CGE_LIGHT_SEGMENT) {
+            if (soft) {
+                const uint32_t n = uint32_t(std::max(p.segment_samples, 0));
+                draws += n;
+                shadows += n;
+            }
+        } else if (soft) {
+            const uint32_t n = uint32_t(std::max(p.parallelogram_samples, 0));
+            draws += 2 * n * n;
+            shadows += n * n;
+        }
+    }
+}
+
+std::vector<float> pack_lights(const cge_light_desc* lights, uint32_t n)
+{
+    std::vector<float> out(size_t(n) * kLightFloats, 0.0f);
+    for (uint32_t i = 0; i < n; i++) {
+        out[size_t(i) * kLightFloats] = bitsf(lights[i].type);
+        std::memcpy(&out[size_t(i) * kLightFloats + 1], lights[i].v, sizeof(float) * 21);
+    }
+    return out;
+}
+
+int acquire_scratch(cge_scene* sc, size_t pixels, bool wantIds, size_t gatherPixels, Scratch** out)
+{
+    Scratch* s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(sc->mu);
+        for (auto* c : sc->pool)
+            if (!c->busy) {
+                s = c;
+                break;
+            }
+        if (!s) {
+            s = new Scratch();
+            sc->pool.push_back(s);
+        }
+        s->busy = true;
+    }
+    *out = s;
+    if (!s->stream) {
+        CGE_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CGE_CUDA(cudaEventCreate(&s->ev0));
+        CGE_CUDA(cudaEventCreate(&s->ev1));
+        CGE_CUDA(cudaEventCreate(&s->ev2));
+        CGE_CUDA(cudaMalloc(&s->tileCounter, 64));
+        CGE_CUDA(cudaMalloc(&s->counters, sizeof(Counters)));
+    }
+    if (s->pixels < pixels || (wantIds && !s->ids)) {
+        if (s->rgb)
+            cudaFree(s->rgb);
+        if (s->ids)
+            cudaFree(s->ids);
+        s->rgb = nullptr;
+        s->ids = nullptr;
+        s->pixels = 0;
+        CGE_CUDA(cudaMalloc(&s->rgb, pixels * 3 * sizeof(float)));
+        CGE_CUDA(cudaMalloc(&s->ids, pixels * sizeof(int)));
+        s->pixels = pixels;
+    }
+    if (gatherPixels > s->gatherPixels) {
+        if (s->gatherRgb)
+            cudaFree(s->gatherRgb);
+        if (s->gatherIds)
+            cudaFree(s->gatherIds);
+        s->gatherRgb = nullptr;
+        s->gatherIds = nullptr;
+        s->gatherPixels = 0;
+        CGE_CUDA(cudaMalloc(&s->gatherRgb, gatherPixels * 3 * sizeof(float)));
+        CGE_CUDA(cudaMalloc(&s->gatherIds, gatherPixels * sizeof(int)));
+        s->gatherPixels = gatherPixels;
+    }
+    return CGE_OK;
+}
+
+void release_scratch(cge_scene* sc, Scratch* s)
+{
+    if (!s)
+        return;
+    std::lock_guard<std::mutex> lk(sc->mu);
+    s->busy = false;
+}
+
+int validate_params(const cge_scene* sc, const cge_params* p)
+{
+    if (!sc || !p)
+        return fail(CGE_ERR_INVALID_ARG, "null scene or params");
+    if (p->width <= 0 || p->height <= 0 || int64_t(p->width) * p->height > (int64_t(1) << 30))
+        return fail(CGE_ERR_INVALID_ARG, "bad resolution");
+    if (p->features & CGE_FEAT_EXTRA_MASK)
+        return fail(CGE_ERR_UNSUPPORTED, "ExtraFeatures (reference src/common.h:54-65) are outside the GPU hot path");
+    if (p->features & ~(0x7fu | CGE_FEAT_EXTRA_MASK))
+        return fail(CGE_ERR_INVALID_ARG, "unknown feature bits");
+    if (p->ray_depth < 0 || p->ray_depth > kMaxRayDepth)
+        return fail(CGE_ERR_INVALID_ARG, "ray_depth must be in [0, 15]");
+    if (p->segment_samples < 0 || p->parallelogram_samples < 0 || p->segment_samples > 4096 || p->parallelogram_samples > 256)
+        return fail(CGE_ERR_INVALID_ARG, "bad sample counts");
+    if (p->sampler != CGE_SAMPLER_HASH)
+        return fail(CGE_ERR_UNSUPPORTED, "only CGE_SAMPLER_HASH is implemented");
+    if (p->traversal > CGE_TRAVERSAL_FAST)
+        return fail(CGE_ERR_INVALID_ARG, "bad traversal mode");
+    if ((p->features & CGE_FEAT_RECURSIVE) && sc->any_transparent)
+        return fail(CGE_ERR_UNSUPPORTED,
+            "a material has transparency != 1: with enableRecursive the reference recurses without bound "
+            "(src/render.cpp:122-130), there is no result to reproduce");
+    return CGE_OK;
+}
+
+DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
+{
+    DevParams d {};
+    d.width = p.width;
+    d.height = p.height;
+    d.features = p.features;
+    d.ray_depth = p.ray_depth;
+    d.segment_samples = p.segment_samples;
+    d.parallelogram_samples = p.parallelogram_samples;
+    d.seed = p.seed;
+    light_counts(sc->host_lights, p, d.draws_per_hit, d.shadow_rays_per_hit);
+    d.part_index = p.part_count > 1 ? p.part_index : 0;
+    d.part_count = p.part_count > 1 ? p.part_count : 1;
+    d.n_tiles_x = uint32_t((p.width + kTileW - 1) / kTileW);
+    d.n_tiles_y = uint32_t((p.height + kTileH - 1) / kTileH);
+    d.accel = (p.features & CGE_FEAT_ACCEL_STRUCTURE) ? 1u : 0u;
+    return d;
+}
+
+DevScene scene_for(const cge_scene* sc, const cge_params& p)
+{
+    DevScene d = sc->dev;
+    if (p.features & CGE_FEAT_ACCEL_STRUCTURE) {
+        d.root_ref = sc->accel_root_ref;
+        d.root_count = sc->accel_root_count;
+    } else {
+        // !enableAccelStructure: one getIntersecting over the whole (permuted) primitive vector
+        // (reference src/bounding_volume_hierarchy.cpp:303-305)
+        d.root_ref = 0;
+        d.root_count = d.n_prims;
+    }
+    return d;
+}
+
+template <typename F>
+void dispatch(bool fast, bool spheres, bool count, F&& f)
+{
+    // 8 instantiations of the kernels; the lambda receives the three flags as integral constants
+    auto d2 = [&](auto kFast, auto kSpheres) {
+        if (count)
+            f(kFast, kSpheres, std::true_type {});
+        else
+            f(kFast, kSpheres, std::false_type {});
+    };
+    auto d1 = [&](auto kFast) {
+        if (spheres)
+            d2(kFast, std::true_type {});
+        else
+            d2(kFast, std::false_type {});
+    };
+    if (fast)
+        d1(std::true_type {});
+    else
+        d1(std::false_type {});
+}
+
+// packed-tile <-> screen layout.  A rank's k-th tile occupies pixels [32k, 32k+32) of its packed buffer.
+__global__ void pack_tiles_kernel(const float* __restrict__ rgb, const int* __restrict__ ids, float* __restrict__ outRgb,
+    int* __restrict__ outIds, DevParams p, unsigned myTiles)
+{
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned k = g / 32, lane = g % 32;
+    if (k >= myTiles)
+        return;
+    const unsigned tile = p.part_index + k * p.part_count;
+    const int x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
+    const int y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
+    float r = 0.f, gg = 0.f, b = 0.f;
+    int id = -1;
+    if (x < p.width && y < p.height) {
+        const size_t idx = size_t(p.height - 1 - y) * size_t(p.width) + size_t(x);
+        r = rgb[idx * 3], gg = rgb[idx * 3 + 1], b = rgb[idx * 3 + 2];
+        if (ids)
+            id = ids[idx];
+    }
+    outRgb[size_t(g) * 3] = r;
+    outRgb[size_t(g) * 3 + 1] = gg;
+    outRgb[size_t(g) * 3 + 2] = b;
+    if (outIds)
+        outIds[g] = id;
+}
+
+__global__ void unpack_tiles_kernel(const float* __restrict__ inRgb, const int* __restrict__ inIds, float* __restrict__ rgb,
+    int* __restrict__ ids, DevParams p, unsigned srcRank, unsigned nRanks, unsigned srcTiles)
+{
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned k = g / 32, lane = g % 32;
+    if (k >= srcTiles)
+        return;
+    const unsigned tile = srcRank + k * nRanks;
+    const int x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
+    const int y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
+    if (x < p.width && y < p.height) {
+        const size_t idx = size_t(p.height - 1 - y) * size_t(p.width) + size_t(x);
+        rgb[idx * 3] = inRgb[size_t(g) * 3];
+        rgb[idx * 3 + 1] = inRgb[size_t(g) * 3 + 1];
+        rgb[idx * 3 + 2] = inRgb[size_t(g) * 3 + 2];
+        if (ids && inIds)
+            ids[idx] = inIds[g];
+    }
+}
+
+unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
+{
+    const unsigned nTiles = d.n_tiles_x * d.n_tiles_y;
+    return nTiles > rank ? (nTiles - rank + nRanks - 1) / nRanks : 0;
+}
+
+int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_params* p, const DevParams& dp, float* rgbDev,
+    int* idsDev, uint32_t* launches)
+{
+    const DevScene ds = scene_for(sc, *p);
+    DevCamera dc { cam->origin[0], cam->origin[1], cam->origin[2], cam->quat[0], cam->quat[1], cam->quat[2], cam->quat[3],
+        cam->half_width, cam->half_height };
+    CGE_CUDA(cudaMemsetAsync(s->tileCounter, 0, 64, s->stream));
+    CGE_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream));
+    const bool fast = p->traversal == CGE_TRAVERSAL_FAST && (p->features & CGE_FEAT_ACCEL_STRUCTURE);
+#ifdef CGE_COUNT_TESTS
+    const bool count = true;
+#else
+    const bool count = false;
+#endif
+    cudaError_t err = cudaSuccess;
+    dispatch(fast, ds.has_spheres != 0, count, [&](auto kFast, auto kSpheres, auto kCount) {
+        auto kern = render_kernel<decltype(kFast)::value, decltype(kSpheres)::value, decltype(kCount)::value>;
+        int perSm = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
+        if (err != cudaSuccess)
+            return;
+        perSm = std::max(perSm, 1);
+        const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
+        unsigned grid = unsigned(sc->sm_count * perSm);
+        grid = std::max(1u, std::min(grid, (myTiles + 3) / 4));
+        kern<<<grid, 128, 0, s->stream>>>(ds, dc, dp, rgbDev, idsDev, s->tileCounter, s->counters);
+        err = cudaGetLastError();
+    });
+    if (err != cudaSuccess)
+        return fail(CGE_ERR_CUDA, std::string("render_kernel launch: ") + cudaGetErrorString(err));
+    *launches += 1;
+    return CGE_OK;
+}
+
+int fill_stats(Scratch* s, cge_stats* st, uint32_t launches)
+{
+    if (!st)
+        return CGE_OK;
+    Counters c {};
+    CGE_CUDA(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CGE_CUDA(cudaStreamSynchronize(s->stream));
+    std::memset(st, 0, sizeof(*st));
+    st->primary_rays = c.primary;
+    st->bounce_rays = c.bounce;
+    st->shadow_rays = c.shadow;
+    st->reference_rays = c.reference;
+    st->box_tests = c.box;
+    st->tri_tests = c.tri;
+    float ms = 0.f;
+    CGE_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    st->kernel_ms = ms;
+    CGE_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev2));
+    st->total_ms = ms;
+    st->kernel_launches = launches;
+    return CGE_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// entry points
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int cge_abi_version(void) { return CGE_ABI_VERSION; }
+const char* cge_last_error(void) { return g_err.c_str(); }
+
+int cge_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cge_camera_from_trackball(float fovy, float aspect, const float look_at[3], float dist, const float rot[3], cge_camera* out)
+{
+    if (!look_at || !rot || !out)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    // Trackball ctor (reference framework/src/trackball.cpp:23-31)
+    out->half_height = std::tan(fovy / 2.0f);
+    out->half_width = aspect * out->half_height;
+    // glm::quat(eulerAngles) (glm/detail/type_quat.inl:208-217)
+    const float cx = std::cos(rot[0] * 0.5f), cy = std::cos(rot[1] * 0.5f), cz = std::cos(rot[2] * 0.5f);
+    const float sx = std::sin(rot[0] * 0.5f), sy = std::sin(rot[1] * 0.5f), sz = std::sin(rot[2] * 0.5f);
+    const float w = cx * cy * cz + sx * sy * sz;
+    const float x = sx * cy * cz - cx * sy * sz;
+    const float y = cx * sy * cz + sx * cy * sz;
+    const float z = cx * cy * sz - sx * sy * cz;
+    out->quat[0] = w, out->quat[1] = x, out->quat[2] = y, out->quat[3] = z;
+    // position() = lookAt + q * vec3(0, 0, -dist) (trackball.cpp:71-74)
+    const vec3 p = quat_rotate(w, v3(x, y, z), v3(0.0f, 0.0f, -dist));
+    out->origin[0] = look_at[0] + p.x;
+    out->origin[1] = look_at[1] + p.y;
+    out->origin[2] = look_at[2] + p.z;
+    return CGE_OK;
+}
+
+int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
+{
+    if (!d || !out)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if ((d->n_meshes && !d->meshes) || (d->n_vertices && !d->vertices) || (d->n_triangles && !d->triangles)
+        || (d->n_spheres && !d->spheres) || (d->n_lights && !d->lights) || (d->n_textures && !d->textures)
+        || (d->n_texels && !d->texels))
+        return fail(CGE_ERR_INVALID_ARG, "count without array");
+    // ---- validate indices -------------------------------------------------------------------------------
+    uint64_t triSum = 0;
+    for (uint32_t m = 0; m < d->n_meshes; m++) {
+        const auto& md = d->meshes[m];
+        if (uint64_t(md.vertex_offset) + md.vertex_count > d->n_vertices || uint64_t(md.triangle_offset) + md.triangle_count > d->n_triangles)
+            return fail(CGE_ERR_INVALID_ARG, "mesh range out of bounds");
+        if (md.triangle_offset != triSum)
+            return fail(CGE_ERR_INVALID_ARG, "meshes must list their triangles contiguously in mesh order");
+        triSum += md.triangle_count;
+        if (md.texture_id >= int32_t(d->n_textures))
+            return fail(CGE_ERR_INVALID_ARG, "texture id out of range");
+        for (uint32_t t = 0; t < md.triangle_count; t++)
+            for (int k = 0; k < 3; k++)
+                if (d->triangles[3 * size_t(md.triangle_offset + t) + k] >= md.vertex_count)
+                    return fail(CGE_ERR_INVALID_ARG, "vertex index out of range");
+    }
+    if (triSum != d->n_triangles)
+        return fail(CGE_ERR_INVALID_ARG, "triangles not covered by meshes");
+    for (uint32_t t = 0; t < d->n_textures; t++) {
+        const auto& td = d->textures[t];
+        if (td.width <= 0 || td.height <= 0 || td.texel_offset + uint64_t(td.width) * uint64_t(td.height) > d->n_texels
+            || td.texel_offset > 0x7fffffffull)
+            return fail(CGE_ERR_INVALID_ARG, "texture out of bounds");
+    }
+    for (uint32_t l = 0; l < d->n_lights; l++)
+        if (d->lights[l].type > CGE_LIGHT_PARALLELOGRAM)
+            return fail(CGE_ERR_INVALID_ARG, "bad light type");
+
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+        cudaGetLastError();
+        return fail(CGE_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    }
+    if (device < 0 || device >= nDev)
+        return fail(CGE_ERR_INVALID_ARG, "bad device ordinal");
+    CGE_CUDA(cudaSetDevice(device));
+
+    auto* sc = new cge_scene();
+    sc->device = device;
+    cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, device);
+    sc->n_triangles = d->n_triangles;
+    sc->n_spheres = d->n_spheres;
+    const uint32_t nPrims = d->n_triangles + d->n_spheres;
+
+    // ---- BVH (reference order) ----------------------------------------------------------------------------
+    bool haveBvh = false;
+    if (nPrims) {
+        haveBvh = d->bvh_nodes ? adopt_bvh(*d, sc->bvh) : build_reference_bvh(*d, sc->bvh);
+        if (!haveBvh) {
+            delete sc;
+            return fail(CGE_ERR_INVALID_ARG, "supplied BVH is inconsistent with the scene");
+        }
+        if (sc->bvh.n_levels > uint32_t(kStackSize - 4)) {
+            delete sc;
+            return fail(CGE_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+        }
+    }
+
+    // ---- global primitive tables ------------------------------------------------------------------------------
+    std::vector<uint32_t> triMesh(d->n_triangles);
+    for (uint32_t m = 0; m < d->n_meshes; m++)
+        for (uint32_t t = 0; t < d->meshes[m].triangle_count; t++)
+            triMesh[d->meshes[m].triangle_offset + t] = m;
+
+    // visit rank = position in the reference's exhaustive right-first DFS (src/bounding_volume_hierarchy.cpp:312-361)
+    std::vector<uint32_t> rank(nPrims, 0);
+    if (haveBvh) {
+        std::vector<uint32_t> st { sc->bvh.root };
+        uint32_t r = 0;
+        while (!st.empty()) {
+            const uint32_t ni = st.back();
+            st.pop_back();
+            const auto& n = sc->bvh.nodes[ni];
+            if (n.is_leaf) {
+                for (uint32_t i = n.beg; i < n.end; i++)
+                    rank[i] = r++;
+            } else {
+                st.push_back(n.left);
+                st.push_back(n.right);
+            }
+        }
+    }
+
+    std::vector<float4> tris(size_t(nPrims) * kTriRows), shade(size_t(nPrims) * kShadeRows);
+    const float qnan = std::nanf("");
+    for (uint32_t i = 0; i < nPrims; i++) {
+        const uint32_t gid = sc->bvh.prim_order[i];
+        float4* tr = &tris[size_t(i) * kTriRows];
+        float4* sh = &shade[size_t(i) * kShadeRows];
+        if (gid < d->n_triangles) {
+            const uint32_t m = triMesh[gid];
+            const auto& md = d->meshes[m];
+            const uint32_t* idx = d->triangles + 3 * size_t(gid);
+            const cge_vertex& a = d->vertices[md.vertex_offset + idx[0]];
+            const cge_vertex& b = d->vertices[md.vertex_offset + idx[1]];
+            const cge_vertex& c = d->vertices[md.vertex_offset + idx[2]];
+            const vec3 v0 = v3(a.position[0], a.position[1], a.position[2]);
+            const vec3 v1 = v3(b.position[0], b.position[1], b.position[2]);
+            const vec3 v2 = v3(c.position[0], c.position[1], c.position[2]);
+            const TriPre t = triangle_precompute(v0, v1, v2);
+            tr[0] = f4(t.n.x, t.n.y, t.n.z, t.D);
+            tr[1] = f4(v0.x, v0.y, v0.z, t.e0.x);
+            tr[2] = f4(t.e0.y, t.e0.z, v1.x, v1.y);
+            tr[3] = f4(v1.z, t.e1.x, t.e1.y, t.e1.z);
+            tr[4] = f4(v2.x, v2.y, v2.z, t.e2.x);
+            tr[5] = f4(t.e2.y, t.e2.z, bitsf(rank[i]), bitsf(0u));
+            sh[0] = f4(a.normal[0], a.normal[1], a.normal[2], a.texcoord[0]);
+            sh[1] = f4(b.normal[0], b.normal[1], b.normal[2], a.texcoord[1]);
+            sh[2] = f4(c.normal[0], c.normal[1], c.normal[2], b.texcoord[0]);
+            sh[3] = f4(b.texcoord[1], c.texcoord[0], c.texcoord[1], 0.0f);
+            sh[4] = f4(bitsf(m), bitsf(gid), 0.0f, 0.0f);
+        } else {
+            const auto& sd = d->spheres[gid - d->n_triangles];
+            tr[0] = f4(qnan, qnan, qnan, qnan);
+            tr[1] = f4(sd.center[0], sd.center[1], sd.center[2], sd.radius);
+            tr[2] = tr[3] = tr[4] = f4(qnan, qnan, qnan, qnan);
+            tr[5] = f4(qnan, qnan, bitsf(rank[i]), bitsf(1u));
+            sh[0] = sh[1] = sh[2] = sh[3] = f4(0, 0, 0, 0);
+            sh[4] = f4(bitsf(d->n_meshes + (gid - d->n_triangles)), bitsf(gid), 0.0f, 0.0f);
+        }
+    }
+
+    // ---- inner nodes: each carries both child boxes ----------------------------------------------------------
+    std::vector<float4> nodes;
+    if (haveBvh) {
+        std::vector<uint32_t> innerIndex(sc->bvh.nodes.size(), 0xffffffffu);
+        uint32_t nInner = 0;
+        for (size_t i = 0; i < sc->bvh.nodes.size(); i++)
+            if (!sc->bvh.nodes[i].is_leaf)
+                innerIndex[i] = nInner++;
+        nodes.resize(size_t(nInner) * kNodeRows);
+        auto childRef = [&](uint32_t ni, uint32_t& ref, uint32_t& cnt) {
+            const auto& n = sc->bvh.nodes[ni];
+            if (n.is_leaf) {
+                ref = n.beg;
+                cnt = n.end - n.beg;
+            } else {
+                ref = innerIndex[ni];
+                cnt = 0;
+            }
+        };
+        for (size_t i = 0; i < sc->bvh.nodes.size(); i++) {
+            const auto& n = sc->bvh.nodes[i];
+            if (n.is_leaf)
+                continue;
+            const auto& L = sc->bvh.nodes[n.left];
+            const auto& R = sc->bvh.nodes[n.right];
+            uint32_t lr, lc, rr, rc;
+            childRef(n.left, lr, lc);
+            childRef(n.right, rr, rc);
+            float4* q = &nodes[size_t(innerIndex[i]) * kNodeRows];
+            q[0] = f4(L.lower[0], L.lower[1], L.lower[2], L.upper[0]);
+            q[1] = f4(L.upper[1], L.upper[2], R.lower[0], R.lower[1]);
+            q[2] = f4(R.lower[2], R.upper[0], R.upper[1], R.upper[2]);
+            q[3] = f4(bitsf(lr), bitsf(rr), bitsf(lc), bitsf(rc));
+        }
+        childRef(sc->bvh.root, sc->accel_root_ref, sc->accel_root_count);
+    }
+
+    // ---- materials: meshes then spheres -----------------------------------------------------------------------
+    std::vector<float4> mats(size_t(d->n_meshes + d->n_spheres) * kMaterialRows);
+    for (uint32_t m = 0; m < d->n_meshes; m++) {
+        const auto& md = d->meshes[m];
+        mats[size_t(m) * 3 + 0] = f4(md.kd[0], md.kd[1], md.kd[2], md.shininess);
+        mats[size_t(m) * 3 + 1] = f4(md.ks[0], md.ks[1], md.ks[2], md.transparency);
+        mats[size_t(m) * 3 + 2] = f4(bitsf(uint32_t(md.texture_id)), 0, 0, 0);
+        if (md.triangle_count && md.transparency != 1.0f)
+            sc->any_transparent = true;
+    }
+    for (uint32_t s = 0; s < d->n_spheres; s++) {
+        const auto& sd = d->spheres[s];
+        const size_t m = d->n_meshes + s;
+        mats[m * 3 + 0] = f4(sd.kd[0], sd.kd[1], sd.kd[2], sd.shininess);
+        mats[m * 3 + 1] = f4(sd.ks[0], sd.ks[1], sd.ks[2], sd.transparency);
+        mats[m * 3 + 2] = f4(bitsf(uint32_t(-1)), 0, 0, 0); // sphere hits never sample a texture (reference :421-423)
+        if (sd.transparency != 1.0f)
+            sc->any_transparent = true;
+    }
+    std::vector<int4> texs(d->n_textures);
+    for (uint32_t t = 0; t < d->n_textures; t++)
+        texs[t] = make_int4(d->textures[t].width, d->textures[t].height, int(d->textures[t].texel_offset), 0);
+    std::vector<float> texels(d->texels, d->texels + size_t(d->n_texels) * 3);
+    sc->host_lights.assign(d->lights, d->lights + d->n_lights);
+    std::vector<float> lights = pack_lights(d->lights, d->n_lights);
+
+    cudaError_t e = cudaSuccess;
+    auto up = [&](auto& buf, const auto& host) {
+        if (e == cudaSuccess)
+            e = buf.upload(host);
+    };
+    up(sc->nodes, nodes);
+    up(sc->tris, tris);
+    up(sc->shade, shade);
+    up(sc->materials, mats);
+    up(sc->textures, texs);
+    up(sc->texels, texels);
+    up(sc->lights, lights);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("scene upload: ") + cudaGetErrorString(e);
+        cge_scene_destroy(sc);
+        return fail(e == cudaErrorMemoryAllocation ? CGE_ERR_NOMEM : CGE_ERR_CUDA, msg);
+    }
+    sc->dev.nodes = sc->nodes.p;
+    sc->dev.tris = sc->tris.p;
+    sc->dev.shade = sc->shade.p;
+    sc->dev.materials = sc->materials.p;
+    sc->dev.textures = sc->textures.p;
+    sc->dev.texels = sc->texels.p;
+    sc->dev.lights = sc->lights.p;
+    sc->dev.n_lights = d->n_lights;
+    sc->dev.n_prims = nPrims;
+    sc->dev.has_spheres = d->n_spheres ? 1u : 0u;
+    *out = sc;
+    return CGE_OK;
+}
+
+int cge_scene_update_lights(cge_scene* sc, const cge_light_desc* lights, uint32_t n)
+{
+    if (!sc || (n && !lights))
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    for (uint32_t l = 0; l < n; l++)
+        if (lights[l].type > CGE_LIGHT_PARALLELOGRAM)
+            return fail(CGE_ERR_INVALID_ARG, "bad light type");
+    CGE_CUDA(cudaSetDevice(sc->device));
+    std::vector<float> packed = pack_lights(lights, n);
+    std::lock_guard<std::mutex> lk(sc->mu);
+    if (n * size_t(kLightFloats) <= sc->lights.n && n > 0) {
+        CGE_CUDA(cudaMemcpy(sc->lights.p, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        CGE_CUDA(cudaDeviceSynchronize());
+        CGE_CUDA(sc->lights.upload(packed));
+        sc->dev.lights = sc->lights.p;
+    }
+    sc->dev.n_lights = n;
+    sc->host_lights.assign(lights, lights + n);
+    return CGE_OK;
+}
+
+int cge_scene_destroy(cge_scene* sc)
+{
+    if (!sc)
+        return CGE_OK;
+    cudaSetDevice(sc->device);
+    for (auto* s : sc->pool) {
+        if (s->stream)
+            cudaStreamSynchronize(s->stream);
+        cudaFree(s->rgb);
+        cudaFree(s->ids);
+        cudaFree(s->tileCounter);
+        cudaFree(s->counters);
+        cudaFree(s->gatherRgb);
+        cudaFree(s->gatherIds);
+        if (s->ev0)
+            cudaEventDestroy(s->ev0);
+        if (s->ev1)
+            cudaEventDestroy(s->ev1);
+        if (s->ev2)
+            cudaEventDestroy(s->ev2);
+        if (s->stream)
+            cudaStreamDestroy(s->stream);
+        delete s;
+    }
+    sc->nodes.release();
+    sc->tris.release();
+    sc->shade.release();
+    sc->materials.release();
+    sc->textures.release();
+    sc->texels.release();
+    sc->lights.release();
+    delete sc;
+    return CGE_OK;
+}
+
+int cge_scene_bvh_info(const cge_scene* sc, uint32_t* nNodes, uint32_t* nLevels, uint32_t* nLeaves, uint32_t* maxLeaf)
+{
+    if (!sc)
+        return fail(CGE_ERR_INVALID_ARG, "null scene");
+    if (nNodes)
+        *nNodes = uint32_t(sc->bvh.nodes.size());
+    if (nLevels)
+        *nLevels = sc->bvh.n_levels;
+    if (nLeaves)
+        *nLeaves = sc->bvh.n_leaves;
+    if (maxLeaf)
+        *maxLeaf = sc->bvh.max_leaf_prims;
+    return CGE_OK;
+}
+
+int cge_scene_bvh_export(const cge_scene* sc, cge_bvh_node* nodesOut, uint32_t* orderOut)
+{
+    if (!sc)
+        return fail(CGE_ERR_INVALID_ARG, "null scene");
+    if (nodesOut && !sc->bvh.nodes.empty())
+        std::memcpy(nodesOut, sc->bvh.nodes.data(), sc->bvh.nodes.size() * sizeof(cge_bvh_node));
+    if (orderOut && !sc->bvh.prim_order.empty())
+        std::memcpy(orderOut, sc->bvh.prim_order.data(), sc->bvh.prim_order.size() * sizeof(uint32_t));
+    return CGE_OK;
+}
+
+int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float* rgbOut, int32_t* idsOut, cge_stats* st)
+{
+    int rc = validate_params(sc, p);
+    if (rc)
+        return rc;
+    if (!cam || !rgbOut)
+        return fail(CGE_ERR_INVALID_ARG, "null camera or output");
+    const bool wantIds = (p->flags & CGE_FLAG_WANT_PRIM_IDS) && idsOut;
+    const bool devOut = p->flags & CGE_FLAG_RGB_DEVICE_PTR;
+    CGE_CUDA(cudaSetDevice(sc->device));
+    const size_t pixels = size_t(p->width) * size_t(p->height);
+    Scratch* s = nullptr;
+    rc = acquire_scratch(sc, devOut ? 1 : pixels, wantIds, 0, &s);
+    if (rc) {
+        release_scratch(sc, s);
+        return rc;
+    }
+    const DevParams dp = make_dev_params(sc, *p);
+    float* rgbDev = devOut ? rgbOut : s->rgb;
+    int* idsDev = wantIds ? (devOut ? idsOut : s->ids) : nullptr;
+    uint32_t launches = 0;
+    cudaEventRecord(s->ev0, s->stream);
+    rc = launch_render(sc, s, cam, p, dp, rgbDev, idsDev, &launches);
+    cudaEventRecord(s->ev1, s->stream);
+    if (rc == CGE_OK && !devOut) {
+        if (dp.part_count <= 1) {
+            cudaMemcpyAsync(rgbOut, s->rgb, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+            if (wantIds)
+                cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+        } else {
+            // partial frame: copy back only the rows of tiles this partition touched would need a gather;
+            // callers that partition (cge_render_distributed) use the packed path instead.  Here: full copy of the
+            // scratch frame is wrong for untouched pixels, so copy tile rows individually.
+            const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
+            for (unsigned k = 0; k < myTiles; k++) {
+                const unsigned tile = dp.part_index + k * dp.part_count;
+                const int x0 = int(tile % dp.n_tiles_x) * kTileW, y0 = int(tile / dp.n_tiles_x) * kTileH;
+                const int w = std::min(kTileW, p->width - x0);
+                for (int y = y0; y < std::min(y0 + kTileH, p->height); y++) {
+                    const size_t idx = size_t(p->height - 1 - y) * size_t(p->width) + size_t(x0);
+                    cudaMemcpyAsync(rgbOut + idx * 3, s->rgb + idx * 3, size_t(w) * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+                    if (wantIds)
+                        cudaMemcpyAsync(idsOut + idx, s->ids + idx, size_t(w) * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+                }
+            }
+        }
+    }
+    cudaEventRecord(s->ev2, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (rc == CGE_OK && e != cudaSuccess)
+        rc = fail(CGE_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    if (rc == CGE_OK)
+        rc = fill_stats(s, st, launches);
+    release_scratch(sc, s);
+    return rc;
+}
+
+int cge_trace_rays(cge_scene* sc, const float* rays7, uint32_t n, const cge_params* pIn, float* rgbOut, int32_t* idsOut)
+{
+    if (!pIn)
+        return fail(CGE_ERR_INVALID_ARG, "null params");
+    cge_params p = *pIn;
+    p.width = p.width > 0 ? p.width : 1;
+    p.height = p.height > 0 ? p.height : 1;
+    int rc = validate_params(sc, &p);
+    if (rc)
+        return rc;
+    if (!rays7 || !rgbOut)
+        return fail(CGE_ERR_INVALID_ARG, "null rays or output");
+    if (n == 0)
+        return CGE_OK;
+    CGE_CUDA(cudaSetDevice(sc->device));
+    Scratch* s = nullptr;
+    rc = acquire_scratch(sc, n, true, 0, &s);
+    if (rc) {
+        release_scratch(sc, s);
+        return rc;
+    }
+    float* dRays = nullptr;
+    cudaError_t e = cudaMalloc(&dRays, size_t(n) * 7 * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dRays, rays7, size_t(n) * 7 * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream);
+    const DevParams dp = make_dev_params(sc, p);
+    const DevScene ds = scene_for(sc, p);
+    const bool fast = p.traversal == CGE_TRAVERSAL_FAST && (p.features & CGE_FEAT_ACCEL_STRUCTURE);
+    if (e == cudaSuccess) {
+        dispatch(fast, ds.has_spheres != 0, false, [&](auto kFast, auto kSpheres, auto kCount) {
+            trace_rays_kernel<decltype(kFast)::value, decltype(kSpheres)::value, decltype(kCount)::value>
+                <<<(n + 127) / 128, 128, 0, s->stream>>>(ds, dp, dRays, n, s->rgb, idsOut ? s->ids : nullptr, s->counters);
+            e = cudaGetLastError();
+        });
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(rgbOut, s->rgb, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && idsOut)
+        e = cudaMemcpyAsync(idsOut, s->ids, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e2 = cudaStreamSynchronize(s->stream);
+    cudaFree(dRays);
+    release_scratch(sc, s);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(CGE_ERR_CUDA, std::string("trace_rays: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return CGE_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// KAT kernels: the six libIntersect functions evaluated on the device, one case per thread
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ Ray load_ray(const float* q) { return Ray { v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), q[6] }; }
+
+__global__ void kat_triangle_kernel(const float* v, float* ray7, int* hit, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = v + size_t(i) * 9;
+    Ray r = load_ray(ray7 + size_t(i) * 7);
+    hit[i] = intersect_triangle(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), v3(a[6], a[7], a[8]), r) ? 1 : 0;
+    ray7[size_t(i) * 7 + 6] = r.t;
+}
+// Same test through the precomputed-plane path used by the traversal kernel (must agree bit for bit with I4).
+__global__ void kat_triangle_pre_kernel(const float* v, float* ray7, int* hit, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = v + size_t(i) * 9;
+    const vec3 v0 = v3(a[0], a[1], a[2]), v1 = v3(a[3], a[4], a[5]), v2 = v3(a[6], a[7], a[8]);
+    Ray r = load_ray(ray7 + size_t(i) * 7);
+    const TriPre t = triangle_precompute(v0, v1, v2);
+    const float tt = fdiv(fsub(t.D, dot(r.o, t.n)), dot(r.d, t.n));
+    bool ok = (tt >= 0.0f) && (r.t >= tt);
+    if (ok) {
+        const vec3 p = r.d * tt + r.o;
+        ok = dot(t.e0, p - v0) >= 0.0f && dot(t.e1, p - v1) >= 0.0f && dot(t.e2, p - v2) >= 0.0f;
+    }
+    hit[i] = ok ? 1 : 0;
+    if (ok)
+        ray7[size_t(i) * 7 + 6] = tt;
+}
+__global__ void kat_aabb_kernel(const float* b, float* ray7, int* hit, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = b + size_t(i) * 6;
+    Ray r = load_ray(ray7 + size_t(i) * 7);
+    hit[i] = intersect_aabb(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), r) ? 1 : 0;
+    ray7[size_t(i) * 7 + 6] = r.t;
+}
+__global__ void kat_sphere_kernel(const float* sp, float* ray7, float* nrm, int* hit, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = sp + size_t(i) * 4;
+    Ray r = load_ray(ray7 + size_t(i) * 7);
+    vec3 nn = v3(0.0f);
+    hit[i] = intersect_sphere(v3(a[0], a[1], a[2]), a[3], r, &nn) ? 1 : 0;
+    ray7[size_t(i) * 7 + 6] = r.t;
+    nrm[size_t(i) * 3] = nn.x, nrm[size_t(i) * 3 + 1] = nn.y, nrm[size_t(i) * 3 + 2] = nn.z;
+}
+__global__ void kat_plane_kernel(const float* pl, float* ray7, int* hit, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = pl + size_t(i) * 4;
+    Ray r = load_ray(ray7 + size_t(i) * 7);
+    Plane p { a[0], v3(a[1], a[2], a[3]) };
+    hit[i] = intersect_plane(p, r) ? 1 : 0;
+    ray7[size_t(i) * 7 + 6] = r.t;
+}
+__global__ void kat_triangle_plane_kernel(const float* v, float* out4, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = v + size_t(i) * 9;
+    const Plane p = triangle_plane(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), v3(a[6], a[7], a[8]));
+    out4[size_t(i) * 4] = p.D, out4[size_t(i) * 4 + 1] = p.n.x, out4[size_t(i) * 4 + 2] = p.n.y, out4[size_t(i) * 4 + 3] = p.n.z;
+}
+__global__ void kat_pit_kernel(const float* v, const float* nrm, const float* pt, int* inside, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* a = v + size_t(i) * 9;
+    inside[i] = point_in_triangle(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), v3(a[6], a[7], a[8]),
+                    v3(nrm[size_t(i) * 3], nrm[size_t(i) * 3 + 1], nrm[size_t(i) * 3 + 2]),
+                    v3(pt[size_t(i) * 3], pt[size_t(i) * 3 + 1], pt[size_t(i) * 3 + 2]))
+        ? 1
+        : 0;
+}
+
+struct KatBufs {
+    std::vector<void*> dev;
+    ~KatBufs()
+    {
+        for (void* p : dev)
+            cudaFree(p);
+    }
+    template <typename T>
+    T* in(const T* host, size_t count, cudaError_t& e)
+    {
+        T* d = nullptr;
+        if (e == cudaSuccess)
+            e = cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) {
+            dev.push_back(d);
+            if (host)
+                e = cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice);
+        }
+        return d;
+    }
+};
+
+int kat_begin(int device)
+{
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+        cudaGetLastError();
+        return fail(CGE_ERR_CUDA, "no CUDA device (the KAT entry points run the device functions; there is no CPU path)");
+    }
+    if (device < 0 || device >= nDev)
+        return fail(CGE_ERR_INVALID_ARG, "bad device ordinal");
+    CGE_CUDA(cudaSetDevice(device));
+    return CGE_OK;
+}
+int kat_end(cudaError_t e)
+{
+    if (e == cudaSuccess)
+        e = cudaDeviceSynchronize();
+    if (e == cudaSuccess)
+        e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(CGE_ERR_CUDA, std::string("kat: ") + cudaGetErrorString(e));
+    return CGE_OK;
+}
+} // namespace
+
+extern "C" {
+
+int cge_kat_triangle(const float* v, float* ray7, int32_t* hit, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(v, size_t(n) * 9, e);
+    float* dr = b.in(ray7, size_t(n) * 7, e);
+    int* dh = b.in<int>(nullptr, n, e);
+    if (e == cudaSuccess) {
+        kat_triangle_kernel<<<(n + 255) / 256, 256>>>(dv, dr, dh, n);
+        e = cudaMemcpy(ray7, dr, size_t(n) * 7 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(hit, dh, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+// variant through the precomputed rows (not in the reference API; used to prove the precompute is exact)
+int cge_kat_triangle_precomputed(const float* v, float* ray7, int32_t* hit, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(v, size_t(n) * 9, e);
+    float* dr = b.in(ray7, size_t(n) * 7, e);
+    int* dh = b.in<int>(nullptr, n, e);
+    if (e == cudaSuccess) {
+        kat_triangle_pre_kernel<<<(n + 255) / 256, 256>>>(dv, dr, dh, n);
+        e = cudaMemcpy(ray7, dr, size_t(n) * 7 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(hit, dh, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+int cge_kat_aabb(const float* box, float* ray7, int32_t* hit, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(box, size_t(n) * 6, e);
+    float* dr = b.in(ray7, size_t(n) * 7, e);
+    int* dh = b.in<int>(nullptr, n, e);
+    if (e == cudaSuccess) {
+        kat_aabb_kernel<<<(n + 255) / 256, 256>>>(dv, dr, dh, n);
+        e = cudaMemcpy(ray7, dr, size_t(n) * 7 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(hit, dh, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+int cge_kat_sphere(const float* sp, float* ray7, float* nrm, int32_t* hit, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(sp, size_t(n) * 4, e);
+    float* dr = b.in(ray7, size_t(n) * 7, e);
+    float* dn = b.in<float>(nullptr, size_t(n) * 3, e);
+    int* dh = b.in<int>(nullptr, n, e);
+    if (e == cudaSuccess) {
+        kat_sphere_kernel<<<(n + 255) / 256, 256>>>(dv, dr, dn, dh, n);
+        e = cudaMemcpy(ray7, dr, size_t(n) * 7 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(nrm, dn, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(hit, dh, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+int cge_kat_plane(const float* pl, float* ray7, int32_t* hit, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(pl, size_t(n) * 4, e);
+    float* dr = b.in(ray7, size_t(n) * 7, e);
+    int* dh = b.in<int>(nullptr, n, e);
+    if (e == cudaSuccess) {
+        kat_plane_kernel<<<(n + 255) / 256, 256>>>(dv, dr, dh, n);
+        e = cudaMemcpy(ray7, dr, size_t(n) * 7 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(hit, dh, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+int cge_kat_triangle_plane(const float* v, float* out4, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(v, size_t(n) * 9, e);
+    float* dout = b.in<float>(nullptr, size_t(n) * 4, e);
+    if (e == cudaSuccess) {
+        kat_triangle_plane_kernel<<<(n + 255) / 256, 256>>>(dv, dout, n);
+        e = cudaMemcpy(out4, dout, size_t(n) * 4 * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+int cge_kat_point_in_triangle(const float* v, const float* nrm, const float* pt, int32_t* inside, uint32_t n, int device)
+{
+    int rc = kat_begin(device);
+    if (rc || n == 0)
+        return rc;
+    KatBufs b;
+    cudaError_t e = cudaSuccess;
+    float* dv = b.in(v, size_t(n) * 9, e);
+    float* dn = b.in(nrm, size_t(n) * 3, e);
+    float* dp = b.in(pt, size_t(n) * 3, e);
+    int* dh = b.in<int>(nullptr, n, e);
+    if (e == cudaSuccess) {
+        kat_pit_kernel<<<(n + 255) / 256, 256>>>(dv, dn, dp, dh, n);
+        e = cudaMemcpy(inside, dh, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    return kat_end(e);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-GPU: NCCL (loaded lazily with dlopen so that the library itself has no link-time NCCL dependency)
+// ---------------------------------------------------------------------------------------------------------------
+int cge_comm_unique_id(uint8_t idOut[CGE_UNIQUE_ID_BYTES])
+{
+    const NcclApi* api = nccl_api();
+    if (!api)
+        return fail(CGE_ERR_NCCL, "libnccl.so.2 not found");
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess)
+        return fail(CGE_ERR_NCCL, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == CGE_UNIQUE_ID_BYTES, "unique id size");
+    std::memcpy(idOut, &id, sizeof(id));
+    return CGE_OK;
+}
+
+int cge_comm_create(const uint8_t idIn[CGE_UNIQUE_ID_BYTES], int rank, int nRanks, int device, cge_comm** out)
+{
+    if (!idIn || !out || rank < 0 || nRanks < 1 || rank >= nRanks)
+        return fail(CGE_ERR_INVALID_ARG, "bad comm arguments");
+    const NcclApi* api = nccl_api();
+    if (!api)
+        return fail(CGE_ERR_NCCL, "libnccl.so.2 not found");
+    CGE_CUDA(cudaSetDevice(device));
+    ncclUniqueId id;
+    std::memcpy(&id, idIn, sizeof(id));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = api->CommInitRank(&comm, nRanks, id, rank);
+    if (r != ncclSuccess)
+        return fail(CGE_ERR_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+    auto* c = new cge_comm();
+    c->rank = rank;
+    c->n_ranks = nRanks;
+    c->device = device;
+    c->nccl = comm;
+    *out = c;
+    return CGE_OK;
+}
+
+int cge_comm_destroy(cge_comm* c)
+{
+    if (!c)
+        return CGE_OK;
+    const NcclApi* api = nccl_api();
+    if (api && c->nccl)
+        api->CommDestroy(static_cast<ncclComm_t>(c->nccl));
+    delete c;
+    return CGE_OK;
+}
+
+int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam, const cge_params* pIn, float* rgbOut,
+    int32_t* idsOut, cge_stats* st)
+{
+    if (!comm || !pIn)
+        return fail(CGE_ERR_INVALID_ARG, "null comm or params");
+    cge_params p = *pIn;
+    p.part_index = uint32_t(comm->rank);
+    p.part_count = uint32_t(comm->n_ranks);
+    int rc = validate_params(sc, &p);
+    if (rc)
+        return rc;
+    if (!cam || (comm->rank == 0 && !rgbOut))
+        return fail(CGE_ERR_INVALID_ARG, "null camera or output");
+    if (sc->device != comm->device)
+        return fail(CGE_ERR_INVALID_ARG, "scene and communicator live on different devices");
+    const NcclApi* api = nccl_api();
+    const bool wantIds = (p.flags & CGE_FLAG_WANT_PRIM_IDS) != 0;
+    const bool devOut = p.flags & CGE_FLAG_RGB_DEVICE_PTR;
+    CGE_CUDA(cudaSetDevice(sc->device));
+    const size_t pixels = size_t(p.width) * size_t(p.height);
+    const DevParams dp = make_dev_params(sc, p);
+    const unsigned R = unsigned(comm->n_ranks);
+    const unsigned myTiles = tiles_of(dp, unsigned(comm->rank), R);
+    // packed staging: this rank's tiles (send side); on rank 0 additionally room for every other rank's tiles
+    size_t othersPixels = 0;
+    std::vector<size_t> offs(R, 0);
+    if (comm->rank == 0)
+        for (unsigned r = 1; r < R; r++) {
+            offs[r] = othersPixels;
+            othersPixels += size_t(tiles_of(dp, r, R)) * 32;
+        }
+    const size_t gatherPixels = comm->rank == 0 ? othersPixels : size_t(myTiles) * 32;
+    Scratch* s = nullptr;
+    rc = acquire_scratch(sc, pixels, true, std::max<size_t>(gatherPixels, 1), &s);
+    if (rc) {
+        release_scratch(sc, s);
+        return rc;
+    }
+    ncclComm_t nc = static_cast<ncclComm_t>(comm->nccl);
+    uint32_t launches = 0;
+    cudaEventRecord(s->ev0, s->stream);
+    // every rank renders its interleaved tile subset straight into the full-frame layout of its own scratch frame
+    float* frame = (comm->rank == 0 && devOut) ? rgbOut : s->rgb;
+    int* frameIds = wantIds ? ((comm->rank == 0 && devOut && idsOut) ? idsOut : s->ids) : nullptr;
+    rc = launch_render(sc, s, cam, &p, dp, frame, frameIds, &launches);
+    cudaEventRecord(s->ev1, s->stream);
+    ncclResult_t nr = ncclSuccess;
+    if (rc == CGE_OK && R > 1) {
+        if (comm->rank != 0) {
+            if (myTiles) {
+                pack_tiles_kernel<<<(myTiles * 32 + 255) / 256, 256, 0, s->stream>>>(frame, frameIds, s->gatherRgb,
+                    wantIds ? s->gatherIds : nullptr, dp, myTiles);
+                launches++;
+                nr = api->GroupStart();
+                if (nr == ncclSuccess)
+                    nr = api->Send(s->gatherRgb, size_t(myTiles) * 32 * 3, ncclFloat, 0, nc, s->stream);
+                if (nr == ncclSuccess && wantIds)
+                    nr = api->Send(s->gatherIds, size_t(myTiles) * 32, ncclInt, 0, nc, s->stream);
+                if (nr == ncclSuccess)
+                    nr = api->GroupEnd();
+            }
+        } else {
+            nr = api->GroupStart();
+            for (unsigned r = 1; r < R && nr == ncclSuccess; r++) {
+                const unsigned t = tiles_of(dp, r, R);
+                if (!t)
+                    continue;
+                nr = api->Recv(s->gatherRgb + offs[r] * 3, size_t(t) * 32 * 3, ncclFloat, int(r), nc, s->stream);
+                if (nr == ncclSuccess && wantIds)
+                    nr = api->Recv(s->gatherIds + offs[r], size_t(t) * 32, ncclInt, int(r), nc, s->stream);
+            }
+            if (nr == ncclSuccess)
+                nr = api->GroupEnd();
+            for (unsigned r = 1; r < R && nr == ncclSuccess; r++) {
+                const unsigned t = tiles_of(dp, r, R);
+                if (!t)
+                    continue;
+                unpack_tiles_kernel<<<(t * 32 + 255) / 256, 256, 0, s->stream>>>(s->gatherRgb + offs[r] * 3,
+                    wantIds ? s->gatherIds + offs[r] : nullptr, frame, frameIds, dp, r, R, t);
+                launches++;
+            }
+        }
+    }
+    if (rc == CGE_OK && nr != ncclSuccess)
+        rc = fail(CGE_ERR_NCCL, std::string("nccl gather: ") + api->GetErrorString(nr));
+    if (rc == CGE_OK && comm->rank == 0 && !devOut) {
+        cudaMemcpyAsync(rgbOut, s->rgb, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+        if (wantIds && idsOut)
+            cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+    }
+    cudaEventRecord(s->ev2, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (rc == CGE_OK && e != cudaSuccess)
+        rc = fail(CGE_ERR_CUDA, std::string("render_distributed: ") + cudaGetErrorString(e));
+    if (rc == CGE_OK)
+        rc = fill_stats(s, st, launches);
+    release_scratch(sc, s);
+    return rc;
+}
+
+// pinned host buffers for callers that want the D2H copy at full PCIe speed
+int cge_host_alloc(void** out, uint64_t bytes)
+{
+    if (!out)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    CGE_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return CGE_OK;
+}
+int cge_host_free(void* p)
+{
+    if (p)
+        CGE_CUDA(cudaFreeHost(p));
+    return CGE_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,47 @@
+// nccl_min.h — the handful of NCCL entry points the framebuffer gather needs, resolved with dlopen at first use.
+// libcge.so therefore loads on machines without NCCL (CPU-only symbol checks) and, inside a torch process, binds to
+// the libnccl.so.2 torch already loaded (2.28.9 here; the system copy is 2.27.3 — the calls below are ABI-stable).
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace cge {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char* (*GetErrorString)(ncclResult_t);
+};
+
+inline const NcclApi* nccl_api()
+{
+    static NcclApi api {};
+    static bool tried = false, ok = false;
+    if (tried)
+        return ok ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+        h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+        return nullptr;
+    auto sym = [&](const char* n) { return dlsym(h, n); };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd
+        && api.GetErrorString;
+    return ok ? &api : nullptr;
+}
+
+} // namespace cge

@@ -1,0 +1,267 @@
+/*
+ * cge.h — C ABI of the B200-native ray-tracing hot path ("cge" = Computer-Graphics-Engine).
+ *
+ * This is the only boundary between host code and the CUDA implementation.  It replaces, for the
+ * reference engine (Anton-Kalpakchiev/Computer-Graphics-Engine), the body of
+ *
+ *     void renderRayTracing(const Scene&, const Trackball&, const BvhInterface&, Screen&, const Features&)
+ *                                                                        (reference src/render.h:32, src/render.cpp:273-329)
+ *
+ * and everything that call reaches: getFinalColor / recursiveRayTrace (src/render.cpp:27-155),
+ * BoundingVolumeHierarchy::intersect (src/bounding_volume_hierarchy.cpp:299-427), the prebuilt
+ * libIntersect functions (src/intersect.h:5-16), computeLightContribution / testVisibilityLightSample /
+ * sample*Light (src/light.cpp:19-164), computeShading / computeReflectionRay (src/shading.cpp:7-62),
+ * computeBarycentricCoord / interpolateNormal / interpolateTexCoord (src/interpolate.cpp:4-28),
+ * acquireTexel nearest (src/texture.cpp:15-27) and Trackball::generateRay (framework/src/trackball.cpp:101-110).
+ *
+ * Rules of the boundary: extern "C", POD only, plain pointers and sizes, int status codes, no exceptions,
+ * no STL / glm / torch types.  Host arrays passed to cge_scene_create are BORROWED for the duration of the
+ * call and copied to HBM; the library owns all device memory.  There is no CPU fallback: if no CUDA device
+ * is usable every entry point returns CGE_ERR_CUDA.
+ */
+#ifndef CGE_H_
+#define CGE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGE_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------------------ */
+enum {
+    CGE_OK = 0,
+    CGE_ERR_INVALID_ARG = 1,  /* null pointer, bad size, index out of range                                */
+    CGE_ERR_UNSUPPORTED = 2,  /* an ExtraFeatures flag (src/common.h:54-65) or a non-terminating material  */
+    CGE_ERR_CUDA = 3,         /* CUDA runtime error or no device; text in cge_last_error()                 */
+    CGE_ERR_NCCL = 4,         /* NCCL error in the multi-GPU gather                                        */
+    CGE_ERR_NOMEM = 5
+};
+
+/* ---- Features (reference src/common.h:67-77), one bit per bool, same order ---------------------------- */
+enum {
+    CGE_FEAT_SHADING = 1u << 0,         /* enableShading          */
+    CGE_FEAT_RECURSIVE = 1u << 1,       /* enableRecursive        */
+    CGE_FEAT_HARD_SHADOW = 1u << 2,     /* enableHardShadow       */
+    CGE_FEAT_SOFT_SHADOW = 1u << 3,     /* enableSoftShadow       */
+    CGE_FEAT_NORMAL_INTERP = 1u << 4,   /* enableNormalInterp     */
+    CGE_FEAT_TEXTURE_MAPPING = 1u << 5, /* enableTextureMapping   */
+    CGE_FEAT_ACCEL_STRUCTURE = 1u << 6, /* enableAccelStructure   */
+    /* ExtraFeatures (src/common.h:54-65) occupy bits 16..25 in declaration order; any of them set makes
+       cge_render return CGE_ERR_UNSUPPORTED instead of silently rendering something else. */
+    CGE_FEAT_EXTRA_MASK = 0x03ff0000u
+};
+
+/* ---- scene description (what Scene, src/scene.h:28-33, flattens to) ---------------------------------- */
+
+/* Same 32-byte layout as the reference Vertex (framework/include/framework/mesh.h:14-20). */
+typedef struct cge_vertex {
+    float position[3];
+    float normal[3];
+    float texcoord[2];
+} cge_vertex;
+
+/* One per Scene::meshes entry (mesh.h:36-43) with its Material (mesh.h:22-34). */
+typedef struct cge_mesh_desc {
+    uint32_t vertex_offset;   /* first vertex of this mesh in cge_scene_desc::vertices   */
+    uint32_t vertex_count;
+    uint32_t triangle_offset; /* first triangle of this mesh in cge_scene_desc::triangles */
+    uint32_t triangle_count;
+    float kd[3];
+    float ks[3];
+    float shininess;
+    float transparency;
+    int32_t texture_id; /* index into textures[], -1 when Material::kdTexture is empty */
+    uint32_t reserved[3];
+} cge_mesh_desc;
+
+/* Sphere (src/common.h:31-35). */
+typedef struct cge_sphere_desc {
+    float center[3];
+    float radius;
+    float kd[3];
+    float ks[3];
+    float shininess;
+    float transparency;
+    int32_t texture_id;
+    uint32_t reserved;
+} cge_sphere_desc;
+
+enum { CGE_LIGHT_POINT = 0, CGE_LIGHT_SEGMENT = 1, CGE_LIGHT_PARALLELOGRAM = 2 };
+
+/* Tagged union of PointLight / SegmentLight / ParallelogramLight (src/common.h:37-52); v[] holds the
+ * members in declaration order:  point: position,color (6) · segment: endpoint0,endpoint1,color0,color1 (12)
+ * · parallelogram: v0,edge01,edge02,color0,color1,color2,color3 (21). */
+typedef struct cge_light_desc {
+    uint32_t type;
+    float v[21];
+} cge_light_desc;
+
+/* Image (framework/include/framework/image.h:13-20): float RGB texels in [0,1], row-major, row 0 first. */
+typedef struct cge_texture_desc {
+    int32_t width;
+    int32_t height;
+    uint64_t texel_offset; /* in texels (3 floats each) into cge_scene_desc::texels */
+} cge_texture_desc;
+
+/* Optional caller-supplied BVH in the reference's own node order (src/bounding_volume_hierarchy.h:31-41):
+ * when bvh_nodes == NULL the library rebuilds the identical tree itself (median split, std::nth_element on
+ * centroid axis depth%3, MAX_DEPTH 16 — src/bounding_volume_hierarchy.cpp:74-78,130-147). */
+typedef struct cge_bvh_node {
+    float lower[3];
+    float upper[3];
+    uint32_t is_leaf;
+    uint32_t depth;
+    uint32_t beg, end;    /* primitive range in bvh_prim_order */
+    uint32_t left, right; /* child node indices (inner nodes only) */
+} cge_bvh_node;
+
+typedef struct cge_scene_desc {
+    uint32_t n_meshes, n_vertices, n_triangles, n_spheres, n_lights, n_textures;
+    uint64_t n_texels;
+    const cge_mesh_desc* meshes;
+    const cge_vertex* vertices;
+    const uint32_t* triangles; /* 3 mesh-local vertex indices per triangle (Mesh::triangles) */
+    const cge_sphere_desc* spheres;
+    const cge_light_desc* lights;
+    const cge_texture_desc* textures;
+    const float* texels;
+    /* optional reference-built BVH; primitive ids are "global primitive ids": triangles of mesh 0, mesh 1, …
+       in Mesh::triangles order, then spheres (src/bounding_volume_hierarchy.cpp:158-172). */
+    uint32_t n_bvh_nodes;
+    uint32_t bvh_root;
+    const cge_bvh_node* bvh_nodes;
+    const uint32_t* bvh_prim_order; /* n_triangles + n_spheres global primitive ids in leaf order */
+} cge_scene_desc;
+
+/* ---- camera: the ray-independent part of Trackball::generateRay (framework/src/trackball.cpp:101-110) -- */
+typedef struct cge_camera {
+    float origin[3]; /* Trackball::position()                                  (trackball.cpp:71-74) */
+    float quat[4];   /* glm::quat(m_rotationEulerAngles) as w,x,y,z            (type_quat.inl:208-217) */
+    float half_width;  /* m_halfScreenSpaceWidth  = aspect * tan(fovy/2)       (trackball.cpp:26-27) */
+    float half_height; /* m_halfScreenSpaceHeight = tan(fovy/2) */
+} cge_camera;
+
+/* Convenience: fill a cge_camera exactly as the reference Trackball would (same float op order).
+ * fovy and rotation in radians; aspect = float(W)/float(H) (framework/src/window.cpp:379-384). */
+int cge_camera_from_trackball(float fovy, float aspect, const float look_at[3], float dist,
+                              const float rotation_euler[3], cge_camera* out);
+
+/* ---- render parameters: every global the reference reads on this path becomes a field ------------------ */
+enum {
+    CGE_TRAVERSAL_REFERENCE = 0, /* exhaustive DFS, right child first, no t culling: visit order and tie
+                                    rule of src/bounding_volume_hierarchy.cpp:312-361 reproduced literally */
+    CGE_TRAVERSAL_FAST = 1       /* same tree, near-child-first with conservative t culling, shadow rays
+                                    stop at the first blocker; winner chosen by the reference's tie rank */
+};
+enum {
+    CGE_SAMPLER_HASH = 0 /* rand() replaced by hash(seed, pixel, draw index) — see DESIGN.md "sampler" */
+};
+enum {
+    CGE_FLAG_WANT_PRIM_IDS = 1u << 0,
+    CGE_FLAG_RGB_DEVICE_PTR = 1u << 1 /* rgb_out / prim_id_out are device pointers on the calling GPU:
+                                         no D2H copy (kernel-only timing, or a caller that keeps the frame in HBM) */
+};
+
+typedef struct cge_params {
+    int32_t width, height;      /* Screen::resolution()                       (src/screen.h:18)        */
+    uint32_t features;          /* CGE_FEAT_* bits                                                       */
+    int32_t ray_depth;          /* rayDepth of getFinalColor; the reference passes the literal 5
+                                   (src/render.cpp:298,308,318)                                          */
+    int32_t segment_samples;    /* segmentLightSamples               = 25    (src/light.cpp:12)         */
+    int32_t parallelogram_samples; /* parallelogramLightDirectionSamples = 5 (src/light.cpp:13)         */
+    uint32_t sampler;           /* CGE_SAMPLER_*                                                          */
+    uint32_t seed;
+    uint32_t traversal;         /* CGE_TRAVERSAL_*                                                        */
+    uint32_t flags;             /* CGE_FLAG_*                                                             */
+    /* image partition for multi-GPU: this call renders only tiles t with t % part_count == part_index
+       (tiles are 8x4 pixels, numbered row-major).  part_count <= 1 renders the whole frame. */
+    uint32_t part_index, part_count;
+    uint32_t reserved[4];
+} cge_params;
+
+typedef struct cge_stats {
+    uint64_t primary_rays;    /* camera rays traced                                   */
+    uint64_t bounce_rays;     /* unique reflection rays traced on the GPU             */
+    uint64_t shadow_rays;     /* unique shadow rays traced on the GPU                 */
+    uint64_t reference_rays;  /* BvhInterface::intersect calls the reference would have made for this frame
+                                 (duplicate reflection subtrees counted, src/render.cpp:100,118) */
+    uint64_t box_tests, tri_tests; /* only filled when the library is built with CGE_COUNT_TESTS */
+    float kernel_ms;          /* device time of the render kernels (CUDA events on the call's stream) */
+    float total_ms;           /* device time including uploads of camera/params and the D2H copy     */
+    uint32_t kernel_launches; /* kernels launched by this call                                        */
+    uint32_t reserved[3];
+} cge_stats;
+
+typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene + BVH on ONE GPU */
+
+/* ---- entry points ------------------------------------------------------------------------------------- */
+
+int cge_abi_version(void);
+const char* cge_last_error(void); /* thread-local message of the last failing call on this thread */
+
+/* Number of usable CUDA devices (0 => every other call fails with CGE_ERR_CUDA). */
+int cge_device_count(void);
+
+/* Flatten + upload.  device = CUDA ordinal.  Builds the reference-order BVH unless desc->bvh_nodes is given. */
+int cge_scene_create(const cge_scene_desc* desc, int device, cge_scene** out);
+/* GUI edits lights every frame (reference src/main.cpp:290-368): replace the light list only. */
+int cge_scene_update_lights(cge_scene* scene, const cge_light_desc* lights, uint32_t n_lights);
+int cge_scene_destroy(cge_scene* scene);
+
+/* Introspection used by BvhInterface::numLevels / numLeaves (src/bvh_interface.h:20,24) and by the tests. */
+int cge_scene_bvh_info(const cge_scene* scene, uint32_t* n_nodes, uint32_t* n_levels, uint32_t* n_leaves,
+                       uint32_t* max_leaf_prims);
+/* Copy out the BVH the library built (for parity tests against the reference's tree). Either pointer may be NULL. */
+int cge_scene_bvh_export(const cge_scene* scene, cge_bvh_node* nodes_out, uint32_t* prim_order_out);
+
+/* Render one frame (or this rank's tile subset).  rgb_out: width*height*3 floats in Screen::pixels() order —
+ * row 0 = TOP of the image, index (H-1-y)*W + x (src/screen.cpp:41-47).  prim_id_out (optional, needs
+ * CGE_FLAG_WANT_PRIM_IDS): width*height int32 global primitive id of the primary hit, -1 on miss, same pixel order.
+ * Pixels outside this call's partition are left untouched.  Thread-safe on one cge_scene: every call uses its own
+ * stream and scratch (reference src/main.cpp:514-528 renders several cameras concurrently). */
+int cge_render(cge_scene* scene, const cge_camera* camera, const cge_params* params, float* rgb_out,
+               int32_t* prim_id_out, cge_stats* stats_out);
+
+/* Single-ray entry mirroring getFinalColor(scene,bvh,ray,features,depth) (src/render.h:35) for the debug-ray
+ * callers (src/main.cpp:398,401): n rays in (origin[3],direction[3],t) records, n RGB out.  pixel ids for the
+ * sampler are 0..n-1. */
+int cge_trace_rays(cge_scene* scene, const float* rays7, uint32_t n, const cge_params* params, float* rgb_out,
+                   int32_t* prim_id_out);
+
+/* ---- device-function KATs: the six libIntersect functions (src/intersect.h:5-16) evaluated ON THE GPU ---- */
+/* in/out arrays are host pointers; n cases each.  ray7 = origin[3], direction[3], t (t updated in place).  */
+int cge_kat_triangle(const float* v0v1v2 /*9n*/, float* ray7 /*7n*/, int32_t* hit_out, uint32_t n, int device);
+/* the same triangle test evaluated through the precomputed plane/edge rows the traversal kernel reads (not a
+ * reference function: proves that hoisting the ray-independent part of I4 is bit-exact) */
+int cge_kat_triangle_precomputed(const float* v0v1v2 /*9n*/, float* ray7 /*7n*/, int32_t* hit_out, uint32_t n, int device);
+int cge_kat_aabb(const float* lower_upper /*6n*/, float* ray7, int32_t* hit_out, uint32_t n, int device);
+int cge_kat_sphere(const float* center_radius /*4n*/, float* ray7, float* normal_out /*3n*/, int32_t* hit_out,
+                   uint32_t n, int device);
+int cge_kat_plane(const float* D_normal /*4n*/, float* ray7, int32_t* hit_out, uint32_t n, int device);
+int cge_kat_triangle_plane(const float* v0v1v2 /*9n*/, float* D_normal_out /*4n*/, uint32_t n, int device);
+int cge_kat_point_in_triangle(const float* v0v1v2 /*9n*/, const float* normal /*3n*/, const float* p /*3n*/,
+                              int32_t* inside_out, uint32_t n, int device);
+
+/* ---- multi-GPU: one process per GPU; the framebuffer tiles are gathered to rank 0 over NCCL -------------- */
+typedef struct cge_comm cge_comm; /* opaque NCCL communicator wrapper */
+#define CGE_UNIQUE_ID_BYTES 128
+int cge_comm_unique_id(uint8_t id_out[CGE_UNIQUE_ID_BYTES]); /* rank 0 calls, broadcasts by any host means */
+int cge_comm_create(const uint8_t id[CGE_UNIQUE_ID_BYTES], int rank, int n_ranks, int device, cge_comm** out);
+int cge_comm_destroy(cge_comm* comm);
+/* Render this rank's interleaved tile subset (part_index/part_count are overwritten with rank/n_ranks), pack
+ * the rendered tiles contiguously, ncclSend them to rank 0, which unpacks all ranks' tiles into the full frame
+ * and (unless CGE_FLAG_RGB_DEVICE_PTR) copies it to rgb_out.  rgb_out / prim_id_out are only written on rank 0. */
+int cge_render_distributed(cge_scene* scene, cge_comm* comm, const cge_camera* camera, const cge_params* params,
+                           float* rgb_out, int32_t* prim_id_out, cge_stats* stats_out);
+
+/* pinned host memory for rgb_out / prim_id_out so the D2H copy runs at full PCIe speed (optional) */
+int cge_host_alloc(void** out, uint64_t bytes);
+int cge_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGE_H_ */

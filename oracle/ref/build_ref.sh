@@ -1,0 +1,67 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY.  Builds the UNMODIFIED reference renderer (sources compiled where they lie under
+# /root/reference, linked with its prebuilt libIntersect archive) into oracle/_ref/:
+#     libcge_ref.so        with ld --wrap counters + primary-id capture   (parity checks)
+#     libcge_ref_plain.so  no intersect interposers, only rand is wrapped  (CPU baseline timing)
+# No reference file is copied into the repo; the reference's CMake build is not used (it needs OpenGL).
+# Flags follow the reference's Release configuration: -O2 -DNDEBUG -fopenmp, NO -march / -ffast-math
+# (FMA contraction changes hit/miss decisions).
+set -euo pipefail
+R=${CGE_REFERENCE_DIR:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+REPO=$(cd "$HERE/../.." && pwd)
+OUT=$REPO/oracle/_ref
+OBJ=$OUT/obj
+if [ ! -d "$R/src" ]; then
+    echo "build_ref.sh: $R not present - keeping prebuilt oracle/_ref as is" >&2
+    exit 0
+fi
+mkdir -p "$OBJ"
+TP=$R/framework/third_party
+INC="-I$HERE/shim -I$R/src -I$R/framework/include -I$R/framework/include/framework -I$TP/glm -I$TP/fmt/include
+     -I$TP/glad/include -I$TP/glfw3/include -I$TP/stb/include -I$TP/tinyobjloader/include -I$TP/toml/include
+     -I$REPO/include"
+CXXFLAGS="-std=c++20 -O2 -DNDEBUG -fopenmp -fPIC -ffp-contract=off -w -DDATA_DIR=\"$R/data/\""
+
+compile() { # src obj extra...
+    local src=$1 obj=$2
+    shift 2
+    if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ]; then
+        g++ $CXXFLAGS $INC "$@" -c "$src" -o "$obj"
+    fi
+}
+pids=()
+for f in render light shading interpolate texture bounding_volume_hierarchy bvh_interface scene screen; do
+    compile "$R/src/$f.cpp" "$OBJ/$f.o" &
+    pids+=($!)
+done
+for f in mesh image trackball; do
+    compile "$R/framework/src/$f.cpp" "$OBJ/fw_$f.o" &
+    pids+=($!)
+done
+compile "$TP/fmt/src/format.cc" "$OBJ/fmt_format.o" &
+pids+=($!)
+compile "$TP/tinyobjloader/src/tiny_obj_loader.cc" "$OBJ/tiny_obj_loader.o" "-I$TP/tinyobjloader/include/tinyobjloader" &
+pids+=($!)
+( [ -f "$OBJ/glad.o" ] || gcc -O2 -fPIC -w $INC -c "$TP/glad/src/glad.c" -o "$OBJ/glad.o" ) &
+pids+=($!)
+g++ $CXXFLAGS $INC -c "$HERE/stubs.cpp" -o "$OBJ/stubs.o" &
+pids+=($!)
+g++ $CXXFLAGS $INC -c "$HERE/ref_api.cpp" -o "$OBJ/ref_api.o" &
+pids+=($!)
+g++ $CXXFLAGS $INC -DCGE_REF_NO_COUNTERS -c "$HERE/ref_api.cpp" -o "$OBJ/ref_api_plain.o" &
+pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+
+COMMON="$OBJ/render.o $OBJ/light.o $OBJ/shading.o $OBJ/interpolate.o $OBJ/texture.o $OBJ/bounding_volume_hierarchy.o
+        $OBJ/bvh_interface.o $OBJ/scene.o $OBJ/screen.o $OBJ/fw_mesh.o $OBJ/fw_image.o $OBJ/fw_trackball.o
+        $OBJ/fmt_format.o $OBJ/tiny_obj_loader.o $OBJ/glad.o $OBJ/stubs.o"
+WRAPS="-Wl,--wrap=_Z24intersectRayWithTriangleRKN3glm3vecILi3EfLNS_9qualifierE0EEES4_S4_R3RayR7HitInfo
+       -Wl,--wrap=_Z21intersectRayWithShapeRK14AxisAlignedBoxR3Ray
+       -Wl,--wrap=_Z21intersectRayWithShapeRK6SphereR3RayR7HitInfo
+       -Wl,--wrap=_ZNK12BvhInterface9intersectER3RayR7HitInfoRK8Features"
+g++ -shared -fopenmp -o "$OUT/libcge_ref.so" $OBJ/ref_api.o $COMMON "$R/prebuilt/libIntersect_linux_x64.a" \
+    $WRAPS -Wl,--wrap=rand -Wl,-Bsymbolic -ldl
+g++ -shared -fopenmp -o "$OUT/libcge_ref_plain.so" $OBJ/ref_api_plain.o $COMMON "$R/prebuilt/libIntersect_linux_x64.a" \
+    -Wl,--wrap=rand -Wl,-Bsymbolic -ldl
+echo "built $OUT/libcge_ref.so $OUT/libcge_ref_plain.so"

@@ -1,0 +1,201 @@
+"""-m gpu: image / primitive-id parity of the CUDA path (through the C ABI) against the reference renderer.
+
+ * committed goldens (tests/golden/*.npz, produced by the unmodified reference in the build container),
+ * live renders by oracle/_ref at reduced sizes (same configs, same camera constants),
+ * full-size, size-independent properties: REFERENCE-order traversal == FAST traversal, an image rendered in
+   N interleaved partitions == the image rendered whole, determinism.
+Bars (BASELINE.json north_star): primary-hit ids bit-exact except <= 0.01 % edge ties; linear RGB within 1e-3
+max-abs; NaN pixels in the same places.
+"""
+import numpy as np
+import pytest
+
+from conftest import compare_images
+
+pytestmark = pytest.mark.gpu
+
+SMALL = {
+    "c1_cornell": (160, 160),
+    "c2_cube_textured": (160, 90),
+    "c3_teapot_soft": (128, 72),
+    "c4_monkey_mirror": (128, 72),
+    "c5_dragon": (96, 54),
+}
+RGB_TOL = 1e-3
+ID_MISMATCH_BUDGET = 1e-4
+
+
+def flat_for(cge, cfg, small_standin=True):
+    if cfg["scene"].startswith("standin:"):
+        return cge.standin.make("dragon", n=40) if small_standin else cge.standin.make("dragon")
+    return cge.load_scene(cfg)
+
+
+def assert_parity(name, rgb, ids, ref_rgb, ref_ids, id_budget=ID_MISMATCH_BUDGET):
+    err, nan_mm = compare_images(rgb, ref_rgb)
+    id_mm = int((ids != ref_ids).sum())
+    npx = ids.size
+    assert id_mm <= max(int(id_budget * npx), 0), f"{name}: {id_mm}/{npx} primary ids differ"
+    assert nan_mm == 0, f"{name}: {nan_mm} pixels differ in NaN-ness"
+    # relative tolerance for the (few) pixels whose value exceeds 1: 1e-3 max-abs is stated for [0,1] radiance
+    scale = np.maximum(1.0, np.nan_to_num(np.abs(ref_rgb), nan=0.0, posinf=0.0).max())
+    assert err <= RGB_TOL * scale, f"{name}: max abs err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+@pytest.mark.parametrize("traversal", [0, 1])
+def test_golden_images(cge, name, traversal):
+    w, h = SMALL[name]
+    cfg = cge.configs.get(name, w, h)
+    g = np.load(cge.configs.SCENE_DIR.parent / f"{name}_{w}x{h}.npz")
+    with cge.Scene(flat_for(cge, cfg)) as sc:
+        info = sc.bvh_info()
+        assert (info["nodes"], info["levels"], info["leaves"]) == (int(g["bvh_nodes"]), int(g["bvh_levels"]), int(g["bvh_leaves"]))
+        rgb, ids, st = sc.render(cfg, traversal=traversal)
+    assert_parity(name, rgb, ids, g["rgb"], g["ids"])
+    # the reference would have made exactly this many BvhInterface::intersect calls (ld --wrap counter)
+    assert st["reference_rays"] == int(g["rays"]), (st["reference_rays"], int(g["rays"]))
+
+
+@pytest.mark.parametrize("name,size", [("c1_cornell", (256, 256)), ("c2_cube_textured", (320, 180)),
+                                       ("c3_teapot_soft", (192, 108)), ("c4_monkey_mirror", (160, 90))])
+def test_live_reference(cge, ref, name, size, tmp_path):
+    cfg = cge.configs.get(name, *size)
+    cfg["seed"] = 99
+    path = cge.configs.scene_path(cfg)
+    with ref.RefScene(path, cfg["features"]) as rs:
+        ref_rgb, ref_ids, rst = rs.render(cfg)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        for traversal in (0, 1):
+            rgb, ids, st = sc.render(cfg, traversal=traversal)
+            assert_parity(f"{name}/t{traversal}", rgb, ids, ref_rgb, ref_ids)
+            assert st["reference_rays"] == rst["rays"]
+
+
+def test_mixed_scene_all_light_kinds_spheres_and_flags(cge, ref):
+    """triangles + spheres, point + segment + parallelogram lights, every Features combination that matters."""
+    C = cge.configs
+    path = C.SCENE_DIR / "mixed.cges"
+    flat = cge.scenefile.load(path)
+    base = {"scene": "mixed.cges", "width": 96, "height": 64, "ray_depth": 2, "segment_samples": 5,
+            "parallelogram_samples": 3, "seed": 5,
+            "camera": {"fov_deg": 60.0, "dist": 4.0, "look_at": [0.0, 0.3, 0.0], "rotation_deg": [15.0, 35.0, 0.0]}}
+    combos = [
+        C.FEAT_ACCEL_STRUCTURE,
+        C.FEAT_SHADING,
+        C.FEAT_SHADING | C.FEAT_ACCEL_STRUCTURE | C.FEAT_HARD_SHADOW,
+        C.FEAT_SHADING | C.FEAT_ACCEL_STRUCTURE | C.FEAT_SOFT_SHADOW,
+        C.FEAT_SHADING | C.FEAT_ACCEL_STRUCTURE | C.FEAT_SOFT_SHADOW | C.FEAT_HARD_SHADOW | C.FEAT_RECURSIVE,
+        C.FEAT_SHADING | C.FEAT_SOFT_SHADOW | C.FEAT_RECURSIVE | C.FEAT_NORMAL_INTERP,
+        C.FEAT_SHADING | C.FEAT_ACCEL_STRUCTURE | C.FEAT_NORMAL_INTERP | C.FEAT_TEXTURE_MAPPING | C.FEAT_RECURSIVE,
+    ]
+    with cge.Scene(flat) as sc:
+        for feats in combos:
+            cfg = dict(base, features=feats)
+            with ref.RefScene(path, feats) as rs:
+                ref_rgb, ref_ids, rst = rs.render(cfg)
+            for traversal in (0, 1):
+                rgb, ids, st = sc.render(cfg, traversal=traversal)
+                assert_parity(f"mixed/f{feats:#x}/t{traversal}", rgb, ids, ref_rgb, ref_ids, id_budget=2e-3)
+                assert st["reference_rays"] == rst["rays"]
+
+
+def test_bvh_matches_reference_tree(cge):
+    g = np.load(cge.configs.SCENE_DIR.parent / "reference_bvh.npz")
+    for f in sorted(cge.configs.SCENE_DIR.glob("*.cges")):
+        flat = cge.scenefile.load(f)
+        with cge.Scene(flat) as sc:
+            nodes, order = sc.bvh_export()
+        assert np.array_equal(order, g[f.stem + "_order"]), f.stem
+        assert nodes.tobytes() == g[f.stem + "_nodes"].tobytes(), f.stem
+
+
+def test_trace_rays_matches_reference_getFinalColor(cge, ref):
+    cfg = cge.configs.get("c4_monkey_mirror", 64, 36)
+    rng = np.random.default_rng(3)
+    n = 4000
+    o = rng.uniform(-0.3, 0.3, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d = (d / np.sqrt((d * d).sum(1, keepdims=True))).astype(np.float32)
+    rays = np.concatenate([o, d, np.full((n, 1), np.float32(3.4028234663852886e38))], 1).astype(np.float32)
+    with ref.RefScene(cge.configs.scene_path(cfg), cfg["features"]) as rs:
+        ref_rgb, ref_ids = rs.trace_rays(rays, cfg)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        rgb, ids = sc.trace_rays(rays, cfg, traversal=1)
+    assert (ids != ref_ids).sum() <= 1
+    err, nan_mm = compare_images(rgb, ref_rgb)
+    assert nan_mm == 0 and err <= 1e-3 * max(1.0, float(np.nan_to_num(ref_rgb, nan=0).max()))
+
+
+@pytest.mark.parametrize("name", ["c1_cornell", "c2_cube_textured", "c3_teapot_soft", "c4_monkey_mirror"])
+def test_full_size_properties(cge, name):
+    """At BASELINE.json's full resolution: FAST traversal == REFERENCE-order traversal (ids within the tie budget,
+    RGB within tolerance) and a 3-way interleaved partition reassembles to the same image bit for bit."""
+    cfg = cge.configs.get(name)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        rgb_f, ids_f, st_f = sc.render(cfg, traversal=1)
+        rgb_r, ids_r, st_r = sc.render(cfg, traversal=0)
+        assert st_f["reference_rays"] == st_r["reference_rays"]
+        assert (ids_f != ids_r).mean() <= ID_MISMATCH_BUDGET
+        err, nan_mm = compare_images(rgb_f, rgb_r)
+        assert nan_mm <= ID_MISMATCH_BUDGET * ids_f.size
+        rgb_p = np.zeros_like(rgb_f)
+        ids_p = np.full_like(ids_f, -7)
+        for k in range(3):
+            sc.render(cfg, traversal=1, rgb_out=rgb_p, ids_out=ids_p, part=(k, 3))
+        assert np.array_equal(ids_p, ids_f)
+        assert rgb_p.tobytes() == rgb_f.tobytes()
+        rgb_2, _, _ = sc.render(cfg, traversal=1)
+        assert rgb_2.tobytes() == rgb_f.tobytes()  # deterministic
+
+
+def test_dragon_standin_full_scene_reduced_frame(cge, ref, tmp_path):
+    """The full 868 334-triangle stand-in (config C5) on a reduced frame against the live reference."""
+    cfg = cge.configs.get("c5_dragon", 160, 90)
+    flat = cge.standin.make("dragon")
+    path = tmp_path / "dragon.cges"
+    cge.scenefile.save(flat, path)
+    with ref.RefScene(path, cfg["features"]) as rs:
+        ref_rgb, ref_ids, rst = rs.render(cfg)
+        info = rs.bvh_info()
+    with cge.Scene(flat) as sc:
+        mine = sc.bvh_info()
+        assert (mine["nodes"], mine["levels"], mine["leaves"]) == (info["nodes"], info["levels"], info["leaves"])
+        for traversal in (0, 1):
+            rgb, ids, st = sc.render(cfg, traversal=traversal)
+            assert_parity(f"dragon/t{traversal}", rgb, ids, ref_rgb, ref_ids)
+            assert st["reference_rays"] == rst["rays"]
+
+
+def test_edge_cases(cge):
+    C = cge.configs
+    cfg = C.get("c1_cornell", 33, 17)  # ragged: not a multiple of the 8x4 tile
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        rgb, ids, st = sc.render(cfg)
+        assert st["primary_rays"] == 33 * 17
+        # ExtraFeatures must be refused, not silently ignored
+        bad = dict(cfg, features=cfg["features"] | (1 << 19))
+        with pytest.raises(cge.CgeError) as e:
+            sc.render(bad)
+        assert e.value.code == cge.ERR_UNSUPPORTED
+        with pytest.raises(cge.CgeError):
+            sc.render(dict(cfg, ray_depth=99))
+        # light update: no lights -> black (shading on), then restore
+        lights = sc.flat.lights.copy()
+        sc.update_lights(lights[:0])
+        rgb0, _, _ = sc.render(cfg)
+        assert np.nan_to_num(rgb0, nan=0.0).max() == 0.0
+        sc.update_lights(lights)
+        rgb1, _, _ = sc.render(cfg)
+        assert rgb1.tobytes() == rgb.tobytes()
+    # empty scene: every ray misses
+    empty = cge.scenefile.FlatScene()
+    with cge.Scene(empty) as sc:
+        rgb, ids, st = sc.render(C.get("c1_cornell", 16, 8))
+        assert (ids == -1).all() and (rgb == 0).all()
+    # a transparent material with recursion has no terminating reference result
+    cube = cge.scenefile.load(C.SCENE_DIR / "cube.cges")
+    with cge.Scene(cube) as sc:
+        with pytest.raises(cge.CgeError) as e:
+            sc.render(C.get("c1_cornell", 16, 8))
+        assert e.value.code == cge.ERR_UNSUPPORTED
