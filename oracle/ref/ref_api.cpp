@@ -670,6 +670,8 @@ struct ref_render_params {
     float rotation[3]; // radians
     // restrict to a pixel window [x0,x1) x [y0,y1) in reference coordinates (y up); all-zero = full frame.
     int32_t x0, y0, x1, y1;
+    // bounded sample for timing: render only rows y with (y - y0) % y_stride == 0 (0/1 = every row).
+    int32_t y_stride;
 };
 struct ref_render_stats {
     uint64_t rays, box_tests, tri_tests, sphere_tests;
@@ -706,6 +708,8 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
         y1 = H;
     }
 
+    const int ystride = p->y_stride > 1 ? p->y_stride : 1;
+    const int nRows = (y1 - y0 + ystride - 1) / ystride;
     const auto t0 = std::chrono::high_resolution_clock::now();
     if (p->use_render_ray_tracing) {
         renderRayTracing(rs->scene, camera, bvh, screen, features);
@@ -715,7 +719,8 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
         {
             tls = Tls {};
 #pragma omp for schedule(guided)
-            for (int y = y0; y < y1; y++) {
+            for (int row = 0; row < nRows; row++) {
+                const int y = y0 + row * ystride;
                 for (int x = x0; x != x1; x++) {
                     const glm::vec2 normalizedPixelPos {
                         float(x) / float(W) * 2.0f - 1.0f,
@@ -749,7 +754,8 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
         return 3;
 #else
 #pragma omp parallel for schedule(guided)
-        for (int y = y0; y < y1; y++) {
+        for (int row = 0; row < nRows; row++) {
+            const int y = y0 + row * ystride;
             for (int x = x0; x != x1; x++) {
                 const glm::vec2 ndc { float(x) / float(W) * 2.0f - 1.0f, float(y) / float(H) * 2.0f - 1.0f };
                 Ray ray = camera.generateRay(ndc);

@@ -22,6 +22,7 @@ class RefRenderParams(C.Structure):
         ("seed", C.c_uint32), ("threads", C.c_int32), ("use_render_ray_tracing", C.c_int32),
         ("want_ids", C.c_int32), ("fovy", C.c_float), ("look_at", C.c_float * 3), ("dist", C.c_float),
         ("rotation", C.c_float * 3), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+        ("y_stride", C.c_int32),
     ]
 
 
@@ -120,7 +121,7 @@ class RefScene:
             raise RuntimeError("ref_scene_write_with_bvh failed")
 
     def make_params(self, cfg: dict, threads: int = 0, want_ids: bool = True, window=None,
-                    use_render_ray_tracing: bool = False) -> RefRenderParams:
+                    use_render_ray_tracing: bool = False, y_stride: int = 1) -> RefRenderParams:
         p = RefRenderParams()
         p.width, p.height = cfg["width"], cfg["height"]
         p.features = cfg["features"]
@@ -139,11 +140,12 @@ class RefScene:
         p.rotation = (C.c_float * 3)(*[np.float32(np.radians(np.float32(r))) for r in cam["rotation_deg"]])
         if window:
             p.x0, p.y0, p.x1, p.y1 = window
+        p.y_stride = y_stride
         return p
 
     def render(self, cfg: dict, threads: int = 0, want_ids: bool = True, window=None,
-               use_render_ray_tracing: bool = False):
-        p = self.make_params(cfg, threads, want_ids, window, use_render_ray_tracing)
+               use_render_ray_tracing: bool = False, y_stride: int = 1):
+        p = self.make_params(cfg, threads, want_ids, window, use_render_ray_tracing, y_stride)
         W, H = p.width, p.height
         rgb = np.zeros((H, W, 3), np.float32)
         ids = np.full((H, W), -1, np.int32)
