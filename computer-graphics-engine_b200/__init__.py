@@ -21,7 +21,7 @@ LIB_PATH = _PKG / "libcge.so"
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
-FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR = 1, 2
+FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_NO_COOPERATIVE = 1, 2, 4, 8
 UNIQUE_ID_BYTES = 128
 
 
@@ -144,7 +144,8 @@ def camera_from_cfg(cfg: dict) -> CgeCamera:
     return out
 
 
-def params_from_cfg(cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool = True, part=(0, 1)) -> CgeParams:
+def params_from_cfg(cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool = True, part=(0, 1),
+                    flags: int = 0) -> CgeParams:
     p = CgeParams()
     p.width, p.height = cfg["width"], cfg["height"]
     p.features = cfg["features"]
@@ -154,7 +155,7 @@ def params_from_cfg(cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool =
     p.sampler = 0
     p.seed = cfg.get("seed", 0)
     p.traversal = traversal
-    p.flags = FLAG_WANT_PRIM_IDS if want_ids else 0
+    p.flags = (FLAG_WANT_PRIM_IDS if want_ids else 0) | flags
     p.part_index, p.part_count = part
     return p
 
@@ -233,10 +234,10 @@ class Scene:
         _check(lib().cge_scene_update_lights(self.handle, _p(lights) if len(lights) else None, len(lights)))
 
     def render(self, cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool = True, rgb_out=None, ids_out=None,
-               part=(0, 1), camera: CgeCamera | None = None):
+               part=(0, 1), camera: CgeCamera | None = None, flags: int = 0):
         """cge_render into host arrays.  Returns (rgb[H,W,3], ids[H,W] or None, stats dict)."""
         cam = camera or camera_from_cfg(cfg)
-        p = params_from_cfg(cfg, traversal, want_ids, part)
+        p = params_from_cfg(cfg, traversal, want_ids, part, flags)
         H, W = cfg["height"], cfg["width"]
         rgb = rgb_out if rgb_out is not None else np.zeros((H, W, 3), np.float32)
         ids = (ids_out if ids_out is not None else np.full((H, W), -1, np.int32)) if want_ids else None
@@ -245,10 +246,10 @@ class Scene:
         return rgb, ids, st.as_dict()
 
     def render_device(self, cfg: dict, rgb_ptr: int, ids_ptr: int = 0, traversal: int = TRAVERSAL_FAST,
-                      camera: CgeCamera | None = None, part=(0, 1)) -> dict:
+                      camera: CgeCamera | None = None, part=(0, 1), flags: int = 0) -> dict:
         """cge_render writing to DEVICE pointers (no D2H): the kernel-only / HBM-resident measurement."""
         cam = camera or camera_from_cfg(cfg)
-        p = params_from_cfg(cfg, traversal, bool(ids_ptr), part)
+        p = params_from_cfg(cfg, traversal, bool(ids_ptr), part, flags)
         p.flags |= FLAG_RGB_DEVICE_PTR
         st = CgeStats()
         _check(lib().cge_render(self.handle, C.byref(cam), C.byref(p), C.c_void_p(rgb_ptr),

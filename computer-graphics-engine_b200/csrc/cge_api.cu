@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "bvh_build.h"
+#include "bvh_sah.h"
 #include "cge.h"
 #include "dev_scene.h"
 #include "nccl_min.h"
@@ -83,7 +84,8 @@ struct cge_scene {
     int device = 0;
     int sm_count = 0;
     DevScene dev {};
-    DevBuf<float4> nodes, tris, shade, materials;
+    DevBuf<float4> nodes, tris, fnodes, ftris, shade, materials;
+    FastBvh fast;
     DevBuf<int4> textures;
     DevBuf<float> texels, lights;
     HostBvh bvh;
@@ -113,15 +115,18 @@ inline float bitsf(uint32_t u)
     return f;
 }
 
-void light_counts(const std::vector<cge_light_desc>& lights, const cge_params& p, uint32_t& draws, uint32_t& shadows)
+void host_light_counts(const std::vector<cge_light_desc>& lights, const cge_params& p, uint32_t& draws, uint32_t& shadows,
+    uint32_t& samples)
 {
     draws = 0;
     shadows = 0;
+    samples = 0;
     if (!(p.features & CGE_FEAT_SHADING))
         return;
     const bool hard = p.features & CGE_FEAT_HARD_SHADOW, soft = p.features & CGE_FEAT_SOFT_SHADOW;
     for (const auto& l : lights) {
         if (l.type == CGE_LIGHT_POINT) {
+            samples += 1;
             if (hard)
                 shadows += 1;
         } else if (l.type == CGE_LIGHT_SEGMENT) {
@@ -129,11 +134,13 @@ void light_counts(const std::vector<cge_light_desc>& lights, const cge_params& p
                 const uint32_t n = uint32_t(std::max(p.segment_samples, 0));
                 draws += n;
                 shadows += n;
+                samples += n;
             }
         } else if (soft) {
             const uint32_t n = uint32_t(std::max(p.parallelogram_samples, 0));
             draws += 2 * n * n;
             shadows += n * n;
+            samples += n * n;
         }
     }
 }
@@ -243,12 +250,13 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     d.segment_samples = p.segment_samples;
     d.parallelogram_samples = p.parallelogram_samples;
     d.seed = p.seed;
-    light_counts(sc->host_lights, p, d.draws_per_hit, d.shadow_rays_per_hit);
+    host_light_counts(sc->host_lights, p, d.draws_per_hit, d.shadow_rays_per_hit, d.samples_per_hit);
+    d.levels = (p.features & CGE_FEAT_RECURSIVE) ? uint32_t(p.ray_depth) + 1u : 1u;
+    d.units_per_lane = d.draws_per_hit == 0 ? d.levels : ((1u << d.levels) - 1u);
     d.part_index = p.part_count > 1 ? p.part_index : 0;
     d.part_count = p.part_count > 1 ? p.part_count : 1;
     d.n_tiles_x = uint32_t((p.width + kTileW - 1) / kTileW);
     d.n_tiles_y = uint32_t((p.height + kTileH - 1) / kTileH);
-    d.accel = (p.features & CGE_FEAT_ACCEL_STRUCTURE) ? 1u : 0u;
     return d;
 }
 
@@ -267,26 +275,44 @@ DevScene scene_for(const cge_scene* sc, const cge_params& p)
     return d;
 }
 
-template <typename F>
-void dispatch(bool fast, bool spheres, bool count, F&& f)
+// Which kernel variant a call runs.
+//   fast tree       : CGE_TRAVERSAL_FAST, enableAccelStructure on, no spheres (the archive's sphere test assumes a unit
+//                     direction, so with shadow rays its result depends on which boxes the REFERENCE tree lets through;
+//                     sphere scenes are therefore always walked literally).
+//   cooperative     : fast tree + shading on + 1..32 shading samples per hit + the per-warp staging fits shared memory.
+//   counting        : literal traversal with box/triangle test counters (CGE_FLAG_COUNT_TESTS).
+struct Variant {
+    bool fast, spheres, count, coop;
+    size_t smem;
+};
+
+constexpr size_t kCoopSmemLimit = 96 * 1024; // per 128-thread CTA: keeps >= 2 CTAs per SM
+
+Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams& dp)
 {
-    // 8 instantiations of the kernels; the lambda receives the three flags as integral constants
-    auto d2 = [&](auto kFast, auto kSpheres) {
-        if (count)
-            f(kFast, kSpheres, std::true_type {});
-        else
-            f(kFast, kSpheres, std::false_type {});
-    };
-    auto d1 = [&](auto kFast) {
-        if (spheres)
-            d2(kFast, std::true_type {});
-        else
-            d2(kFast, std::false_type {});
-    };
-    if (fast)
-        d1(std::true_type {});
+    Variant v {};
+    v.spheres = ds.has_spheres != 0;
+    v.fast = p.traversal == CGE_TRAVERSAL_FAST && (p.features & CGE_FEAT_ACCEL_STRUCTURE) && !v.spheres;
+    v.count = !v.fast && (p.flags & CGE_FLAG_COUNT_TESTS);
+    v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
+    v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
+        && v.smem <= kCoopSmemLimit && !(p.flags & CGE_FLAG_NO_COOPERATIVE);
+    return v;
+}
+
+template <typename F>
+void dispatch(const Variant& v, F&& f)
+{
+    if (v.fast)
+        f(std::true_type {}, std::false_type {}, std::false_type {});
+    else if (v.spheres && v.count)
+        f(std::false_type {}, std::true_type {}, std::true_type {});
+    else if (v.spheres)
+        f(std::false_type {}, std::true_type {}, std::false_type {});
+    else if (v.count)
+        f(std::false_type {}, std::false_type {}, std::true_type {});
     else
-        d1(std::false_type {});
+        f(std::false_type {}, std::false_type {}, std::false_type {});
 }
 
 // packed-tile <-> screen layout.  A rank's k-th tile occupies pixels [32k, 32k+32) of its packed buffer.
@@ -349,26 +375,35 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         cam->half_width, cam->half_height };
     CGE_CUDA(cudaMemsetAsync(s->tileCounter, 0, 64, s->stream));
     CGE_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream));
-    const bool fast = p->traversal == CGE_TRAVERSAL_FAST && (p->features & CGE_FEAT_ACCEL_STRUCTURE);
-#ifdef CGE_COUNT_TESTS
-    const bool count = true;
-#else
-    const bool count = false;
-#endif
+    const Variant v = choose_variant(ds, *p, dp);
+    const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
     cudaError_t err = cudaSuccess;
-    dispatch(fast, ds.has_spheres != 0, count, [&](auto kFast, auto kSpheres, auto kCount) {
-        auto kern = render_kernel<decltype(kFast)::value, decltype(kSpheres)::value, decltype(kCount)::value>;
+    auto grid_for = [&](int perSm) {
+        // persistent CTAs: a multiple of the SM count, never more CTAs than there are 4-tile batches
+        unsigned grid = unsigned(sc->sm_count * std::max(perSm, 1));
+        return std::max(1u, std::min(grid, (myTiles + 3) / 4));
+    };
+    if (v.coop) {
+        auto kern = render_coop_kernel;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v.smem));
         int perSm = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
-        if (err != cudaSuccess)
-            return;
-        perSm = std::max(perSm, 1);
-        const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
-        unsigned grid = unsigned(sc->sm_count * perSm);
-        grid = std::max(1u, std::min(grid, (myTiles + 3) / 4));
-        kern<<<grid, 128, 0, s->stream>>>(ds, dc, dp, rgbDev, idsDev, s->tileCounter, s->counters);
-        err = cudaGetLastError();
-    });
+        if (err == cudaSuccess)
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, v.smem);
+        if (err == cudaSuccess) {
+            kern<<<grid_for(perSm), 128, v.smem, s->stream>>>(ds, dc, dp, rgbDev, idsDev, s->tileCounter, s->counters);
+            err = cudaGetLastError();
+        }
+    } else {
+        dispatch(v, [&](auto kFast, auto kSpheres, auto kCount) {
+            auto kern = render_kernel<decltype(kFast)::value, decltype(kSpheres)::value, decltype(kCount)::value>;
+            int perSm = 0;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
+            if (err != cudaSuccess)
+                return;
+            kern<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, dp, rgbDev, idsDev, s->tileCounter, s->counters);
+            err = cudaGetLastError();
+        });
+    }
     if (err != cudaSuccess)
         return fail(CGE_ERR_CUDA, std::string("render_kernel launch: ") + cudaGetErrorString(err));
     *launches += 1;
@@ -502,7 +537,7 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
             delete sc;
             return fail(CGE_ERR_INVALID_ARG, "supplied BVH is inconsistent with the scene");
         }
-        if (sc->bvh.n_levels > uint32_t(kStackSize - 4)) {
+        if (sc->bvh.n_levels > uint32_t(kRefStackSize - 4)) {
             delete sc;
             return fail(CGE_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
         }
@@ -533,12 +568,18 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
         }
     }
 
-    std::vector<float4> tris(size_t(nPrims) * kTriRows), shade(size_t(nPrims) * kShadeRows);
+    // rank is indexed by reference leaf position; re-index by global primitive id
+    std::vector<uint32_t> rankOf(nPrims, 0);
+    for (uint32_t i = 0; i < nPrims; i++)
+        rankOf[sc->bvh.prim_order[i]] = rank[i];
+
+    // per-primitive records by GLOBAL id (the ray-independent part of libIntersect's triangle test, precomputed on the
+    // host with the same operation order and no FMA), then laid out in each tree's leaf order
+    std::vector<float4> recs(size_t(nPrims) * kTriRows), shade(size_t(nPrims) * kShadeRows);
     const float qnan = std::nanf("");
-    for (uint32_t i = 0; i < nPrims; i++) {
-        const uint32_t gid = sc->bvh.prim_order[i];
-        float4* tr = &tris[size_t(i) * kTriRows];
-        float4* sh = &shade[size_t(i) * kShadeRows];
+    for (uint32_t gid = 0; gid < nPrims; gid++) {
+        float4* tr = &recs[size_t(gid) * kTriRows];
+        float4* sh = &shade[size_t(gid) * kShadeRows];
         if (gid < d->n_triangles) {
             const uint32_t m = triMesh[gid];
             const auto& md = d->meshes[m];
@@ -555,20 +596,46 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
             tr[2] = f4(t.e0.y, t.e0.z, v1.x, v1.y);
             tr[3] = f4(v1.z, t.e1.x, t.e1.y, t.e1.z);
             tr[4] = f4(v2.x, v2.y, v2.z, t.e2.x);
-            tr[5] = f4(t.e2.y, t.e2.z, bitsf(rank[i]), bitsf(0u));
+            tr[5] = f4(t.e2.y, t.e2.z, bitsf(rankOf[gid]), bitsf(gid));
             sh[0] = f4(a.normal[0], a.normal[1], a.normal[2], a.texcoord[0]);
             sh[1] = f4(b.normal[0], b.normal[1], b.normal[2], a.texcoord[1]);
             sh[2] = f4(c.normal[0], c.normal[1], c.normal[2], b.texcoord[0]);
             sh[3] = f4(b.texcoord[1], c.texcoord[0], c.texcoord[1], 0.0f);
-            sh[4] = f4(bitsf(m), bitsf(gid), 0.0f, 0.0f);
+            sh[4] = f4(bitsf(m), 0.0f, 0.0f, 0.0f);
         } else {
             const auto& sd = d->spheres[gid - d->n_triangles];
             tr[0] = f4(qnan, qnan, qnan, qnan);
             tr[1] = f4(sd.center[0], sd.center[1], sd.center[2], sd.radius);
             tr[2] = tr[3] = tr[4] = f4(qnan, qnan, qnan, qnan);
-            tr[5] = f4(qnan, qnan, bitsf(rank[i]), bitsf(1u));
+            tr[5] = f4(qnan, qnan, bitsf(rankOf[gid]), bitsf(gid | kSphereBit));
             sh[0] = sh[1] = sh[2] = sh[3] = f4(0, 0, 0, 0);
-            sh[4] = f4(bitsf(d->n_meshes + (gid - d->n_triangles)), bitsf(gid), 0.0f, 0.0f);
+            sh[4] = f4(bitsf(d->n_meshes + (gid - d->n_triangles)), 0.0f, 0.0f, 0.0f);
+        }
+    }
+    auto in_order = [&](const std::vector<uint32_t>& order) {
+        std::vector<float4> out(size_t(nPrims) * kTriRows);
+        for (uint32_t i = 0; i < nPrims; i++)
+            std::memcpy(&out[size_t(i) * kTriRows], &recs[size_t(order[i]) * kTriRows], sizeof(float4) * kTriRows);
+        return out;
+    };
+    std::vector<float4> tris = haveBvh ? in_order(sc->bvh.prim_order) : std::vector<float4>();
+
+    // ---- fast tree (binned SAH, <= 4 primitives per leaf) for CGE_TRAVERSAL_FAST; triangles-only scenes ---------------
+    std::vector<float4> ftris, fnodes;
+    if (haveBvh && d->n_spheres == 0) {
+        if (!build_sah_bvh(*d, sc->fast) || sc->fast.depth > uint32_t(kFastStackSize - 2)) {
+            delete sc;
+            return fail(CGE_ERR_UNSUPPORTED, "fast BVH build failed");
+        }
+        ftris = in_order(sc->fast.prim_order);
+        fnodes.resize(sc->fast.nodes.size() * kNodeRows);
+        for (size_t i = 0; i < sc->fast.nodes.size(); i++) {
+            const FastNode& n = sc->fast.nodes[i];
+            float4* q = &fnodes[i * kNodeRows];
+            q[0] = f4(n.l_lo[0], n.l_lo[1], n.l_lo[2], n.l_hi[0]);
+            q[1] = f4(n.l_hi[1], n.l_hi[2], n.r_lo[0], n.r_lo[1]);
+            q[2] = f4(n.r_lo[2], n.r_hi[0], n.r_hi[1], n.r_hi[2]);
+            q[3] = f4(bitsf(n.left), bitsf(n.right), 0.0f, 0.0f);
         }
     }
 
@@ -642,6 +709,8 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     };
     up(sc->nodes, nodes);
     up(sc->tris, tris);
+    up(sc->fnodes, fnodes);
+    up(sc->ftris, ftris);
     up(sc->shade, shade);
     up(sc->materials, mats);
     up(sc->textures, texs);
@@ -654,6 +723,9 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     }
     sc->dev.nodes = sc->nodes.p;
     sc->dev.tris = sc->tris.p;
+    sc->dev.fnodes = sc->fnodes.p;
+    sc->dev.ftris = sc->ftris.p;
+    sc->dev.froot = sc->fast.root;
     sc->dev.shade = sc->shade.p;
     sc->dev.materials = sc->materials.p;
     sc->dev.textures = sc->textures.p;
@@ -714,6 +786,8 @@ int cge_scene_destroy(cge_scene* sc)
     }
     sc->nodes.release();
     sc->tris.release();
+    sc->fnodes.release();
+    sc->ftris.release();
     sc->shade.release();
     sc->materials.release();
     sc->textures.release();
@@ -835,9 +909,10 @@ int cge_trace_rays(cge_scene* sc, const float* rays7, uint32_t n, const cge_para
         e = cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream);
     const DevParams dp = make_dev_params(sc, p);
     const DevScene ds = scene_for(sc, p);
-    const bool fast = p.traversal == CGE_TRAVERSAL_FAST && (p.features & CGE_FEAT_ACCEL_STRUCTURE);
+    Variant v = choose_variant(ds, p, dp);
+    v.count = false;
     if (e == cudaSuccess) {
-        dispatch(fast, ds.has_spheres != 0, false, [&](auto kFast, auto kSpheres, auto kCount) {
+        dispatch(v, [&](auto kFast, auto kSpheres, auto kCount) {
             trace_rays_kernel<decltype(kFast)::value, decltype(kSpheres)::value, decltype(kCount)::value>
                 <<<(n + 127) / 128, 128, 0, s->stream>>>(ds, dp, dRays, n, s->rgb, idsOut ? s->ids : nullptr, s->counters);
             e = cudaGetLastError();

@@ -1,26 +1,33 @@
-// dev_scene.h — layout of the flattened scene + BVH resident in HBM (all arrays 16-byte aligned float4 rows so
+// dev_scene.h — layout of the flattened scene + BVHs resident in HBM (all arrays 16-byte aligned float4 rows so
 // every fetch on the traversal path is one LDG.128).
 //
-//   nodes     4 x float4 per INNER node (64 B).  A node carries the boxes of BOTH children, so one pop = one
+// Two trees index the same primitives:
+//   * the REFERENCE-ORDER tree (nodes/tris): node for node the reference's median-split tree, walked literally by
+//     CGE_TRAVERSAL_REFERENCE (exhaustive, right-first, exact libIntersect box arithmetic);
+//   * the FAST tree (fnodes/ftris): binned-SAH, <= 4 primitives per leaf, walked near-first with t culling by
+//     CGE_TRAVERSAL_FAST (bvh_sah.h explains why the result is the same).
+//
+//   nodes / fnodes   4 x float4 per INNER node (64 B).  A node carries the boxes of BOTH children, so one visit = one
 //             64-byte fetch = two box tests, as in the reference's inner-node branch
 //             (reference src/bounding_volume_hierarchy.cpp:331-355):
 //               q0 = L.lower.xyz, L.upper.x     q1 = L.upper.yz, R.lower.xy
-//               q2 = R.lower.z, R.upper.xyz     q3 = bits{ left ref, right ref, left count, right count }
-//             child "ref/count": count == 0 -> ref is an inner-node index; count > 0 -> the child is a leaf
-//             holding primitives [ref, ref+count) of the leaf-ordered primitive arrays.
-//   tris      6 x float4 per primitive (96 B), in LEAF ORDER (the reference's permuted `primitives` vector):
+//               q2 = R.lower.z, R.upper.xyz     q3 = child references (bit patterns)
+//             reference-order tree: q3 = { left ref, right ref, left count, right count }; count == 0 -> ref is an
+//             inner-node index, count > 0 -> leaf holding primitives [ref, ref+count) of `tris`.
+//             fast tree: q3 = { left, right, 0, 0 } packed as in bvh_sah.h (bit 31 leaf, bits 28..30 count-1).
+//   tris / ftris     6 x float4 per primitive (96 B), in the LEAF ORDER of the respective tree:
 //               r0 = n.xyz, D                 plane of trianglePlane (libIntersect I1), bit-identical: same ops, no FMA
 //               r1 = v0.xyz, e0.x             e0 = cross(v2 - v0, n)   first edge test of pointInTriangle (I3)
 //               r2 = e0.yz, v1.xy
 //               r3 = v1.z, e1.xyz             e1 = cross(v0 - v1, n)
 //               r4 = v2.xyz, e2.x             e2 = cross(v1 - v2, n)
-//               r5 = e2.yz, bits{rank}, bits{tag}
+//               r5 = e2.yz, bits{rank}, bits{global primitive id | sphere << 31}
 //             rank = position of the primitive in the reference's exhaustive right-first DFS visit order; among
 //             equal-t hits the reference keeps the LAST visited one (:288-290), i.e. the largest rank.
-//             tag 0 = triangle, 1 = sphere (then r1 = center.xyz, radius and r0 = NaN so the plane test rejects).
-//   shade     5 x float4 per primitive (80 B), leaf order, touched once per closest hit:
+//             sphere records: r1 = center.xyz, radius and r0 = NaN so the plane test rejects.
+//   shade     5 x float4 per primitive (80 B), indexed by GLOBAL primitive id, touched once per closest hit:
 //               s0 = n0.xyz, uv0.x   s1 = n1.xyz, uv0.y   s2 = n2.xyz, uv1.x   s3 = uv1.y, uv2.xy, 0
-//               s4 = bits{ material id, global primitive id, 0, 0 }
+//               s4 = bits{ material id, 0, 0, 0 }
 //   materials 3 x float4 per material: kd.xyz, shininess | ks.xyz, transparency | bits{texture id,0,0,0}
 //   textures  int4 per texture: width, height, texel offset, 0;  texels: packed float RGB
 //   lights    24 floats per light: bits{type}, v[21], 0, 0   (cge_light_desc, include/cge.h)
@@ -37,10 +44,13 @@ constexpr int kMaterialRows = 3;
 constexpr int kLightFloats = 24;
 constexpr int kMaxRayDepth = 15;
 constexpr int kTileW = 8, kTileH = 4; // one warp = one 8x4 pixel tile
+constexpr uint32_t kSphereBit = 0x80000000u;
 
 struct DevScene {
     const float4* nodes;
     const float4* tris;
+    const float4* fnodes;
+    const float4* ftris;
     const float4* shade;
     const float4* materials;
     const int4* textures;
@@ -48,7 +58,8 @@ struct DevScene {
     const float* lights;
     uint32_t n_lights;
     uint32_t n_prims;
-    uint32_t root_ref, root_count; // same encoding as a child slot; n_prims == 0 -> nothing to hit
+    uint32_t root_ref, root_count; // reference-order tree root, same encoding as a child slot
+    uint32_t froot;                // fast tree root (packed)
     uint32_t has_spheres;
 };
 
@@ -64,11 +75,14 @@ struct DevParams {
     int32_t ray_depth;
     int32_t segment_samples, parallelogram_samples;
     uint32_t seed;
-    uint32_t draws_per_hit;   // rand() draws one computeLightContribution call makes (0 -> deterministic fold)
-    uint32_t shadow_rays_per_hit;
+    uint32_t draws_per_hit;       // rand() draws one computeLightContribution call makes (0 -> deterministic fold)
+    uint32_t shadow_rays_per_hit; // shadow rays one computeLightContribution call traces
+    uint32_t samples_per_hit;     // shading evaluations per call (point: 1, segment: N, parallelogram: N*N)
     uint32_t part_index, part_count;
     uint32_t n_tiles_x, n_tiles_y;
-    uint32_t accel;           // enableAccelStructure
+    // cooperative kernel only
+    uint32_t levels;          // ray_depth + 1 when recursive, else 1
+    uint32_t units_per_lane;  // direct-lighting evaluations a pixel can need: levels (fold) or 2^levels - 1
 };
 
 } // namespace cge

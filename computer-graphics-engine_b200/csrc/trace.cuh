@@ -1,0 +1,202 @@
+// trace.cuh — BVH traversal on the device.
+//
+//   trace_reference : BoundingVolumeHierarchy::intersect's traversal reproduced literally
+//                     (reference src/bounding_volume_hierarchy.cpp:312-361 + getIntersecting :272-293): exhaustive DFS
+//                     of the reference's own tree, both child boxes tested with ray.t = FLT_MAX through the exact
+//                     libIntersect box arithmetic (I5), left pushed then right pushed (right popped first), leaf
+//                     primitives ascending, every accepted primitive overwrites the winner, NO culling by t.
+//   trace_fast      : the same answer from the SAH tree (bvh_sah.h): near child first, boxes culled against the
+//                     best t so far, slab test with a precomputed reciprocal direction and a conservative slack,
+//                     equal-t ties resolved by the reference visit rank, optional any-hit exit for shadow rays.
+// Both use the SAME triangle arithmetic: the archive's plane test + three inclusive edge tests (I2-I4) on the
+// precomputed rows, no FMA, IEEE division.
+#pragma once
+#include "dev_scene.h"
+#include "intersect.cuh"
+
+namespace cge {
+
+constexpr int kRefStackSize = 40;
+constexpr int kFastStackSize = 64;
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+struct Hit {
+    float t;
+    int prim;      // index into the tree's leaf-ordered primitive array (-1: miss)
+    unsigned gid;  // global primitive id | kSphereBit
+};
+
+// One triangle candidate against the current best.  Returns true when the archive would accept it
+// (0 <= t <= best and inside all three edges).  r5 is returned for rank / id.
+__device__ __forceinline__ bool triangle_rows_hit(const float4* __restrict__ tr, const vec3 o, const vec3 d, float best, float& tOut,
+    float4& r5)
+{
+    const float4 r0 = ldg4(tr);
+    const vec3 n = v3(r0.x, r0.y, r0.z);
+    const float t = fdiv(fsub(r0.w, dot(o, n)), dot(d, n)); // I2
+    if (!(t >= 0.0f))
+        return false;
+    if (!(best >= t))
+        return false;
+    const vec3 p = d * t + o;
+    const float4 r1 = ldg4(tr + 1);
+    const float4 r2 = ldg4(tr + 2);
+    if (!(dot(v3(r1.w, r2.x, r2.y), p - v3(r1.x, r1.y, r1.z)) >= 0.0f)) // I3, archive order, short-circuit
+        return false;
+    const float4 r3 = ldg4(tr + 3);
+    if (!(dot(v3(r3.y, r3.z, r3.w), p - v3(r2.z, r2.w, r3.x)) >= 0.0f))
+        return false;
+    const float4 r4 = ldg4(tr + 4);
+    r5 = ldg4(tr + 5);
+    if (!(dot(v3(r4.w, r5.x, r5.y), p - v3(r4.x, r4.y, r4.z)) >= 0.0f))
+        return false;
+    tOut = t;
+    return true;
+}
+
+template <bool kSpheres, bool kCount>
+__device__ Hit trace_reference(const DevScene& s, const vec3 o, const vec3 d, float tmax, unsigned& nbox, unsigned& ntri)
+{
+    Hit h { tmax, -1, 0u };
+    if (s.n_prims == 0)
+        return h;
+    uint2 stack[kRefStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(s.root_ref, s.root_count);
+    while (sp > 0) {
+        const uint2 e = stack[--sp];
+        if (e.y > 0) {
+            for (unsigned i = e.x; i < e.x + e.y; i++) {
+                const float4* tr = s.tris + size_t(i) * kTriRows;
+                if (kCount)
+                    ntri++;
+                if (kSpheres) {
+                    const float4 r5 = ldg4(tr + 5);
+                    if (__float_as_uint(r5.w) & kSphereBit) {
+                        const float4 r1 = ldg4(tr + 1);
+                        Ray ray { o, d, h.t };
+                        if (intersect_sphere(v3(r1.x, r1.y, r1.z), r1.w, ray, nullptr)) { // strict t < ray.t (I6)
+                            h.t = ray.t;
+                            h.prim = int(i);
+                            h.gid = __float_as_uint(r5.w);
+                        }
+                        continue;
+                    }
+                }
+                float t;
+                float4 r5;
+                if (triangle_rows_hit(tr, o, d, h.t, t, r5)) {
+                    h.t = t;
+                    h.prim = int(i);
+                    h.gid = __float_as_uint(r5.w);
+                }
+            }
+        } else {
+            const float4* nd = s.nodes + size_t(e.x) * kNodeRows;
+            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+            if (kCount)
+                nbox += 2;
+            Ray ray { o, d, FLT_MAX };
+            const bool hitL = intersect_aabb(v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), ray);
+            ray.t = FLT_MAX;
+            const bool hitR = intersect_aabb(v3(q1.z, q1.w, q2.x), v3(q2.y, q2.z, q2.w), ray);
+            if (hitL)
+                stack[sp++] = make_uint2(__float_as_uint(q3.x), __float_as_uint(q3.z));
+            if (hitR)
+                stack[sp++] = make_uint2(__float_as_uint(q3.y), __float_as_uint(q3.w)); // popped first
+        }
+    }
+    return h;
+}
+
+// Fast tree.  Triangles only (scenes with spheres are always walked by trace_reference, see cge_api.cu).
+template <bool kAnyHit>
+__device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax)
+{
+    Hit h { tmax, -1, 0u };
+    if (s.n_prims == 0)
+        return h;
+    unsigned bestRank = 0;
+    // The archive replaces the slab of an axis with d == 0 by the constants [FLT_MIN, FLT_MAX] whatever the origin
+    // (SURVEY.md Appendix A, I5); such rays take the exact box function so that no box the reference enters is skipped.
+    const bool exactBoxes = d.x == 0.0f || d.y == 0.0f || d.z == 0.0f;
+    const vec3 inv = v3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z));
+
+    uint2 stack[kFastStackSize]; // (child ref, entry distance bits): re-culled against the best t when popped
+    int sp = 0;
+    unsigned cur = s.froot;
+    auto pop = [&]() -> bool {
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) > h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f)
+                continue;
+            cur = e.x;
+            return true;
+        }
+        return false;
+    };
+    for (;;) {
+        if (cur & 0x80000000u) {
+            const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+            for (unsigned i = first; i < first + count; i++) {
+                float t;
+                float4 r5;
+                if (!triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, h.t, t, r5))
+                    continue;
+                const unsigned rank = __float_as_uint(r5.z);
+                if (t == h.t && h.prim >= 0 && rank < bestRank)
+                    continue; // an equal-t triangle the reference visits later is already held
+                h.t = t;
+                h.prim = int(i);
+                h.gid = __float_as_uint(r5.w);
+                bestRank = rank;
+                if (kAnyHit)
+                    return h;
+            }
+            if (!pop())
+                break;
+            continue;
+        }
+        const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+        const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+        // a box is skipped only if it starts clearly beyond the best hit so far
+        const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
+        bool hitL, hitR;
+        float entL, entR;
+        if (!exactBoxes) {
+            const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
+            const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
+            const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
+            entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+            const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+            hitL = entL <= extL * 1.000002f && entL <= bound;
+            const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
+            const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
+            const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
+            entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+            const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+            hitR = entR <= extR * 1.000002f && entR <= bound;
+        } else {
+            Ray ray { o, d, FLT_MAX };
+            hitL = intersect_aabb(v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), ray, &entL) && !(entL > bound);
+            ray.t = FLT_MAX;
+            hitR = intersect_aabb(v3(q1.z, q1.w, q2.x), v3(q2.y, q2.z, q2.w), ray, &entR) && !(entR > bound);
+        }
+        const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+        if (hitL && hitR) {
+            const bool leftFirst = entL <= entR;
+            stack[sp++] = leftFirst ? make_uint2(cr, __float_as_uint(entR)) : make_uint2(cl, __float_as_uint(entL));
+            cur = leftFirst ? cl : cr;
+        } else if (hitL) {
+            cur = cl;
+        } else if (hitR) {
+            cur = cr;
+        } else if (!pop()) {
+            break;
+        }
+    }
+    return h;
+}
+
+} // namespace cge

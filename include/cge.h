@@ -153,16 +153,22 @@ int cge_camera_from_trackball(float fovy, float aspect, const float look_at[3], 
 enum {
     CGE_TRAVERSAL_REFERENCE = 0, /* exhaustive DFS, right child first, no t culling: visit order and tie
                                     rule of src/bounding_volume_hierarchy.cpp:312-361 reproduced literally */
-    CGE_TRAVERSAL_FAST = 1       /* same tree, near-child-first with conservative t culling, shadow rays
-                                    stop at the first blocker; winner chosen by the reference's tie rank */
+    CGE_TRAVERSAL_FAST = 1       /* binned-SAH tree (<= 4 primitives per leaf), near child first, conservative t culling,
+                                    shadow rays stop at the first blocker; equal-t winner chosen by the reference's
+                                    visit rank; warp-cooperative shadow-ray queue.  Scenes with spheres and
+                                    !enableAccelStructure fall back to the literal traversal. */
 };
 enum {
     CGE_SAMPLER_HASH = 0 /* rand() replaced by hash(seed, pixel, draw index) — see DESIGN.md "sampler" */
 };
 enum {
     CGE_FLAG_WANT_PRIM_IDS = 1u << 0,
-    CGE_FLAG_RGB_DEVICE_PTR = 1u << 1 /* rgb_out / prim_id_out are device pointers on the calling GPU:
-                                         no D2H copy (kernel-only timing, or a caller that keeps the frame in HBM) */
+    CGE_FLAG_RGB_DEVICE_PTR = 1u << 1, /* rgb_out / prim_id_out are device pointers on the calling GPU:
+                                          no D2H copy (kernel-only timing, or a caller that keeps the frame in HBM) */
+    CGE_FLAG_COUNT_TESTS = 1u << 2,    /* CGE_TRAVERSAL_REFERENCE only: fill cge_stats::box_tests / tri_tests (they
+                                          equal the reference's own intersectRayWithShape/Triangle call counts) */
+    CGE_FLAG_NO_COOPERATIVE = 1u << 3  /* CGE_TRAVERSAL_FAST: use the one-thread-per-pixel kernel instead of the
+                                          warp-cooperative one (A/B measurements, tests) */
 };
 
 typedef struct cge_params {
@@ -188,7 +194,7 @@ typedef struct cge_stats {
     uint64_t shadow_rays;     /* unique shadow rays traced on the GPU                 */
     uint64_t reference_rays;  /* BvhInterface::intersect calls the reference would have made for this frame
                                  (duplicate reflection subtrees counted, src/render.cpp:100,118) */
-    uint64_t box_tests, tri_tests; /* only filled when the library is built with CGE_COUNT_TESTS */
+    uint64_t box_tests, tri_tests; /* only filled with CGE_FLAG_COUNT_TESTS */
     float kernel_ms;          /* device time of the render kernels (CUDA events on the call's stream) */
     float total_ms;           /* device time including uploads of camera/params and the D2H copy     */
     uint32_t kernel_launches; /* kernels launched by this call                                        */

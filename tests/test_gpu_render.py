@@ -42,19 +42,29 @@ def assert_parity(name, rgb, ids, ref_rgb, ref_ids, id_budget=ID_MISMATCH_BUDGET
     assert err <= RGB_TOL * scale, f"{name}: max abs err {err} (scale {scale})"
 
 
+# (traversal, flags): literal traversal with test counters / fast tree per-thread kernel / fast tree cooperative kernel
+MODES = {"reference": (0, 4), "fast-thread": (1, 8), "fast-coop": (1, 0)}
+
+
 @pytest.mark.parametrize("name", list(SMALL))
-@pytest.mark.parametrize("traversal", [0, 1])
-def test_golden_images(cge, name, traversal):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_golden_images(cge, name, mode):
     w, h = SMALL[name]
+    traversal, flags = MODES[mode]
     cfg = cge.configs.get(name, w, h)
     g = np.load(cge.configs.SCENE_DIR.parent / f"{name}_{w}x{h}.npz")
     with cge.Scene(flat_for(cge, cfg)) as sc:
         info = sc.bvh_info()
         assert (info["nodes"], info["levels"], info["leaves"]) == (int(g["bvh_nodes"]), int(g["bvh_levels"]), int(g["bvh_leaves"]))
-        rgb, ids, st = sc.render(cfg, traversal=traversal)
+        rgb, ids, st = sc.render(cfg, traversal=traversal, flags=flags)
     assert_parity(name, rgb, ids, g["rgb"], g["ids"])
     # the reference would have made exactly this many BvhInterface::intersect calls (ld --wrap counter)
     assert st["reference_rays"] == int(g["rays"]), (st["reference_rays"], int(g["rays"]))
+    if mode == "reference":
+        # literal traversal: the device performs exactly the reference's box and triangle tests (ld --wrap counters).
+        # The GPU traces each mirror chain once, so compare per unique ray class where no duplication happens.
+        if not (cfg["features"] & cge.configs.FEAT_RECURSIVE):
+            assert st["box_tests"] == int(g["box_tests"]) and st["tri_tests"] == int(g["tri_tests"])
 
 
 @pytest.mark.parametrize("name,size", [("c1_cornell", (256, 256)), ("c2_cube_textured", (320, 180)),
@@ -66,9 +76,9 @@ def test_live_reference(cge, ref, name, size, tmp_path):
     with ref.RefScene(path, cfg["features"]) as rs:
         ref_rgb, ref_ids, rst = rs.render(cfg)
     with cge.Scene(cge.load_scene(cfg)) as sc:
-        for traversal in (0, 1):
-            rgb, ids, st = sc.render(cfg, traversal=traversal)
-            assert_parity(f"{name}/t{traversal}", rgb, ids, ref_rgb, ref_ids)
+        for mode, (traversal, flags) in MODES.items():
+            rgb, ids, st = sc.render(cfg, traversal=traversal, flags=flags)
+            assert_parity(f"{name}/{mode}", rgb, ids, ref_rgb, ref_ids)
             assert st["reference_rays"] == rst["rays"]
 
 
@@ -94,10 +104,28 @@ def test_mixed_scene_all_light_kinds_spheres_and_flags(cge, ref):
             cfg = dict(base, features=feats)
             with ref.RefScene(path, feats) as rs:
                 ref_rgb, ref_ids, rst = rs.render(cfg)
-            for traversal in (0, 1):
-                rgb, ids, st = sc.render(cfg, traversal=traversal)
-                assert_parity(f"mixed/f{feats:#x}/t{traversal}", rgb, ids, ref_rgb, ref_ids, id_budget=2e-3)
+            for mode, (traversal, flags) in MODES.items():
+                rgb, ids, st = sc.render(cfg, traversal=traversal, flags=flags)
+                assert_parity(f"mixed/f{feats:#x}/{mode}", rgb, ids, ref_rgb, ref_ids, id_budget=2e-3)
                 assert st["reference_rays"] == rst["rays"]
+    # the same lights over a triangles-only scene exercise the fast tree + cooperative kernel with 1 + 5 + 9 samples
+    path = C.SCENE_DIR / "monkey.cges"
+    mk = cge.scenefile.load(path)
+    mk.lights = flat.lights
+    tmp = C.SCENE_DIR.parent / "_tmp_monkey_lights.cges"
+    cge.scenefile.save(mk, tmp)
+    try:
+        with cge.Scene(mk) as sc:
+            for feats in combos[2:]:
+                cfg = dict(base, features=feats, camera=dict(base["camera"], dist=2.5))
+                with ref.RefScene(tmp, feats) as rs:
+                    ref_rgb, ref_ids, rst = rs.render(cfg)
+                for mode, (traversal, flags) in MODES.items():
+                    rgb, ids, st = sc.render(cfg, traversal=traversal, flags=flags)
+                    assert_parity(f"monkey-lights/f{feats:#x}/{mode}", rgb, ids, ref_rgb, ref_ids, id_budget=2e-3)
+                    assert st["reference_rays"] == rst["rays"]
+    finally:
+        tmp.unlink(missing_ok=True)
 
 
 def test_bvh_matches_reference_tree(cge):
@@ -135,10 +163,15 @@ def test_full_size_properties(cge, name):
     with cge.Scene(cge.load_scene(cfg)) as sc:
         rgb_f, ids_f, st_f = sc.render(cfg, traversal=1)
         rgb_r, ids_r, st_r = sc.render(cfg, traversal=0)
-        assert st_f["reference_rays"] == st_r["reference_rays"]
+        rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_NO_COOPERATIVE)
+        assert st_f["reference_rays"] == st_r["reference_rays"] == st_t["reference_rays"]
         assert (ids_f != ids_r).mean() <= ID_MISMATCH_BUDGET
+        # cooperative and per-thread kernels walk the same tree with the same arithmetic: identical bits
+        assert np.array_equal(ids_t, ids_f) and rgb_t.tobytes() == rgb_f.tobytes()
         err, nan_mm = compare_images(rgb_f, rgb_r)
         assert nan_mm <= ID_MISMATCH_BUDGET * ids_f.size
+        differing = (np.abs(np.nan_to_num(rgb_f, nan=0.0) - np.nan_to_num(rgb_r, nan=0.0)).max(-1) > 1e-3).mean()
+        assert differing <= ID_MISMATCH_BUDGET, differing
         rgb_p = np.zeros_like(rgb_f)
         ids_p = np.full_like(ids_f, -7)
         for k in range(3):
@@ -161,9 +194,9 @@ def test_dragon_standin_full_scene_reduced_frame(cge, ref, tmp_path):
     with cge.Scene(flat) as sc:
         mine = sc.bvh_info()
         assert (mine["nodes"], mine["levels"], mine["leaves"]) == (info["nodes"], info["levels"], info["leaves"])
-        for traversal in (0, 1):
-            rgb, ids, st = sc.render(cfg, traversal=traversal)
-            assert_parity(f"dragon/t{traversal}", rgb, ids, ref_rgb, ref_ids)
+        for mode, (traversal, flags) in MODES.items():
+            rgb, ids, st = sc.render(cfg, traversal=traversal, flags=flags)
+            assert_parity(f"dragon/{mode}", rgb, ids, ref_rgb, ref_ids)
             assert st["reference_rays"] == rst["rays"]
 
 

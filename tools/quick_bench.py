@@ -15,13 +15,16 @@ for name in names:
     t0 = time.time(); flat = pkg.load_scene(cfg); t1 = time.time()
     with pkg.Scene(flat) as sc:
         t2 = time.time()
-        for trav in ((1, 0) if name != "c5_dragon" else (1,)):
+        modes = [(1, 0, "fast-coop"), (1, pkg.FLAG_NO_COOPERATIVE, "fast-thread"), (0, 0, "reference")]
+        if name == "c5_dragon" and scale > 0.3:
+            modes = modes[:2]
+        for trav, flags, label in modes:
             best = None
             for it in range(3):
-                rgb, ids, st = sc.render(cfg, traversal=trav, want_ids=False)
+                rgb, ids, st = sc.render(cfg, traversal=trav, want_ids=False, flags=flags)
                 if best is None or st["kernel_ms"] < best["kernel_ms"]:
                     best = st
-            print(json.dumps({"cfg": name, "w": cfg["width"], "h": cfg["height"], "traversal": trav,
+            print(json.dumps({"cfg": name, "w": cfg["width"], "h": cfg["height"], "mode": label,
                               "kernel_ms": round(best["kernel_ms"], 3), "total_ms": round(best["total_ms"], 3),
                               "gpu_rays": best["gpu_rays"], "ref_rays": best["reference_rays"],
                               "Mrays_s": round(best["gpu_rays"] / best["kernel_ms"] / 1e3, 1),
