@@ -17,11 +17,11 @@ from . import configs, scenefile, standin  # noqa: F401
 from .scenefile import FlatScene
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libcge.so"
+LIB_PATH = Path(os.environ.get("CGE_LIB", _PKG / "libcge.so"))  # CGE_LIB: development A/B builds only
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
-FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_NO_COOPERATIVE = 1, 2, 4, 8
+FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1, 2, 4, 8
 UNIQUE_ID_BYTES = 128
 
 

@@ -9,11 +9,12 @@ PKG=$(cd "$HERE/.." && pwd)
 REPO=$(cd "$PKG/.." && pwd)
 EXTRA=${CGE_NVCC_EXTRA:-}
 OUT=${CGE_OUT:-$PKG/libcge.so}
+LOG=${OUT%.so}_ptxas.log   # registers / spills / shared memory per kernel (-Xptxas -v)
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -fmad=false -prec-div=true -prec-sqrt=true \
     -Xcompiler -fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function \
     -Xptxas -v $EXTRA \
     -I"$REPO/include" -I"$HERE" \
-    -shared -o "$OUT" "$HERE/cge_api.cu" "$HERE/bvh_build.cpp" "$HERE/bvh_sah.cpp" -ldl 2> "$PKG/build_ptxas.log" || { cat "$PKG/build_ptxas.log" >&2; exit 1; }
-grep -E "error|warning" "$PKG/build_ptxas.log" | grep -v "ptxas info" | head -20 >&2 || true
+    -shared -o "$OUT" "$HERE/cge_api.cu" "$HERE/bvh_build.cpp" "$HERE/bvh_sah.cpp" -ldl 2> "$LOG" || { cat "$LOG" >&2; exit 1; }
+grep -E "error|warning" "$LOG" | grep -v "ptxas info" | head -20 >&2 || true
 echo "built $OUT"

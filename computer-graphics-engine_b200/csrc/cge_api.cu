@@ -279,7 +279,8 @@ DevScene scene_for(const cge_scene* sc, const cge_params& p)
 //   fast tree       : CGE_TRAVERSAL_FAST, enableAccelStructure on, no spheres (the archive's sphere test assumes a unit
 //                     direction, so with shadow rays its result depends on which boxes the REFERENCE tree lets through;
 //                     sphere scenes are therefore always walked literally).
-//   cooperative     : fast tree + shading on + 1..32 shading samples per hit + the per-warp staging fits shared memory.
+//   cooperative     : opt-in (CGE_FLAG_COOPERATIVE): fast tree + shading on + 1..32 shading samples per hit + the
+//                     per-warp staging fits shared memory.
 //   counting        : literal traversal with box/triangle test counters (CGE_FLAG_COUNT_TESTS).
 struct Variant {
     bool fast, spheres, count, coop;
@@ -296,7 +297,7 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
     v.count = !v.fast && (p.flags & CGE_FLAG_COUNT_TESTS);
     v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
     v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
-        && v.smem <= kCoopSmemLimit && !(p.flags & CGE_FLAG_NO_COOPERATIVE);
+        && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE);
     return v;
 }
 

@@ -20,6 +20,15 @@ namespace cge {
 
 constexpr int kMaxLevels = kMaxRayDepth + 1;
 
+// minimum resident 128-thread CTAs per SM the kernels are compiled for (register budget = 65536 / (128 * N));
+// chosen from the A/B runs recorded in profiles/ (see DESIGN.md "Occupancy").
+#ifndef CGE_MINB_THREAD
+#define CGE_MINB_THREAD 8
+#endif
+#ifndef CGE_MINB_COOP
+#define CGE_MINB_COOP 3
+#endif
+
 struct Counters {
     unsigned long long primary, bounce, shadow, reference, box, tri;
 };
@@ -231,7 +240,7 @@ __device__ __forceinline__ void store_pixel(const DevParams& p, float* __restric
 }
 
 template <bool kFast, bool kSpheres, bool kCount>
-__global__ void __launch_bounds__(128) render_kernel(DevScene s, DevCamera cam, DevParams p, float* __restrict__ rgb,
+__global__ void __launch_bounds__(128, CGE_MINB_THREAD) render_kernel(DevScene s, DevCamera cam, DevParams p, float* __restrict__ rgb,
     int* __restrict__ ids, unsigned* __restrict__ tileCounter, Counters* __restrict__ gcnt)
 {
     const unsigned lane = threadIdx.x & 31;
@@ -303,7 +312,7 @@ __device__ __forceinline__ HitRec rec_load(const float* rec, unsigned level, uns
     return h;
 }
 
-__global__ void __launch_bounds__(128) render_coop_kernel(DevScene s, DevCamera cam, DevParams p, float* __restrict__ rgb,
+__global__ void __launch_bounds__(128, CGE_MINB_COOP) render_coop_kernel(DevScene s, DevCamera cam, DevParams p, float* __restrict__ rgb,
     int* __restrict__ ids, unsigned* __restrict__ tileCounter, Counters* __restrict__ gcnt)
 {
     extern __shared__ float smem[];

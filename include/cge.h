@@ -155,7 +155,7 @@ enum {
                                     rule of src/bounding_volume_hierarchy.cpp:312-361 reproduced literally */
     CGE_TRAVERSAL_FAST = 1       /* binned-SAH tree (<= 4 primitives per leaf), near child first, conservative t culling,
                                     shadow rays stop at the first blocker; equal-t winner chosen by the reference's
-                                    visit rank; warp-cooperative shadow-ray queue.  Scenes with spheres and
+                                    visit rank.  Scenes with spheres and
                                     !enableAccelStructure fall back to the literal traversal. */
 };
 enum {
@@ -167,8 +167,9 @@ enum {
                                           no D2H copy (kernel-only timing, or a caller that keeps the frame in HBM) */
     CGE_FLAG_COUNT_TESTS = 1u << 2,    /* CGE_TRAVERSAL_REFERENCE only: fill cge_stats::box_tests / tri_tests (they
                                           equal the reference's own intersectRayWithShape/Triangle call counts) */
-    CGE_FLAG_NO_COOPERATIVE = 1u << 3  /* CGE_TRAVERSAL_FAST: use the one-thread-per-pixel kernel instead of the
-                                          warp-cooperative one (A/B measurements, tests) */
+    CGE_FLAG_COOPERATIVE = 1u << 3     /* CGE_TRAVERSAL_FAST: use the warp-cooperative shadow-queue kernel instead of
+                                          the one-thread-per-pixel kernel.  It wins on sparse / low-resolution frames
+                                          and loses at the judged resolutions (DESIGN.md "Kernels"), hence opt-in. */
 };
 
 typedef struct cge_params {

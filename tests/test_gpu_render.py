@@ -43,7 +43,7 @@ def assert_parity(name, rgb, ids, ref_rgb, ref_ids, id_budget=ID_MISMATCH_BUDGET
 
 
 # (traversal, flags): literal traversal with test counters / fast tree per-thread kernel / fast tree cooperative kernel
-MODES = {"reference": (0, 4), "fast-thread": (1, 8), "fast-coop": (1, 0)}
+MODES = {"reference": (0, 4), "fast-thread": (1, 0), "fast-coop": (1, 8)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
@@ -163,7 +163,7 @@ def test_full_size_properties(cge, name):
     with cge.Scene(cge.load_scene(cfg)) as sc:
         rgb_f, ids_f, st_f = sc.render(cfg, traversal=1)
         rgb_r, ids_r, st_r = sc.render(cfg, traversal=0)
-        rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_NO_COOPERATIVE)
+        rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_COOPERATIVE)
         assert st_f["reference_rays"] == st_r["reference_rays"] == st_t["reference_rays"]
         assert (ids_f != ids_r).mean() <= ID_MISMATCH_BUDGET
         # cooperative and per-thread kernels walk the same tree with the same arithmetic: identical bits

@@ -1,0 +1,34 @@
+"""Summarise an .ncu-rep into the handful of counters DESIGN.md argues from.  usage: ncu_summary.py file.ncu-rep"""
+import csv, subprocess, sys
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "local_load", "local_store", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+for vals in rows[2:]:
+    d = dict(zip(hdr, vals))
+    print("kernel:", d.get("Kernel Name", "?")[:80])
+    for h, u in zip(hdr, units):
+        if any(h == w or h.startswith(w) for w in WANT) and ".max" not in h and ".min" not in h and ".per_second" not in h and "pct_of_peak_sustained_elapsed" not in h.replace("sm__throughput.avg.pct_of_peak_sustained_elapsed","").replace("dram__throughput.avg.pct_of_peak_sustained_elapsed","").replace("lts__throughput.avg.pct_of_peak_sustained_elapsed",""):
+            print(f"  {h} = {d[h]} {u}")
