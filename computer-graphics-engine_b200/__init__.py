@@ -22,6 +22,7 @@ LIB_PATH = Path(os.environ.get("CGE_LIB", _PKG / "libcge.so"))  # CGE_LIB: devel
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
 FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1, 2, 4, 8
+FLAG_DEBUG_CYCLES, FLAG_PER_THREAD = 16, 32
 UNIQUE_ID_BYTES = 128
 
 

@@ -18,6 +18,7 @@
 #include "dev_scene.h"
 #include "nccl_min.h"
 #include "render_kernels.cuh"
+#include "wavefront.cuh"
 
 using namespace cge;
 
@@ -74,6 +75,9 @@ struct Scratch {
     float* gatherRgb = nullptr; // rank 0 only: receive staging for the other ranks' packed tiles
     int* gatherIds = nullptr;
     size_t gatherPixels = 0;
+    // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
+    WaveBuffers wave {};
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     bool busy = false;
@@ -253,6 +257,7 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     host_light_counts(sc->host_lights, p, d.draws_per_hit, d.shadow_rays_per_hit, d.samples_per_hit);
     d.levels = (p.features & CGE_FEAT_RECURSIVE) ? uint32_t(p.ray_depth) + 1u : 1u;
     d.units_per_lane = d.draws_per_hit == 0 ? d.levels : ((1u << d.levels) - 1u);
+    d.debug_cycles = (p.flags & CGE_FLAG_DEBUG_CYCLES) ? 1u : 0u;
     d.part_index = p.part_count > 1 ? p.part_index : 0;
     d.part_count = p.part_count > 1 ? p.part_count : 1;
     d.n_tiles_x = uint32_t((p.width + kTileW - 1) / kTileW);
@@ -275,6 +280,12 @@ DevScene scene_for(const cge_scene* sc, const cge_params& p)
     return d;
 }
 
+unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
+{
+    const unsigned nTiles = d.n_tiles_x * d.n_tiles_y;
+    return nTiles > rank ? (nTiles - rank + nRanks - 1) / nRanks : 0;
+}
+
 // Which kernel variant a call runs.
 //   fast tree       : CGE_TRAVERSAL_FAST, enableAccelStructure on, no spheres (the archive's sphere test assumes a unit
 //                     direction, so with shadow rays its result depends on which boxes the REFERENCE tree lets through;
@@ -283,28 +294,50 @@ DevScene scene_for(const cge_scene* sc, const cge_params& p)
 //                     per-warp staging fits shared memory.
 //   counting        : literal traversal with box/triangle test counters (CGE_FLAG_COUNT_TESTS).
 struct Variant {
-    bool fast, spheres, count, coop;
+    bool fast, spheres, count, coop, wave;
     size_t smem;
+    size_t waveBytes;
 };
 
 constexpr size_t kCoopSmemLimit = 96 * 1024; // per 128-thread CTA: keeps >= 2 CTAs per SM
+constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than this fall back to the per-thread kernel
+
+struct WaveSizes {
+    size_t recFloats, meta, next, dirFloats;
+    size_t bytes() const { return recFloats * 4 + meta * 8 + next * 4 + dirFloats * 4; }
+};
+WaveSizes wave_sizes(const DevParams& dp, size_t cap)
+{
+    WaveSizes w;
+    w.recFloats = size_t(dp.levels) * kRecFloats * cap;
+    w.meta = size_t(dp.levels) * cap;
+    w.next = size_t(dp.levels) * cap;
+    w.dirFloats = size_t(dp.units_per_lane) * 3 * cap;
+    return w;
+}
 
 Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams& dp)
 {
     Variant v {};
     v.spheres = ds.has_spheres != 0;
     v.fast = p.traversal == CGE_TRAVERSAL_FAST && (p.features & CGE_FEAT_ACCEL_STRUCTURE) && !v.spheres;
-    v.count = !v.fast && (p.flags & CGE_FLAG_COUNT_TESTS);
+    v.count = (p.flags & CGE_FLAG_COUNT_TESTS) != 0;
     v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
     v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
-        && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE);
+        && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count;
+    const size_t cap = size_t(tiles_of(dp, dp.part_index, dp.part_count)) * 32;
+    v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
+    v.wave = v.fast && !v.coop && !v.count && (p.features & CGE_FEAT_SHADING) && !(p.flags & (CGE_FLAG_PER_THREAD | CGE_FLAG_DEBUG_CYCLES))
+        && v.waveBytes <= kWaveScratchLimit && cap > 0;
     return v;
 }
 
 template <typename F>
 void dispatch(const Variant& v, F&& f)
 {
-    if (v.fast)
+    if (v.fast && v.count)
+        f(std::true_type {}, std::false_type {}, std::true_type {});
+    else if (v.fast)
         f(std::true_type {}, std::false_type {}, std::false_type {});
     else if (v.spheres && v.count)
         f(std::false_type {}, std::true_type {}, std::true_type {});
@@ -362,12 +395,6 @@ __global__ void unpack_tiles_kernel(const float* __restrict__ inRgb, const int* 
     }
 }
 
-unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
-{
-    const unsigned nTiles = d.n_tiles_x * d.n_tiles_y;
-    return nTiles > rank ? (nTiles - rank + nRanks - 1) / nRanks : 0;
-}
-
 int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_params* p, const DevParams& dp, float* rgbDev,
     int* idsDev, uint32_t* launches)
 {
@@ -384,7 +411,52 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         unsigned grid = unsigned(sc->sm_count * std::max(perSm, 1));
         return std::max(1u, std::min(grid, (myTiles + 3) / 4));
     };
-    if (v.coop) {
+    if (v.wave) {
+        const size_t cap = size_t(myTiles) * 32;
+        const WaveSizes ws = wave_sizes(dp, cap);
+        auto grow = [&](auto*& ptr, size_t& have, size_t need, size_t elem) -> cudaError_t {
+            if (have >= need)
+                return cudaSuccess;
+            if (ptr)
+                cudaFree(ptr);
+            ptr = nullptr;
+            have = 0;
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), need * elem);
+            if (e == cudaSuccess)
+                have = need;
+            return e;
+        };
+        err = grow(s->wave.rec, s->waveRecFloats, ws.recFloats, sizeof(float));
+        if (err == cudaSuccess)
+            err = grow(s->wave.meta, s->waveMeta, ws.meta, sizeof(uint2));
+        if (err == cudaSuccess)
+            err = grow(s->wave.next, s->waveNext, ws.next, sizeof(unsigned));
+        if (err == cudaSuccess)
+            err = grow(s->wave.dir, s->waveDirFloats, ws.dirFloats, sizeof(float));
+        if (err == cudaSuccess && !s->wave.counts)
+            err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 32 * sizeof(unsigned));
+        if (err == cudaSuccess)
+            err = cudaMemsetAsync(s->wave.counts, 0, 32 * sizeof(unsigned), s->stream);
+        s->wave.cap = unsigned(cap);
+        int perSm = 0;
+        if (err == cudaSuccess)
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
+        if (err == cudaSuccess) {
+            wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, dp, s->wave, rgbDev, idsDev, s->counters);
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess)
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel, 128, 0);
+        if (err == cudaSuccess) {
+            wf_shade_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess) {
+            wf_fold_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(dp, s->wave, rgbDev);
+            err = cudaGetLastError();
+        }
+        *launches += 2;
+    } else if (v.coop) {
         auto kern = render_coop_kernel;
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v.smem));
         int perSm = 0;
@@ -775,6 +847,11 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->counters);
         cudaFree(s->gatherRgb);
         cudaFree(s->gatherIds);
+        cudaFree(s->wave.rec);
+        cudaFree(s->wave.meta);
+        cudaFree(s->wave.next);
+        cudaFree(s->wave.dir);
+        cudaFree(s->wave.counts);
         if (s->ev0)
             cudaEventDestroy(s->ev0);
         if (s->ev1)

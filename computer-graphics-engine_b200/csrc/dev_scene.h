@@ -83,6 +83,7 @@ struct DevParams {
     // cooperative kernel only
     uint32_t levels;          // ray_depth + 1 when recursive, else 1
     uint32_t units_per_lane;  // direct-lighting evaluations a pixel can need: levels (fold) or 2^levels - 1
+    uint32_t debug_cycles;    // CGE_FLAG_DEBUG_CYCLES
 };
 
 } // namespace cge

@@ -76,14 +76,14 @@ struct PixelTracer {
     __device__ Hit closest(const Ray& r)
     {
         if (kFast)
-            return trace_fast<false>(s, r.o, r.d, r.t);
+            return trace_fast<false, kCount>(s, r.o, r.d, r.t, &nbox, &ntri);
         return trace_reference<kSpheres, kCount>(s, r.o, r.d, r.t, nbox, ntri);
     }
     __device__ bool occluded(vec3 o, vec3 d)
     {
         cnt.shadow++;
         if (kFast)
-            return trace_fast<true>(s, o, d, 1.0f).prim >= 0;
+            return trace_fast<true, kCount>(s, o, d, 1.0f, &nbox, &ntri).prim >= 0;
         return trace_reference<kSpheres, kCount>(s, o, d, 1.0f, nbox, ntri).prim >= 0;
     }
     __device__ const float4* rows(const Hit& h) const { return (kFast ? s.ftris : s.tris) + size_t(h.prim) * kTriRows; }
@@ -248,9 +248,13 @@ __global__ void __launch_bounds__(128, CGE_MINB_THREAD) render_kernel(DevScene s
     int x, y;
     while (next_tile(p, tileCounter, lane, x, y)) {
         if (x < p.width && y < p.height) {
+            const long long t0 = p.debug_cycles ? clock64() : 0;
+            const unsigned b0 = pt.nbox;
             const Ray ray = generate_ray(cam, x, y, p.width, p.height);
             int primId;
             const vec3 c = pt.final_color(ray, unsigned(y) * unsigned(p.width) + unsigned(x), primId);
+            if (p.debug_cycles) // development aid: per-pixel cost map in place of the primitive ids
+                primId = kCount ? int(pt.nbox - b0) : int((clock64() - t0) >> 4);
             store_pixel(p, rgb, ids, x, y, c, primId);
         }
     }

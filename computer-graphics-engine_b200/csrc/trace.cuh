@@ -111,8 +111,8 @@ __device__ Hit trace_reference(const DevScene& s, const vec3 o, const vec3 d, fl
 }
 
 // Fast tree.  Triangles only (scenes with spheres are always walked by trace_reference, see cge_api.cu).
-template <bool kAnyHit>
-__device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax)
+template <bool kAnyHit, bool kCount = false>
+__device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax, unsigned* nbox = nullptr, unsigned* ntri = nullptr)
 {
     Hit h { tmax, -1, 0u };
     if (s.n_prims == 0)
@@ -139,6 +139,8 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
     for (;;) {
         if (cur & 0x80000000u) {
             const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+            if (kCount)
+                *ntri += count;
             for (unsigned i = first; i < first + count; i++) {
                 float t;
                 float4 r5;
@@ -160,6 +162,8 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
         }
         const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
         const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+        if (kCount)
+            *nbox += 2;
         // a box is skipped only if it starts clearly beyond the best hit so far
         const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
         bool hitL, hitR;

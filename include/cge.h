@@ -155,7 +155,7 @@ enum {
                                     rule of src/bounding_volume_hierarchy.cpp:312-361 reproduced literally */
     CGE_TRAVERSAL_FAST = 1       /* binned-SAH tree (<= 4 primitives per leaf), near child first, conservative t culling,
                                     shadow rays stop at the first blocker; equal-t winner chosen by the reference's
-                                    visit rank.  Scenes with spheres and
+                                    visit rank; three-kernel wavefront over warp-compacted hit queues.  Scenes with spheres and
                                     !enableAccelStructure fall back to the literal traversal. */
 };
 enum {
@@ -165,11 +165,13 @@ enum {
     CGE_FLAG_WANT_PRIM_IDS = 1u << 0,
     CGE_FLAG_RGB_DEVICE_PTR = 1u << 1, /* rgb_out / prim_id_out are device pointers on the calling GPU:
                                           no D2H copy (kernel-only timing, or a caller that keeps the frame in HBM) */
-    CGE_FLAG_COUNT_TESTS = 1u << 2,    /* CGE_TRAVERSAL_REFERENCE only: fill cge_stats::box_tests / tri_tests (they
-                                          equal the reference's own intersectRayWithShape/Triangle call counts) */
-    CGE_FLAG_COOPERATIVE = 1u << 3     /* CGE_TRAVERSAL_FAST: use the warp-cooperative shadow-queue kernel instead of
-                                          the one-thread-per-pixel kernel.  It wins on sparse / low-resolution frames
-                                          and loses at the judged resolutions (DESIGN.md "Kernels"), hence opt-in. */
+    CGE_FLAG_COUNT_TESTS = 1u << 2,    /* fill cge_stats::box_tests / tri_tests (with CGE_TRAVERSAL_REFERENCE they equal
+                                          the reference's own intersectRayWithShape/Triangle call counts) */
+    CGE_FLAG_DEBUG_CYCLES = 1u << 4,   /* (implies the per-thread kernel) */
+    CGE_FLAG_PER_THREAD = 1u << 5,     /* CGE_TRAVERSAL_FAST: one-thread-per-pixel kernel instead of the wavefront pipeline */
+    CGE_FLAG_DEBUG_CYCLES_ = 0,   /* development aid: prim_id_out receives each pixel's cost (SM cycles >> 4) */
+    CGE_FLAG_COOPERATIVE = 1u << 3     /* CGE_TRAVERSAL_FAST: use the single-kernel warp-cooperative shadow-queue variant
+                                          instead of the wavefront pipeline (A/B measurements; DESIGN.md "Kernels") */
 };
 
 typedef struct cge_params {

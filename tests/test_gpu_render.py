@@ -43,7 +43,7 @@ def assert_parity(name, rgb, ids, ref_rgb, ref_ids, id_budget=ID_MISMATCH_BUDGET
 
 
 # (traversal, flags): literal traversal with test counters / fast tree per-thread kernel / fast tree cooperative kernel
-MODES = {"reference": (0, 4), "fast-thread": (1, 0), "fast-coop": (1, 8)}
+MODES = {"reference": (0, 4), "fast-wave": (1, 0), "fast-thread": (1, 32), "fast-coop": (1, 8)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
@@ -163,11 +163,13 @@ def test_full_size_properties(cge, name):
     with cge.Scene(cge.load_scene(cfg)) as sc:
         rgb_f, ids_f, st_f = sc.render(cfg, traversal=1)
         rgb_r, ids_r, st_r = sc.render(cfg, traversal=0)
-        rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_COOPERATIVE)
-        assert st_f["reference_rays"] == st_r["reference_rays"] == st_t["reference_rays"]
         assert (ids_f != ids_r).mean() <= ID_MISMATCH_BUDGET
-        # cooperative and per-thread kernels walk the same tree with the same arithmetic: identical bits
-        assert np.array_equal(ids_t, ids_f) and rgb_t.tobytes() == rgb_f.tobytes()
+        assert st_f["reference_rays"] == st_r["reference_rays"]
+        # wavefront, per-thread and cooperative kernels walk the same tree with the same arithmetic: identical bits
+        for fl in (cge.FLAG_PER_THREAD, cge.FLAG_COOPERATIVE):
+            rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=fl)
+            assert st_t["reference_rays"] == st_f["reference_rays"] and st_t["gpu_rays"] == st_f["gpu_rays"]
+            assert np.array_equal(ids_t, ids_f) and rgb_t.tobytes() == rgb_f.tobytes()
         err, nan_mm = compare_images(rgb_f, rgb_r)
         assert nan_mm <= ID_MISMATCH_BUDGET * ids_f.size
         differing = (np.abs(np.nan_to_num(rgb_f, nan=0.0) - np.nan_to_num(rgb_r, nan=0.0)).max(-1) > 1e-3).mean()

@@ -1,0 +1,36 @@
+"""torchrun target: N-GPU tile-partitioned render + NCCL gather must equal the 1-GPU frame bit for bit.
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py [cfg ...]"""
+import importlib, os, sys, json
+from pathlib import Path
+import numpy as np
+import torch, torch.distributed as dist
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+pkg = importlib.import_module("computer-graphics-engine_b200")
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+idt = torch.zeros(pkg.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt.copy_(torch.frombuffer(bytearray(pkg.Comm.unique_id()), dtype=torch.uint8))
+dist.broadcast(idt, 0)
+comm = pkg.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, local)
+ok = True
+for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_soft:0.5", "c5_dragon:0.25"]):
+    name, scale = (spec.split(":") + ["1.0"])[:2]
+    full = pkg.configs.get(name)
+    cfg = pkg.configs.get(name, int(full["width"] * float(scale)), int(full["height"] * float(scale)))
+    with pkg.Scene(pkg.load_scene(cfg), device=local) as sc:
+        rgb, ids, st = comm.render(sc, cfg, want_ids=True)
+        dist.barrier()
+        if rank == 0:
+            rgb1, ids1, st1 = sc.render(cfg, want_ids=True)
+            same = rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1)
+            ok &= same
+            print(json.dumps({"cfg": name, "w": cfg["width"], "h": cfg["height"], "ranks": world, "bit_identical_to_1gpu": bool(same),
+                              "dist_total_ms": round(st["total_ms"], 3), "dist_kernel_ms_rank0": round(st["kernel_ms"], 3),
+                              "single_kernel_ms": round(st1["kernel_ms"], 3), "launches_rank0": st["kernel_launches"]}), flush=True)
+        dist.barrier()
+comm.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
