@@ -34,7 +34,12 @@ __device__ __forceinline__ bool triangle_rows_hit(const float4* __restrict__ tr,
 {
     const float4 r0 = ldg4(tr);
     const vec3 n = v3(r0.x, r0.y, r0.z);
-    const float t = fdiv(fsub(r0.w, dot(o, n)), dot(d, n)); // I2
+    const float num = fsub(r0.w, dot(o, n)), den = dot(d, n);
+    // IEEE division gives sign(num) xor sign(den); when they differ and the quotient cannot underflow to -0 the
+    // archive's `t >= 0` is false, so the (10-instruction) division can be skipped without changing any decision.
+    if ((__float_as_uint(num) ^ __float_as_uint(den)) >> 31 && fabsf(num) >= 1e-30f && fabsf(den) <= 1e6f)
+        return false;
+    const float t = fdiv(num, den); // I2
     if (!(t >= 0.0f))
         return false;
     if (!(best >= t))
@@ -118,87 +123,81 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
     if (s.n_prims == 0)
         return h;
     unsigned bestRank = 0;
-    // The archive replaces the slab of an axis with d == 0 by the constants [FLT_MIN, FLT_MAX] whatever the origin
-    // (SURVEY.md Appendix A, I5); such rays take the exact box function so that no box the reference enters is skipped.
-    const bool exactBoxes = d.x == 0.0f || d.y == 0.0f || d.z == 0.0f;
-    const vec3 inv = v3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z));
+    // Reciprocal direction for the slab test.  For an axis with d == 0 the archive's box function substitutes the
+    // constants [FLT_MIN, FLT_MAX] whatever the origin, i.e. it never rejects on that axis.
+    // That quirk only ADDS box visits: a triangle can be hit only where the ray really passes, so every accepted hit
+    // lies inside the geometric slabs of all its ancestors' boxes.  The fast tree therefore uses ordinary slab
+    // semantics; a huge finite reciprocal (not inf) keeps 0 * inv == 0 instead of NaN when the origin lies exactly
+    // on a box face.
+    const vec3 inv = v3(d.x != 0.0f ? fdiv(1.0f, d.x) : 3.0e38f, d.y != 0.0f ? fdiv(1.0f, d.y) : 3.0e38f,
+        d.z != 0.0f ? fdiv(1.0f, d.z) : 3.0e38f);
 
     uint2 stack[kFastStackSize]; // (child ref, entry distance bits): re-culled against the best t when popped
     int sp = 0;
+    constexpr unsigned kDone = 0x7fffffffu; // not a valid inner-node index
     unsigned cur = s.froot;
-    auto pop = [&]() -> bool {
+    auto pop = [&]() -> unsigned {
         while (sp > 0) {
             const uint2 e = stack[--sp];
             if (__uint_as_float(e.y) > h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f)
                 continue;
-            cur = e.x;
-            return true;
+            return e.x;
         }
-        return false;
+        return kDone;
     };
-    for (;;) {
-        if (cur & 0x80000000u) {
-            const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+    // "while-while" traversal: all lanes of a warp walk inner nodes together, then all process their leaves together,
+    // so the two code paths are not interleaved lane by lane.
+    while (cur != kDone) {
+        while (cur < kDone) { // inner node (leaf references have bit 31 set)
+            const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
             if (kCount)
-                *ntri += count;
-            for (unsigned i = first; i < first + count; i++) {
-                float t;
-                float4 r5;
-                if (!triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, h.t, t, r5))
-                    continue;
-                const unsigned rank = __float_as_uint(r5.z);
-                if (t == h.t && h.prim >= 0 && rank < bestRank)
-                    continue; // an equal-t triangle the reference visits later is already held
-                h.t = t;
-                h.prim = int(i);
-                h.gid = __float_as_uint(r5.w);
-                bestRank = rank;
-                if (kAnyHit)
-                    return h;
-            }
-            if (!pop())
-                break;
-            continue;
-        }
-        const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
-        const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-        if (kCount)
-            *nbox += 2;
-        // a box is skipped only if it starts clearly beyond the best hit so far
-        const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
-        bool hitL, hitR;
-        float entL, entR;
-        if (!exactBoxes) {
+                *nbox += 2;
+            // a box is skipped only if it starts clearly beyond the best hit so far; the slab test carries a small
+            // multiplicative slack so that rounding can only ADD visits relative to the exact arithmetic
+            const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
             const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
             const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
             const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
-            entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+            const float entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
             const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
-            hitL = entL <= extL * 1.000002f && entL <= bound;
+            const bool hitL = entL <= extL * 1.000002f && entL <= bound;
             const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
             const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
             const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
-            entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+            const float entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
             const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
-            hitR = entR <= extR * 1.000002f && entR <= bound;
-        } else {
-            Ray ray { o, d, FLT_MAX };
-            hitL = intersect_aabb(v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), ray, &entL) && !(entL > bound);
-            ray.t = FLT_MAX;
-            hitR = intersect_aabb(v3(q1.z, q1.w, q2.x), v3(q2.y, q2.z, q2.w), ray, &entR) && !(entR > bound);
+            const bool hitR = entR <= extR * 1.000002f && entR <= bound;
+            const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+            const bool leftFirst = hitL && (!hitR || entL <= entR);
+            if (hitL && hitR)
+                stack[sp++] = leftFirst ? make_uint2(cr, __float_as_uint(entR)) : make_uint2(cl, __float_as_uint(entL));
+            if (hitL || hitR)
+                cur = leftFirst ? cl : cr;
+            else
+                cur = pop();
         }
-        const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
-        if (hitL && hitR) {
-            const bool leftFirst = entL <= entR;
-            stack[sp++] = leftFirst ? make_uint2(cr, __float_as_uint(entR)) : make_uint2(cl, __float_as_uint(entL));
-            cur = leftFirst ? cl : cr;
-        } else if (hitL) {
-            cur = cl;
-        } else if (hitR) {
-            cur = cr;
-        } else if (!pop()) {
+        if (cur == kDone)
             break;
+        const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+        if (kCount)
+            *ntri += count;
+        for (unsigned i = first; i < first + count; i++) {
+            float t;
+            float4 r5;
+            if (!triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, h.t, t, r5))
+                continue;
+            const unsigned rank = __float_as_uint(r5.z);
+            if (t == h.t && h.prim >= 0 && rank < bestRank)
+                continue; // an equal-t triangle the reference visits later is already held
+            h.t = t;
+            h.prim = int(i);
+            h.gid = __float_as_uint(r5.w);
+            bestRank = rank;
+            if (kAnyHit)
+                return h;
         }
+        cur = pop();
     }
     return h;
 }

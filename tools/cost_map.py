@@ -7,6 +7,8 @@ sys.path.insert(0, str(ROOT))
 pkg = importlib.import_module("computer-graphics-engine_b200")
 name = sys.argv[1]
 cfg = pkg.configs.get(name)
+if len(sys.argv) > 2:
+    cfg["features"] = int(sys.argv[2], 0)
 with pkg.Scene(pkg.load_scene(cfg)) as sc:
     sc.render(cfg)
     rgb, cost, st = sc.render(cfg, flags=16 | 32)
@@ -27,3 +29,7 @@ rows = tiles.sum(1)
 print("cost by tile-row decile (top of image first):", [round(float(x), 1) for x in (np.add.reduceat(rows, np.linspace(0, len(rows), 11)[:-1].astype(int)) / rows.sum() * 100)])
 hit = (ids >= 0)
 print("hit frac", hit.mean())
+ti = np.argsort(tiles.ravel())[::-1][:8]
+for i in ti:
+    r, c = np.unravel_index(i, tiles.shape)
+    print("hot tile row", r, "col", c, "cycles", tiles[r, c], "max box tests of a pixel in it", nb[r * 4:(r + 1) * 4, c * 8:(c + 1) * 8].max())
