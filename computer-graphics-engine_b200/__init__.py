@@ -357,6 +357,14 @@ def kat_point_in_triangle(v9, n3, p3, device=0):
     return out
 
 
+def partition_tiles(width: int, height: int, part_index: int, part_count: int) -> list:
+    """Tile ids (row-major 8x4 tiles) that cge_render renders for part_index / part_count — the host-side statement of
+    the multi-GPU image partition (csrc/render_kernels.cuh next_tile, csrc/cge_api.cu tiles_of)."""
+    n_tiles = ((width + 7) // 8) * ((height + 3) // 4)
+    part_count = max(part_count, 1)
+    return list(range(part_index if part_count > 1 else 0, n_tiles, part_count))
+
+
 def load_scene(cfg: dict) -> FlatScene:
     """Flat scene for a config: a committed .cges fixture, or the procedurally generated dragon stand-in."""
     if cfg["scene"].startswith("standin:"):

@@ -1,0 +1,7 @@
+#!/usr/bin/env bash
+# builds the headless C++ entry that uses the mirrored reference interface (host/cge_engine.hpp) on top of libcge.so
+set -euo pipefail
+HERE=$(cd "$(dirname "$0")" && pwd)
+REPO=$(cd "$HERE/../.." && pwd)
+g++ -std=c++17 -O2 -Wall -I"$REPO/include" -I"$REPO/computer-graphics-engine_b200/host" "$HERE/drop_in_main.cpp" \
+    -L"$REPO/computer-graphics-engine_b200" -lcge -Wl,-rpath,"$REPO/computer-graphics-engine_b200" -o "$HERE/drop_in_main"

@@ -234,3 +234,24 @@ def test_edge_cases(cge):
         with pytest.raises(cge.CgeError) as e:
             sc.render(C.get("c1_cornell", 16, 8))
         assert e.value.code == cge.ERR_UNSUPPORTED
+
+
+def test_partition_matches_host_tile_list(cge):
+    """cge_render with part_index/part_count touches exactly the tiles partition_tiles() lists (multi-GPU sharding)."""
+    cfg = cge.configs.get("c1_cornell", 100, 50)  # ragged in both directions
+    W, H = cfg["width"], cfg["height"]
+    ntx = (W + 7) // 8
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        for parts in (2, 3, 8):
+            for k in range(parts):
+                ids = np.full((H, W), -7, np.int32)
+                rgb = np.full((H, W, 3), -7.0, np.float32)
+                sc.render(cfg, rgb_out=rgb, ids_out=ids, part=(k, parts))
+                touched = ids != -7
+                expect = np.zeros((H, W), bool)
+                for t in cge.partition_tiles(W, H, k, parts):
+                    tx, ty = t % ntx, t // ntx
+                    y0, y1 = ty * 4, min(ty * 4 + 4, H)
+                    expect[H - y1:H - y0, tx * 8:min(tx * 8 + 8, W)] = True
+                assert np.array_equal(touched, expect), (parts, k)
+                assert np.array_equal((rgb != -7.0).all(-1) | np.isnan(rgb).any(-1), expect)
