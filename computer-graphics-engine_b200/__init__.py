@@ -62,12 +62,14 @@ class CgeStats(C.Structure):
     _fields_ = [
         ("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("reference_rays", C.c_uint64), ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
+        ("reference_shadow_rays", C.c_uint64),
         ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-        ("reserved", C.c_uint32 * 3),
+        ("stage_ms", C.c_float * 3),
     ]
 
     def as_dict(self) -> dict:
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "stage_ms"}
+        d["stage_ms"] = [float(x) for x in self.stage_ms]
         d["gpu_rays"] = d["primary_rays"] + d["bounce_rays"] + d["shadow_rays"]
         return d
 

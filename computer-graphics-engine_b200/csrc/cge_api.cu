@@ -79,7 +79,8 @@ struct Scratch {
     WaveBuffers wave {};
     size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;
+    bool staged = false; // evA..evC recorded by the last launch
     bool busy = false;
 };
 } // namespace
@@ -181,6 +182,9 @@ int acquire_scratch(cge_scene* sc, size_t pixels, bool wantIds, size_t gatherPix
         CGE_CUDA(cudaEventCreate(&s->ev0));
         CGE_CUDA(cudaEventCreate(&s->ev1));
         CGE_CUDA(cudaEventCreate(&s->ev2));
+        CGE_CUDA(cudaEventCreate(&s->evA));
+        CGE_CUDA(cudaEventCreate(&s->evB));
+        CGE_CUDA(cudaEventCreate(&s->evC));
         CGE_CUDA(cudaMalloc(&s->tileCounter, 64));
         CGE_CUDA(cudaMalloc(&s->counters, sizeof(Counters)));
     }
@@ -404,6 +408,7 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
     CGE_CUDA(cudaMemsetAsync(s->tileCounter, 0, 64, s->stream));
     CGE_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream));
     const Variant v = choose_variant(ds, *p, dp);
+    s->staged = false;
     const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
     cudaError_t err = cudaSuccess;
     auto grid_for = [&](int perSm) {
@@ -442,14 +447,18 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         if (err == cudaSuccess)
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
         if (err == cudaSuccess) {
+            cudaEventRecord(s->evA, s->stream);
             wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, dp, s->wave, rgbDev, idsDev, s->counters);
             err = cudaGetLastError();
+            cudaEventRecord(s->evB, s->stream);
         }
         if (err == cudaSuccess)
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel, 128, 0);
         if (err == cudaSuccess) {
             wf_shade_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
             err = cudaGetLastError();
+            cudaEventRecord(s->evC, s->stream);
+            s->staged = true;
         }
         if (err == cudaSuccess) {
             wf_fold_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(dp, s->wave, rgbDev);
@@ -497,12 +506,18 @@ int fill_stats(Scratch* s, cge_stats* st, uint32_t launches)
     st->reference_rays = c.reference;
     st->box_tests = c.box;
     st->tri_tests = c.tri;
+    st->reference_shadow_rays = c.reference_shadow;
     float ms = 0.f;
     CGE_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     st->kernel_ms = ms;
     CGE_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev2));
     st->total_ms = ms;
     st->kernel_launches = launches;
+    if (s->staged) {
+        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[0], s->evA, s->evB));
+        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[1], s->evB, s->evC));
+        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[2], s->evC, s->ev1));
+    }
     return CGE_OK;
 }
 
@@ -858,6 +873,12 @@ int cge_scene_destroy(cge_scene* sc)
             cudaEventDestroy(s->ev1);
         if (s->ev2)
             cudaEventDestroy(s->ev2);
+        if (s->evA)
+            cudaEventDestroy(s->evA);
+        if (s->evB)
+            cudaEventDestroy(s->evB);
+        if (s->evC)
+            cudaEventDestroy(s->evC);
         if (s->stream)
             cudaStreamDestroy(s->stream);
         delete s;

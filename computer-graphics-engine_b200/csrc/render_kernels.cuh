@@ -30,14 +30,14 @@ constexpr int kMaxLevels = kMaxRayDepth + 1;
 #endif
 
 struct Counters {
-    unsigned long long primary, bounce, shadow, reference, box, tri;
+    unsigned long long primary, bounce, shadow, reference, box, tri, reference_shadow;
 };
 
 __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g)
 {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&c);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(g);
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 7; k++) {
         unsigned long long v = src[k];
         for (int off = 16; off > 0; off >>= 1)
             v += __shfl_down_sync(0xffffffffu, v, off);
@@ -47,14 +47,15 @@ __device__ __forceinline__ void flush_counters(const Counters& c, Counters* g)
 }
 
 // reference-equivalent BvhInterface::intersect calls of one pixel: level k is visited 2^k times
-__device__ __forceinline__ unsigned long long reference_calls(int n, bool missEnd, unsigned shadowPerHit)
+__device__ __forceinline__ void reference_calls(Counters& c, int n, bool missEnd, unsigned shadowPerHit)
 {
     unsigned long long calls = 0;
     for (int k = 0; k < n; k++)
         calls += (1ull << k) * (1ull + shadowPerHit);
     if (missEnd)
         calls += 1ull << n;
-    return calls;
+    c.reference += calls;
+    c.reference_shadow += ((1ull << n) - 1ull) * shadowPerHit;
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -164,7 +165,7 @@ struct PixelTracer {
                 break;
             ray = next;
         }
-        cnt.reference += reference_calls(n, missEnd, p.shadow_rays_per_hit);
+        reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
         if (n == 0)
             return v3(0.0f);
         if (fold) {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_COOP) render_coop_kernel(DevScen
                     break;
                 ray = next;
             }
-            cnt.reference += reference_calls(n, missEnd, p.shadow_rays_per_hit);
+            reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
         }
         // ---- phase B: direct lighting of every (pixel, level, copy), dealt out to all lanes --------------------------
         const unsigned myUnits = fold ? unsigned(n) : ((1u << n) - 1u);

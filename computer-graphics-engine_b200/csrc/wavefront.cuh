@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128, 6) wf_chain_kernel(DevScene s, DevCamera 
             }
         }
         if (live) {
-            cnt.reference += reference_calls(n, missEnd, p.shadow_rays_per_hit);
+            reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
             const unsigned tag = unsigned(n) | (missEnd ? 256u : 0u);
             for (int k = 0; k < n; k++)
                 wb.meta[size_t(k) * wb.cap + slots[k]] = make_uint2(pixel, tag);

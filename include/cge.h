@@ -198,10 +198,11 @@ typedef struct cge_stats {
     uint64_t reference_rays;  /* BvhInterface::intersect calls the reference would have made for this frame
                                  (duplicate reflection subtrees counted, src/render.cpp:100,118) */
     uint64_t box_tests, tri_tests; /* only filled with CGE_FLAG_COUNT_TESTS */
+    uint64_t reference_shadow_rays; /* the part of reference_rays made from testVisibilityLightSample (src/light.cpp:61) */
     float kernel_ms;          /* device time of the render kernels (CUDA events on the call's stream) */
     float total_ms;           /* device time including uploads of camera/params and the D2H copy     */
     uint32_t kernel_launches; /* kernels launched by this call                                        */
-    uint32_t reserved[3];
+    float stage_ms[3];        /* wavefront pipeline: wf_chain / wf_shade / wf_fold device times; 0 otherwise */
 } cge_stats;
 
 typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene + BVH on ONE GPU */
