@@ -309,6 +309,14 @@ def main():
     ms_per_step = total_s / args.steps * 1e3
     value = ref_rays / ms_per_step / 1e3
 
+    # fast-tree test counts of this frame (one untimed counting render, per-thread kernel: 64 B per node visit = two box
+    # tests, first 16-byte row per triangle test) -> the bytes OUR traversal requests, beside the reference-defined figure
+    fast_counts = None
+    if world == 1:
+        stc = scene.render_device(cfg, frame_dev.data_ptr(), camera=cam, flags=pkg.FLAG_COUNT_TESTS | pkg.FLAG_PER_THREAD)
+        fast_counts = {"box_tests_per_ray": stc["box_tests"] / max(stc["gpu_rays"], 1),
+                       "tri_tests_per_ray": stc["tri_tests"] / max(stc["gpu_rays"], 1)}
+
     e2e_total_s, st_e, _, _ = timed(step_e2e, max(args.warmup, 1), args.steps)
     e2e_ms = e2e_total_s / args.steps * 1e3
     e2e_value = ref_rays / e2e_ms / 1e3
@@ -378,6 +386,12 @@ def main():
                                  "pipeline": pipeline_ms},
                     "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_ray": bytes_per_ray,
                     "box_tests_per_ray": box_per_ray, "tri_tests_per_ray": tri_per_ray,
+                    "fast_tree": None if not fast_counts else {
+                        **fast_counts,
+                        "requested_bytes_per_ray": 32.0 * fast_counts["box_tests_per_ray"] + 16.0 * fast_counts["tri_tests_per_ray"],
+                        "requested_gbs": float(cnt[4]) * (32.0 * fast_counts["box_tests_per_ray"] + 16.0 * fast_counts["tri_tests_per_ray"])
+                                         / (shade_ms * 1e-3) / 1e9,
+                        "note": "bytes the SAH traversal itself requests (L1/L2-served; ncu DRAM traffic is in `traffic`)"},
                     "whole_frame": {"algorithmic_bytes": ref_rays / world * bytes_per_ray + 12.0 * W * H / world,
                                     "achieved_gbs": (ref_rays / world * bytes_per_ray + 12.0 * W * H / world) / (pipeline_ms * 1e-3) / 1e9},
                     "note": "algorithmic bytes are those of the reference's EXHAUSTIVE traversal (SURVEY.md 8d); the fast tree "
