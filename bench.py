@@ -367,7 +367,7 @@ def main():
         # box/triangle traffic for the shadow rays this launch covers (32 B per box test, 48 B per triangle
         # test, per-ray counts from the reference's ld --wrap counters on sampled rows of this very frame).
         bytes_per_ray = BYTES_PER_BOX_TEST * box_per_ray + BYTES_PER_TRI_TEST * tri_per_ray
-        pipeline_ms, chain_ms, shade_ms, fold_ms = [float(x) for x in kms]
+        pipeline_ms, chain_ms, vis_ms, shade_ms, fold_ms = [float(x) for x in kms]
         shadow_ref_rays = float(cnt[5])
         algo_bytes = shadow_ref_rays / world * bytes_per_ray
         traffic = None
@@ -382,7 +382,8 @@ def main():
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel": "cge::wf_shade_kernel",
                     "kernel_ms": shade_ms, "share_of_step": shade_ms / ms_per_step,
-                    "stage_ms": {"wf_chain_kernel": chain_ms, "wf_shade_kernel": shade_ms, "wf_fold_kernel": fold_ms,
+                    "stage_ms": {"wf_chain_kernel": chain_ms, "wf_visibility_kernel (opt-in, 0 = not run)": vis_ms,
+                                 "wf_shade_kernel": shade_ms, "wf_fold_kernel": fold_ms,
                                  "pipeline": pipeline_ms},
                     "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_ray": bytes_per_ray,
                     "box_tests_per_ray": box_per_ray, "tri_tests_per_ray": tri_per_ray,

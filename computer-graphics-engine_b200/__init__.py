@@ -22,7 +22,7 @@ LIB_PATH = Path(os.environ.get("CGE_LIB", _PKG / "libcge.so"))  # CGE_LIB: devel
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
 FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1, 2, 4, 8
-FLAG_DEBUG_CYCLES, FLAG_PER_THREAD = 16, 32
+FLAG_DEBUG_CYCLES, FLAG_PER_THREAD, FLAG_DECOUPLED_SHADE = 16, 32, 64
 UNIQUE_ID_BYTES = 128
 
 
@@ -64,7 +64,7 @@ class CgeStats(C.Structure):
         ("reference_rays", C.c_uint64), ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
         ("reference_shadow_rays", C.c_uint64),
         ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-        ("stage_ms", C.c_float * 3),
+        ("stage_ms", C.c_float * 4),
     ]
 
     def as_dict(self) -> dict:

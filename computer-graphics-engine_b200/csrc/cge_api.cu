@@ -77,9 +77,9 @@ struct Scratch {
     size_t gatherPixels = 0;
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
-    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0;
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
     bool staged = false; // evA..evC recorded by the last launch
     bool busy = false;
 };
@@ -185,6 +185,7 @@ int acquire_scratch(cge_scene* sc, size_t pixels, bool wantIds, size_t gatherPix
         CGE_CUDA(cudaEventCreate(&s->evA));
         CGE_CUDA(cudaEventCreate(&s->evB));
         CGE_CUDA(cudaEventCreate(&s->evC));
+        CGE_CUDA(cudaEventCreate(&s->evD));
         CGE_CUDA(cudaMalloc(&s->tileCounter, 64));
         CGE_CUDA(cudaMalloc(&s->counters, sizeof(Counters)));
     }
@@ -307,13 +308,14 @@ constexpr size_t kCoopSmemLimit = 96 * 1024; // per 128-thread CTA: keeps >= 2 C
 constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than this fall back to the per-thread kernel
 
 struct WaveSizes {
-    size_t recFloats, meta, next, dirFloats;
-    size_t bytes() const { return recFloats * 4 + meta * 8 + next * 4 + dirFloats * 4; }
+    size_t recFloats, meta, next, dirFloats, vis;
+    size_t bytes() const { return recFloats * 4 + meta * 8 + next * 4 + dirFloats * 4 + vis; }
 };
 WaveSizes wave_sizes(const DevParams& dp, size_t cap)
 {
     WaveSizes w;
-    w.recFloats = size_t(dp.levels) * kRecFloats * cap;
+    w.vis = size_t(dp.units_per_lane) * std::max<size_t>(dp.samples_per_hit, 1) * cap; // one byte per light sample
+    w.recFloats = size_t(dp.levels) * kWaveRecFloats * cap;
     w.meta = size_t(dp.levels) * cap;
     w.next = size_t(dp.levels) * cap;
     w.dirFloats = size_t(dp.units_per_lane) * 3 * cap;
@@ -438,6 +440,10 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
             err = grow(s->wave.next, s->waveNext, ws.next, sizeof(unsigned));
         if (err == cudaSuccess)
             err = grow(s->wave.dir, s->waveDirFloats, ws.dirFloats, sizeof(float));
+        // the decoupled visibility pass indexes rays with 32 bits
+        const bool decoupled = (p->flags & CGE_FLAG_DECOUPLED_SHADE) && dp.samples_per_hit >= 1 && ws.vis < (size_t(1) << 32);
+        if (err == cudaSuccess && decoupled)
+            err = grow(s->wave.vis, s->waveVis, ws.vis, 1);
         if (err == cudaSuccess && !s->wave.counts)
             err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 32 * sizeof(unsigned));
         if (err == cudaSuccess)
@@ -452,12 +458,22 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
             err = cudaGetLastError();
             cudaEventRecord(s->evB, s->stream);
         }
+        if (err == cudaSuccess && decoupled) {
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_visibility_kernel, 128, 0);
+            if (err == cudaSuccess) {
+                wf_visibility_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
+        }
+        cudaEventRecord(s->evC, s->stream);
+        auto shade = decoupled ? wf_shade_kernel<true> : wf_shade_kernel<false>;
         if (err == cudaSuccess)
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel, 128, 0);
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, shade, 128, 0);
         if (err == cudaSuccess) {
-            wf_shade_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
+            shade<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
             err = cudaGetLastError();
-            cudaEventRecord(s->evC, s->stream);
+            cudaEventRecord(s->evD, s->stream);
             s->staged = true;
         }
         if (err == cudaSuccess) {
@@ -516,7 +532,8 @@ int fill_stats(Scratch* s, cge_stats* st, uint32_t launches)
     if (s->staged) {
         CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[0], s->evA, s->evB));
         CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[1], s->evB, s->evC));
-        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[2], s->evC, s->ev1));
+        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[2], s->evC, s->evD));
+        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[3], s->evD, s->ev1));
     }
     return CGE_OK;
 }
@@ -866,6 +883,7 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.meta);
         cudaFree(s->wave.next);
         cudaFree(s->wave.dir);
+        cudaFree(s->wave.vis);
         cudaFree(s->wave.counts);
         if (s->ev0)
             cudaEventDestroy(s->ev0);
@@ -879,6 +897,8 @@ int cge_scene_destroy(cge_scene* sc)
             cudaEventDestroy(s->evB);
         if (s->evC)
             cudaEventDestroy(s->evC);
+        if (s->evD)
+            cudaEventDestroy(s->evD);
         if (s->stream)
             cudaStreamDestroy(s->stream);
         delete s;

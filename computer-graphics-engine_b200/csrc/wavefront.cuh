@@ -18,7 +18,8 @@
 //                    direct terms (reference src/render.cpp:100,118: Lo = (direct + R1) + R2) and writes the pixel.
 //
 // Queue layout (cap = pixels covered by this launch):
-//   rec   [level][kRecFloats][cap] float   hit record, structure of arrays
+//   rec   [level][kWaveRecFloats][cap] float   hit record + shadow-ray origin, structure of arrays
+//   vis   [ray index] u8                   ray index = level offset + ((copy * S + sample) * count[level]) + slot
 //   meta  [level][cap] uint2                .x = pixel index (y*W + x, reference coordinates), .y = n | missEnd << 8
 //   next  [level][cap] uint                 queue slot of the same pixel at level+1 (valid while level+1 < n)
 //   dir   block of level k at dirOff(k): [copy][3][cap] float
@@ -27,12 +28,15 @@
 
 namespace cge {
 
+constexpr int kWaveRecFloats = kRecFloats + 3; // hit record + the shadow-ray origin of src/light.cpp:54-58 (hoisted)
+
 struct WaveBuffers {
     float* rec;
     uint2* meta;
     unsigned* next;
     float* dir;
-    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter
+    unsigned char* vis; // one byte per (level, copy, sample, slot): 1 = light sample visible
+    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] ray counter
     unsigned cap;
 };
 
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(128, 6) wf_chain_kernel(DevScene s, DevCamera 
                 ray.t = h.t;
                 HitRec r;
                 resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
-                float* b = wb.rec + (size_t(level) * kRecFloats) * wb.cap + slot;
+                float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + slot;
                 const size_t c = wb.cap;
                 b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
                 b[3 * c] = r.ray.d.x, b[4 * c] = r.ray.d.y, b[5 * c] = r.ray.d.z;
@@ -96,6 +100,8 @@ __global__ void __launch_bounds__(128, 6) wf_chain_kernel(DevScene s, DevCamera 
                 b[10 * c] = r.m.kd.x, b[11 * c] = r.m.kd.y, b[12 * c] = r.m.kd.z;
                 b[13 * c] = r.m.ks.x, b[14 * c] = r.m.ks.y, b[15 * c] = r.m.ks.z;
                 b[16 * c] = r.m.shininess;
+                const vec3 so = shadow_origin(r);
+                b[17 * c] = so.x, b[18 * c] = so.y, b[19 * c] = so.z;
                 if (level > 0)
                     wb.next[size_t(level - 1) * wb.cap + slots[level - 1]] = slot;
                 else if (ids)
@@ -120,12 +126,15 @@ __global__ void __launch_bounds__(128, 6) wf_chain_kernel(DevScene s, DevCamera 
     flush_counters(cnt, gcnt);
 }
 
-// computeLightContribution for one (pixel, level, copy): same arithmetic and order as PixelTracer::direct
+// computeLightContribution for one (pixel, level, copy): same arithmetic and order as PixelTracer::direct.
+// kLookup: visibilities were traced by wf_visibility_kernel; vis points at this evaluation's sample 0, stride = queue length.
+template <bool kLookup>
 __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p, const HitRec& h, unsigned pixel, unsigned ctr,
-    unsigned long long& nshadow)
+    unsigned long long& nshadow, const unsigned char* __restrict__ vis, size_t visStride)
 {
-    const vec3 sp = shadow_origin(h);
+    const vec3 sp = kLookup ? v3(0.0f) : shadow_origin(h);
     vec3 result = v3(0.0f);
+    unsigned sg = 0; // running sample index over all lights
     for (unsigned li = 0; li < s.n_lights; li++) {
         const float* L = s.lights + size_t(li) * kLightFloats;
         const unsigned type = __float_as_uint(__ldg(L));
@@ -134,29 +143,233 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
         if (type == CGE_LIGHT_POINT) {
             const LightSample ls = sample_light(L, type, 0, p, pixel, ctr);
             const vec3 c = compute_shading(ls.pos, ls.col, h);
-            float vis = 1.0f;
-            if (ls.shadowed) {
+            float v = 1.0f;
+            if (kLookup) {
+                v = vis[size_t(sg) * visStride] ? 1.0f : 0.0f;
+            } else if (ls.shadowed) {
                 nshadow++;
-                vis = trace_fast<true>(s, sp, ls.pos - sp, 1.0f).prim >= 0 ? 0.0f : 1.0f;
+                v = trace_fast<true>(s, sp, ls.pos - sp, 1.0f).prim >= 0 ? 0.0f : 1.0f;
             }
-            result = result + c * vis;
+            result = result + c * v;
         } else if (samples) {
             vec3 color = v3(0.0f);
             for (unsigned si = 0; si < samples; si++) {
                 const LightSample ls = sample_light(L, type, int(si), p, pixel, ctr);
-                nshadow++;
-                const float vis = trace_fast<true>(s, sp, ls.pos - sp, 1.0f).prim >= 0 ? 0.0f : 1.0f;
-                color = color + compute_shading(ls.pos, ls.col, h) * vis;
+                float v;
+                if (kLookup) {
+                    v = vis[size_t(sg + si) * visStride] ? 1.0f : 0.0f;
+                } else {
+                    nshadow++;
+                    v = trace_fast<true>(s, sp, ls.pos - sp, 1.0f).prim >= 0 ? 0.0f : 1.0f;
+                }
+                color = color + compute_shading(ls.pos, ls.col, h) * v;
             }
             const float denom = type == CGE_LIGHT_SEGMENT ? float(p.segment_samples)
                                                           : fmul(float(p.parallelogram_samples), float(p.parallelogram_samples));
             result = result + color / denom;
         }
         ctr += draws;
+        sg += samples;
     }
     return result;
 }
 
+// first rand() draw index of the direct-lighting evaluation (level k, copy `path`) of a chain with n hit levels, in the
+// reference's depth-first order over its 2-ary recursion:  index = sum_{i=1..k} (1 + b_i * (2^(n-i) - 1)),
+// b_i = i-th copy choice on the way down (src/render.cpp:33,100,118)
+__device__ __forceinline__ unsigned wf_draw_base(const DevParams& p, unsigned k, unsigned path, unsigned nChain)
+{
+    if (p.draws_per_hit == 0)
+        return 0;
+    unsigned idx = 0;
+    for (unsigned i = 1; i <= k; i++) {
+        const unsigned b = (path >> (k - i)) & 1u;
+        idx += 1u + b * ((1u << (nChain - i)) - 1u);
+    }
+    return idx * p.draws_per_hit;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wf_visibility_kernel: every shadow ray of the frame, one ray per lane, lanes DECOUPLED.
+// In wf_shade_kernel<false> a lane owns 16 consecutive shadow rays and the warp waits for its slowest lane on every one of
+// them; ncu (profiles/r01_wf_shade_c5.txt) shows the traversal loop running at 11 of 32 threads because occluded rays end
+// after a few nodes while their unoccluded neighbours walk ~40.  Here a lane that finishes its ray simply takes the next
+// one: lanes that are out of work are counted with __ballot_sync and, once kRefill of them wait (or nothing is in flight),
+// ONE atomicAdd hands each a new ray index (consecutive indices = neighbouring pixels, same sample).  The result is one
+// byte per ray; the arithmetic-order-sensitive part (shading and the ordered sums) runs afterwards in
+// wf_shade_kernel<true>, fully convergent.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef CGE_REFILL
+#define CGE_REFILL 10
+#endif
+#ifndef CGE_INNER_MIN
+#define CGE_INNER_MIN 12
+#endif
+constexpr unsigned kRefill = CGE_REFILL;      // refill when this many lanes have no ray in flight
+constexpr unsigned kInnerMin = CGE_INNER_MIN; // keep stepping inner nodes while this many lanes are on one
+
+__global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const bool fold = p.draws_per_hit == 0;
+    const unsigned S = p.samples_per_hit;
+    // direct-lighting evaluations ("units") are numbered like wf_shade_kernel's work items
+    unsigned cum[kMaxLevels + 1];
+    cum[0] = 0;
+    for (unsigned k = 0; k < p.levels; k++)
+        cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
+    const unsigned totalUnits = cum[p.levels];
+    unsigned long long nshadow = 0;
+    constexpr unsigned kDone = 0x7fffffffu;
+
+    // per-lane state: the unit being evaluated, the sample whose ray is in flight, and that ray's traversal state
+    bool haveUnit = false, busy = false, drained = false;
+    unsigned pixel = 0, ctrBase = 0, sg = 0;       // sg = sample index within the unit (over all lights)
+    unsigned char* visOut = nullptr;                // this unit's sample 0
+    size_t visStride = 0;
+    vec3 o = v3(0.0f), d = v3(0.0f), inv = v3(0.0f);
+    unsigned stack[kFastStackSize];
+    int sp = 0;
+    unsigned cur = kDone;
+
+    for (;;) {
+        // ---- A. lanes without a ray in flight take their unit's next sample, or a new unit ----------------------------
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle == 0xffffffffu || unsigned(__popc(idle)) >= kRefill || drained) {
+            bool needUnit = !busy && (!haveUnit || sg >= S);
+            const unsigned want = __ballot_sync(0xffffffffu, needUnit && !drained);
+            if (want) {
+                unsigned base = 0;
+                if (lane == 0)
+                    base = atomicAdd(wb.counts + 18, unsigned(__popc(want)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + unsigned(__popc(want)) >= totalUnits)
+                    drained = true; // warp-uniform: every unit of the frame has been handed out
+                const unsigned u = base + unsigned(__popc(want & below));
+                if (needUnit) {
+                    haveUnit = u < totalUnits;
+                    if (haveUnit) {
+                        unsigned k = 0;
+                        while (u >= cum[k + 1])
+                            k++;
+                        const unsigned inLevel = u - cum[k], cnt = wb.counts[k];
+                        const unsigned path = inLevel / cnt, e = inLevel - path * cnt;
+                        const uint2 m = wb.meta[size_t(k) * wb.cap + e];
+                        pixel = m.x;
+                        ctrBase = wf_draw_base(p, k, path, m.y & 255u);
+                        const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
+                        o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
+                        visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
+                        visStride = cnt;
+                        sg = 0;
+                    }
+                }
+            } else if (needUnit) {
+                haveUnit = false;
+            }
+            if (!busy && haveUnit && sg < S) {
+                // sample sg -> (light, sample within the light, first draw of that light)
+                unsigned li = 0, si = sg, samples = 0, draws = 0, type = 0, ctr = ctrBase;
+                const float* L = s.lights;
+                for (;; li++) {
+                    L = s.lights + size_t(li) * kLightFloats;
+                    type = __float_as_uint(__ldg(L));
+                    light_counts(type, p, samples, draws);
+                    if (si < samples)
+                        break;
+                    si -= samples;
+                    ctr += draws;
+                }
+                const LightSample ls = sample_light(L, type, int(si), p, pixel, ctr);
+                if (!ls.shadowed) {
+                    visOut[size_t(sg) * visStride] = 1; // the reference does not test this sample
+                    sg++;
+                } else {
+                    d = ls.pos - o;
+                    inv = v3(d.x != 0.0f ? fdiv(1.0f, d.x) : 3.0e38f, d.y != 0.0f ? fdiv(1.0f, d.y) : 3.0e38f,
+                        d.z != 0.0f ? fdiv(1.0f, d.z) : 3.0e38f);
+                    cur = s.n_prims ? s.froot : kDone;
+                    sp = 0;
+                    busy = true;
+                    nshadow++;
+                    if (cur == kDone) { // empty scene: nothing can block
+                        visOut[size_t(sg) * visStride] = 1;
+                        sg++;
+                        busy = false;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, busy) == 0) {
+            if (drained && __ballot_sync(0xffffffffu, haveUnit && sg < S) == 0)
+                break;
+            continue;
+        }
+        // ---- B. inner nodes: step every lane that is on one, while enough of them are -----------------------------------
+        for (;;) {
+            const bool onInner = busy && cur < kDone;
+            const unsigned nInner = unsigned(__popc(__ballot_sync(0xffffffffu, onInner)));
+            const unsigned nBusy = unsigned(__popc(__ballot_sync(0xffffffffu, busy)));
+            if (nInner == 0 || (nInner < kInnerMin && nBusy > nInner) || (!drained && 32u - nBusy >= kRefill))
+                break;
+            if (onInner) { // same slab test as trace_fast with the constant bound t <= 1
+                const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+                const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+                const float bound = 1.0001f;
+                const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
+                const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
+                const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
+                const float entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+                const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+                const bool hitL = entL <= extL * 1.000002f && entL <= bound;
+                const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
+                const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
+                const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
+                const float entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+                const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+                const bool hitR = entR <= extR * 1.000002f && entR <= bound;
+                const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+                const bool leftFirst = hitL && (!hitR || entL <= entR);
+                if (hitL && hitR)
+                    stack[sp++] = leftFirst ? cr : cl;
+                if (hitL || hitR) {
+                    cur = leftFirst ? cl : cr;
+                } else if (sp > 0) {
+                    cur = stack[--sp];
+                } else { // walked everything along the ray: the sample is visible
+                    visOut[size_t(sg) * visStride] = 1;
+                    sg++;
+                    busy = false;
+                    cur = kDone;
+                }
+            }
+        }
+        // ---- C. leaves: every lane that reached one tests its triangles (the archive's test against t <= 1) --------------
+        if (busy && cur > kDone) {
+            const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+            bool occluded = false;
+            for (unsigned i = first; i < first + count && !occluded; i++) {
+                float t;
+                float4 r5;
+                occluded = triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, 1.0f, t, r5);
+            }
+            if (occluded || sp == 0) {
+                visOut[size_t(sg) * visStride] = occluded ? 0 : 1;
+                sg++;
+                busy = false;
+                cur = kDone;
+            } else {
+                cur = stack[--sp];
+            }
+        }
+    }
+    Counters cnt {};
+    cnt.shadow = nshadow;
+    flush_counters(cnt, gcnt);
+}
+
+template <bool kLookup>
 __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
 {
     const unsigned lane = threadIdx.x & 31;
@@ -168,6 +381,7 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
         cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
     const unsigned total = cum[p.levels];
     unsigned long long nshadow = 0;
+    const unsigned S = p.samples_per_hit;
     for (;;) {
         unsigned chunk = 0;
         if (lane == 0)
@@ -188,18 +402,8 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
         const unsigned path = inLevel / cnt, e = inLevel - path * cnt;
         const uint2 m = wb.meta[size_t(k) * wb.cap + e];
         const unsigned nChain = m.y & 255u;
-        unsigned ctr = 0;
-        if (!fold) {
-            // first draw index of this evaluation in the reference's depth-first order over the 2-ary recursion:
-            // index = sum_{i=1..k} (1 + b_i * (2^(n-i) - 1)),  b_i = i-th copy choice on the way down
-            unsigned idx = 0;
-            for (unsigned i = 1; i <= k; i++) {
-                const unsigned b = (path >> (k - i)) & 1u;
-                idx += 1u + b * ((1u << (nChain - i)) - 1u);
-            }
-            ctr = idx * p.draws_per_hit;
-        }
-        const float* b = wb.rec + (size_t(k) * kRecFloats) * wb.cap + e;
+        const unsigned ctr = wf_draw_base(p, k, path, nChain);
+        const float* b = wb.rec + (size_t(k) * kWaveRecFloats) * wb.cap + e;
         const size_t c = wb.cap;
         HitRec h;
         h.ray.o = v3(b[0 * c], b[1 * c], b[2 * c]);
@@ -209,7 +413,9 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
         h.m.kd = v3(b[10 * c], b[11 * c], b[12 * c]);
         h.m.ks = v3(b[13 * c], b[14 * c], b[15 * c]);
         h.m.shininess = b[16 * c];
-        const vec3 d = wf_direct(s, p, h, m.x, ctr, nshadow);
+        // ray index of this evaluation's sample 0 (see wf_visibility_kernel); consecutive samples are cnt bytes apart
+        const unsigned char* vis = kLookup ? wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e) : nullptr;
+        const vec3 d = wf_direct<kLookup>(s, p, h, m.x, ctr, nshadow, vis, cnt);
         float* out = wb.dir + wf_dir_off(p, wb.cap, k) + (size_t(path) * 3u) * wb.cap + e;
         out[0] = d.x;
         out[c] = d.y;

@@ -168,7 +168,11 @@ enum {
     CGE_FLAG_COUNT_TESTS = 1u << 2,    /* fill cge_stats::box_tests / tri_tests (with CGE_TRAVERSAL_REFERENCE they equal
                                           the reference's own intersectRayWithShape/Triangle call counts) */
     CGE_FLAG_DEBUG_CYCLES = 1u << 4,   /* (implies the per-thread kernel) */
-    CGE_FLAG_PER_THREAD = 1u << 5,     /* CGE_TRAVERSAL_FAST: one-thread-per-pixel kernel instead of the wavefront pipeline */
+    CGE_FLAG_PER_THREAD = 1u << 5,
+    CGE_FLAG_DECOUPLED_SHADE = 1u << 6, /* wavefront: trace the shadow rays in the lane-decoupled wf_visibility_kernel (one ray
+                                          per lane, idle lanes refilled through ballot + one atomic) and shade from its
+                                          visibility bytes, instead of 16 coupled rays per lane inside wf_shade_kernel.
+                                          Wins on small / sparse frames, loses ~15 % at the judged sizes */     /* CGE_TRAVERSAL_FAST: one-thread-per-pixel kernel instead of the wavefront pipeline */
     CGE_FLAG_DEBUG_CYCLES_ = 0,   /* development aid: prim_id_out receives each pixel's cost (SM cycles >> 4) */
     CGE_FLAG_COOPERATIVE = 1u << 3     /* CGE_TRAVERSAL_FAST: use the single-kernel warp-cooperative shadow-queue variant
                                           instead of the wavefront pipeline (A/B measurements; DESIGN.md "Kernels") */
@@ -202,7 +206,7 @@ typedef struct cge_stats {
     float kernel_ms;          /* device time of the render kernels (CUDA events on the call's stream) */
     float total_ms;           /* device time including uploads of camera/params and the D2H copy     */
     uint32_t kernel_launches; /* kernels launched by this call                                        */
-    float stage_ms[3];        /* wavefront pipeline: wf_chain / wf_shade / wf_fold device times; 0 otherwise */
+    float stage_ms[4];        /* wavefront pipeline: wf_chain / wf_visibility / wf_shade / wf_fold device times */
 } cge_stats;
 
 typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene + BVH on ONE GPU */
