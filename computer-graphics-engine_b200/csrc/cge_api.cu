@@ -20,6 +20,10 @@
 #include "render_kernels.cuh"
 #include "wavefront.cuh"
 
+#ifndef CGE_GROUP
+#define CGE_GROUP 4 // shadow rays per lane in wf_vis_grouped_kernel (A/B in DESIGN.md 5.3)
+#endif
+
 using namespace cge;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -305,6 +309,7 @@ struct Variant {
 };
 
 constexpr size_t kCoopSmemLimit = 96 * 1024; // per 128-thread CTA: keeps >= 2 CTAs per SM
+constexpr size_t kGroupedThreshold = 24; // worst-case 32-unit chunks per resident warp below which shadow rays are traced 4 per lane
 constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than this fall back to the per-thread kernel
 
 struct WaveSizes {
@@ -440,9 +445,27 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
             err = grow(s->wave.next, s->waveNext, ws.next, sizeof(unsigned));
         if (err == cudaSuccess)
             err = grow(s->wave.dir, s->waveDirFloats, ws.dirFloats, sizeof(float));
-        // the decoupled visibility pass indexes rays with 32 bits
-        const bool decoupled = (p->flags & CGE_FLAG_DECOUPLED_SHADE) && dp.samples_per_hit >= 1 && ws.vis < (size_t(1) << 32);
-        if (err == cudaSuccess && decoupled)
+        // Shadow-ray granularity.  Default: 16 coupled rays per lane inside wf_shade_kernel<false>.  When the launch has few
+        // direct-lighting evaluations per resident warp (small frames, one rank's share of a multi-GPU frame) the tail of
+        // that coarse granularity dominates, so the rays are traced in groups of 4 per lane (wf_vis_grouped_kernel) into
+        // visibility bytes and shaded by wf_shade_kernel<true>.  The choice needs the queue lengths, which only exist on the
+        // device: both variants are launched and each kernel returns at once unless it is the selected one (no host sync).
+        const bool visFits = dp.samples_per_hit >= 1 && ws.vis < (size_t(1) << 32);
+        DevParams wp = dp;
+        wp.grouped_below_chunks = uint32_t(size_t(sc->sm_count) * 32 * kGroupedThreshold);
+        if ((p->flags & CGE_FLAG_DECOUPLED_SHADE) && visFits)
+            wp.shade_mode = 3;
+        else if ((p->flags & CGE_FLAG_GROUPED_SHADE) && visFits)
+            wp.shade_mode = 2;
+        else if ((p->flags & CGE_FLAG_COUPLED_SHADE) || !visFits || dp.samples_per_hit < 8)
+            wp.shade_mode = 1;
+        else if (p->flags & CGE_FLAG_AUTO_SHADE)
+            wp.shade_mode = 0;
+        else
+            wp.shade_mode = 2; // measured faster than the coupled kernel at every size tried
+        const bool decoupled = wp.shade_mode == 3;
+        const bool grouped = wp.shade_mode == 0 || wp.shade_mode == 2;
+        if (err == cudaSuccess && wp.shade_mode != 1)
             err = grow(s->wave.vis, s->waveVis, ws.vis, 1);
         if (err == cudaSuccess && !s->wave.counts)
             err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 32 * sizeof(unsigned));
@@ -454,33 +477,50 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
         if (err == cudaSuccess) {
             cudaEventRecord(s->evA, s->stream);
-            wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, dp, s->wave, rgbDev, idsDev, s->counters);
+            wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
             err = cudaGetLastError();
             cudaEventRecord(s->evB, s->stream);
         }
         if (err == cudaSuccess && decoupled) {
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_visibility_kernel, 128, 0);
             if (err == cudaSuccess) {
-                wf_visibility_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
+                wf_visibility_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
+        }
+        if (err == cudaSuccess && grouped) {
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_vis_grouped_kernel<CGE_GROUP>, 128, 0);
+            if (err == cudaSuccess) {
+                wf_vis_grouped_kernel<CGE_GROUP><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
                 err = cudaGetLastError();
                 *launches += 1;
             }
         }
         cudaEventRecord(s->evC, s->stream);
-        auto shade = decoupled ? wf_shade_kernel<true> : wf_shade_kernel<false>;
-        if (err == cudaSuccess)
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, shade, 128, 0);
-        if (err == cudaSuccess) {
-            shade<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, dp, s->wave, s->counters);
-            err = cudaGetLastError();
-            cudaEventRecord(s->evD, s->stream);
-            s->staged = true;
+        if (err == cudaSuccess && wp.shade_mode <= 1) {
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel<false>, 128, 0);
+            if (err == cudaSuccess) {
+                wf_shade_kernel<false><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
         }
+        if (err == cudaSuccess && wp.shade_mode != 1) {
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel<true>, 128, 0);
+            if (err == cudaSuccess) {
+                wf_shade_kernel<true><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
+        }
+        cudaEventRecord(s->evD, s->stream);
+        s->staged = true;
         if (err == cudaSuccess) {
-            wf_fold_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(dp, s->wave, rgbDev);
+            wf_fold_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(wp, s->wave, rgbDev);
             err = cudaGetLastError();
         }
-        *launches += 2;
+        *launches += 1; // chain + fold (the caller adds one)
     } else if (v.coop) {
         auto kern = render_coop_kernel;
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v.smem));

@@ -84,6 +84,9 @@ struct DevParams {
     uint32_t levels;          // ray_depth + 1 when recursive, else 1
     uint32_t units_per_lane;  // direct-lighting evaluations a pixel can need: levels (fold) or 2^levels - 1
     uint32_t debug_cycles;    // CGE_FLAG_DEBUG_CYCLES
+    // wavefront shadow-ray granularity: 0 auto (decided on the device from the queue lengths), 1 coupled, 2 grouped, 3 decoupled
+    uint32_t shade_mode;
+    uint32_t grouped_below_chunks; // auto: trace 4 rays per lane when the launch has fewer 32-evaluation chunks than this
 };
 
 } // namespace cge

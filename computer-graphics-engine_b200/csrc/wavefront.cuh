@@ -40,6 +40,21 @@ struct WaveBuffers {
     unsigned cap;
 };
 
+// Shadow-ray granularity of this launch (see cge_api.cu launch_render): true = rays are traced 4 per lane into the visibility
+// bytes (wf_vis_grouped_kernel) and wf_shade_kernel<true> shades; false = wf_shade_kernel<false> traces 16 per lane itself.
+// Decided from the queue lengths the chain kernel produced, identically by every kernel of the pipeline, without a host sync.
+__device__ __forceinline__ bool wf_use_visibility_bytes(const DevParams& p, const WaveBuffers& wb)
+{
+    if (p.shade_mode == 1)
+        return false;
+    if (p.shade_mode >= 2)
+        return true;
+    unsigned long long units = 0;
+    for (unsigned k = 0; k < p.levels; k++)
+        units += (unsigned long long)wb.counts[k] * (p.draws_per_hit == 0 ? 1u : (1u << k));
+    return units / 32ull < p.grouped_below_chunks;
+}
+
 __device__ __forceinline__ size_t wf_dir_off(const DevParams& p, unsigned cap, unsigned k)
 {
     const unsigned unitsBefore = p.draws_per_hit == 0 ? k : ((1u << k) - 1u);
@@ -369,6 +384,77 @@ __global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevPa
     flush_counters(cnt, gcnt);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// wf_vis_grouped_kernel: shadow rays in groups of kGroup consecutive samples per lane (lanes coupled, like wf_shade_kernel<false>,
+// but 16/kGroup times finer work items).  Used when a launch has too few direct-lighting evaluations per resident warp for the
+// 16-rays-per-lane granularity: on a 1/8 tile partition of C5 the coupled shade kernel left the SMs idle a third of its run
+// time (profiles/, smsp__cycles_active 5.3 M of 8.0 M).  Results go to the visibility bytes; wf_shade_kernel<true> shades.
+// ---------------------------------------------------------------------------------------------------------------------
+template <unsigned kGroup>
+__global__ void __launch_bounds__(128, 8) wf_vis_grouped_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const bool fold = p.draws_per_hit == 0;
+    const unsigned S = p.samples_per_hit;
+    const unsigned groups = (S + kGroup - 1) / kGroup;
+    unsigned cum[kMaxLevels + 1]; // in units (direct-lighting evaluations)
+    cum[0] = 0;
+    for (unsigned k = 0; k < p.levels; k++)
+        cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
+    const unsigned long long total = (unsigned long long)cum[p.levels] * groups;
+    unsigned long long nshadow = 0;
+    if (!wf_use_visibility_bytes(p, wb))
+        return;
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0)
+            chunk = atomicAdd(wb.counts + 18, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const unsigned long long first = (unsigned long long)chunk * 32ull;
+        if (first >= total)
+            break;
+        const unsigned long long item = first + lane;
+        if (item >= total)
+            continue;
+        // item -> (level k, copy, sample group, slot): level-major, then copy, then group, then queue order
+        unsigned k = 0;
+        while (item >= (unsigned long long)cum[k + 1] * groups)
+            k++;
+        const unsigned inLevel = unsigned(item - (unsigned long long)cum[k] * groups), cnt = wb.counts[k];
+        const unsigned block = inLevel / cnt, e = inLevel - block * cnt;
+        const unsigned path = block / groups, g = block - path * groups;
+        const uint2 m = wb.meta[size_t(k) * wb.cap + e];
+        const unsigned ctrBase = wf_draw_base(p, k, path, m.y & 255u);
+        const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
+        const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
+        unsigned char* visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
+        const unsigned sEnd = min(S, (g + 1u) * kGroup);
+        for (unsigned sg = g * kGroup; sg < sEnd; sg++) {
+            unsigned li = 0, si = sg, samples = 0, draws = 0, type = 0, ctr = ctrBase;
+            const float* L = s.lights;
+            for (;; li++) { // sample -> (light, sample within the light, first draw of that light)
+                L = s.lights + size_t(li) * kLightFloats;
+                type = __float_as_uint(__ldg(L));
+                light_counts(type, p, samples, draws);
+                if (si < samples)
+                    break;
+                si -= samples;
+                ctr += draws;
+            }
+            const LightSample ls = sample_light(L, type, int(si), p, m.x, ctr);
+            unsigned char v = 1;
+            if (ls.shadowed) {
+                nshadow++;
+                v = trace_fast<true>(s, o, ls.pos - o, 1.0f).prim >= 0 ? 0 : 1;
+            }
+            visOut[size_t(sg) * cnt] = v;
+        }
+    }
+    Counters cnt {};
+    cnt.shadow = nshadow;
+    flush_counters(cnt, gcnt);
+}
+
 template <bool kLookup>
 __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
 {
@@ -382,6 +468,8 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
     const unsigned total = cum[p.levels];
     unsigned long long nshadow = 0;
     const unsigned S = p.samples_per_hit;
+    if (wf_use_visibility_bytes(p, wb) != kLookup)
+        return; // the other instantiation handles this launch
     for (;;) {
         unsigned chunk = 0;
         if (lane == 0)

@@ -169,6 +169,9 @@ enum {
                                           the reference's own intersectRayWithShape/Triangle call counts) */
     CGE_FLAG_DEBUG_CYCLES = 1u << 4,   /* (implies the per-thread kernel) */
     CGE_FLAG_PER_THREAD = 1u << 5,
+    CGE_FLAG_COUPLED_SHADE = 1u << 7,   /* wavefront: always 16 coupled shadow rays per lane (disable the small-launch heuristic) */
+    CGE_FLAG_GROUPED_SHADE = 1u << 8,   /* wavefront: trace shadow rays 4 per lane into visibility bytes (the default for area lights) */
+    CGE_FLAG_AUTO_SHADE = 1u << 9,      /* wavefront: pick coupled / grouped on the device from the queue lengths */
     CGE_FLAG_DECOUPLED_SHADE = 1u << 6, /* wavefront: trace the shadow rays in the lane-decoupled wf_visibility_kernel (one ray
                                           per lane, idle lanes refilled through ballot + one atomic) and shade from its
                                           visibility bytes, instead of 16 coupled rays per lane inside wf_shade_kernel.

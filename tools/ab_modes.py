@@ -4,7 +4,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 pkg = importlib.import_module("computer-graphics-engine_b200")
-MODES = {"wave": 0, "decoupled": pkg.FLAG_DECOUPLED_SHADE, "thread": pkg.FLAG_PER_THREAD}
+MODES = {"wave": 0, "coupled": pkg.FLAG_COUPLED_SHADE, "grouped": pkg.FLAG_GROUPED_SHADE, "decoupled": pkg.FLAG_DECOUPLED_SHADE, "thread": pkg.FLAG_PER_THREAD}
 for spec in sys.argv[1:]:
     name, scale = (spec.split(":") + ["1.0"])[:2]
     full = pkg.configs.get(name)
@@ -18,6 +18,6 @@ for spec in sys.argv[1:]:
                 if best is None or st["kernel_ms"] < best["kernel_ms"]:
                     best = st
             out[label] = round(best["kernel_ms"], 3)
-            if label == "wave":
-                out["wave_stages"] = [round(x, 3) for x in best["stage_ms"]]
+            if label in ("wave", "grouped"):
+                out[label + "_stages"] = [round(x, 3) for x in best["stage_ms"]]
         print(name, cfg["width"], json.dumps(out), flush=True)
