@@ -8,10 +8,16 @@
 namespace cge {
 namespace {
 
+#ifndef CGE_SAH_MAX_LEAF
+#define CGE_SAH_MAX_LEAF 4
+#endif
+#ifndef CGE_SAH_CT
+#define CGE_SAH_CT 1.0f
+#endif
 constexpr int kBins = 16;
-constexpr uint32_t kMaxLeaf = 4;
+constexpr uint32_t kMaxLeaf = CGE_SAH_MAX_LEAF;   // <= 8 (3 bits in the packed leaf reference)
 constexpr uint32_t kMaxDepth = 56;
-constexpr float kTraversalCost = 1.0f; // relative to one primitive test
+constexpr float kTraversalCost = CGE_SAH_CT; // cost of one inner-node visit relative to one primitive test
 
 struct Box {
     float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };

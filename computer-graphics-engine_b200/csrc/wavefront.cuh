@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(128, 8) wf_vis_grouped_kernel(DevScene s, DevP
         const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
         unsigned char* visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
         const unsigned sEnd = min(S, (g + 1u) * kGroup);
+        int occluder = -1; // the triangle that blocked this lane's previous sample: tested first (occluder coherence)
         for (unsigned sg = g * kGroup; sg < sEnd; sg++) {
             unsigned li = 0, si = sg, samples = 0, draws = 0, type = 0, ctr = ctrBase;
             const float* L = s.lights;
@@ -445,7 +446,20 @@ __global__ void __launch_bounds__(128, 8) wf_vis_grouped_kernel(DevScene s, DevP
             unsigned char v = 1;
             if (ls.shadowed) {
                 nshadow++;
-                v = trace_fast<true>(s, o, ls.pos - o, 1.0f).prim >= 0 ? 0 : 1;
+                const vec3 d = ls.pos - o;
+                float t;
+                float4 r5;
+                // Any accepted triangle proves occlusion, whichever one the traversal would have met first; an accepted
+                // hit point lies inside its triangle and hence inside every (conservatively tested) ancestor box.
+                if (occluder >= 0 && triangle_rows_hit(s.ftris + size_t(occluder) * kTriRows, o, d, 1.0f, t, r5)) {
+                    v = 0;
+                } else {
+                    const Hit h = trace_fast<true>(s, o, d, 1.0f);
+                    if (h.prim >= 0) {
+                        v = 0;
+                        occluder = h.prim;
+                    }
+                }
             }
             visOut[size_t(sg) * cnt] = v;
         }
