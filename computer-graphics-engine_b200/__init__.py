@@ -23,7 +23,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
 FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1, 2, 4, 8
 FLAG_DEBUG_CYCLES, FLAG_PER_THREAD, FLAG_DECOUPLED_SHADE = 16, 32, 64
-FLAG_COUPLED_SHADE, FLAG_GROUPED_SHADE = 128, 256
+FLAG_COUPLED_SHADE, FLAG_GROUPED_SHADE, FLAG_AUTO_SHADE, FLAG_WAVEFRONT = 128, 256, 512, 1024
 UNIQUE_ID_BYTES = 128
 
 

@@ -338,8 +338,12 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
         && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count;
     const size_t cap = size_t(tiles_of(dp, dp.part_index, dp.part_count)) * 32;
     v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
-    v.wave = v.fast && !v.coop && !v.count && (p.features & CGE_FEAT_SHADING) && !(p.flags & (CGE_FLAG_PER_THREAD | CGE_FLAG_DEBUG_CYCLES))
-        && v.waveBytes <= kWaveScratchLimit && cap > 0;
+    // The wavefront pays off when a pixel's cost is wildly non-uniform, i.e. with area lights (16+ shadow rays per evaluation,
+    // 2^k evaluations at level k).  Point-light frames (<= 1 shadow ray per light and hit, recursion folded) are bounded per
+    // pixel and launch-latency sensitive: there the single per-thread kernel is faster.
+    const bool areaLights = dp.draws_per_hit > 0 || (p.flags & CGE_FLAG_WAVEFRONT);
+    v.wave = v.fast && !v.coop && !v.count && areaLights && (p.features & CGE_FEAT_SHADING)
+        && !(p.flags & (CGE_FLAG_PER_THREAD | CGE_FLAG_DEBUG_CYCLES)) && v.waveBytes <= kWaveScratchLimit && cap > 0;
     return v;
 }
 

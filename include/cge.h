@@ -155,7 +155,8 @@ enum {
                                     rule of src/bounding_volume_hierarchy.cpp:312-361 reproduced literally */
     CGE_TRAVERSAL_FAST = 1       /* binned-SAH tree (<= 4 primitives per leaf), near child first, conservative t culling,
                                     shadow rays stop at the first blocker; equal-t winner chosen by the reference's
-                                    visit rank; three-kernel wavefront over warp-compacted hit queues.  Scenes with spheres and
+                                    visit rank; with area lights a wavefront pipeline over warp-compacted hit queues, otherwise
+                                    one thread per pixel.  Scenes with spheres and
                                     !enableAccelStructure fall back to the literal traversal. */
 };
 enum {
@@ -171,7 +172,8 @@ enum {
     CGE_FLAG_PER_THREAD = 1u << 5,
     CGE_FLAG_COUPLED_SHADE = 1u << 7,   /* wavefront: always 16 coupled shadow rays per lane (disable the small-launch heuristic) */
     CGE_FLAG_GROUPED_SHADE = 1u << 8,   /* wavefront: trace shadow rays 4 per lane into visibility bytes (the default for area lights) */
-    CGE_FLAG_AUTO_SHADE = 1u << 9,      /* wavefront: pick coupled / grouped on the device from the queue lengths */
+    CGE_FLAG_AUTO_SHADE = 1u << 9,
+    CGE_FLAG_WAVEFRONT = 1u << 10,      /* use the wavefront pipeline even for point-light frames (default there: per-thread kernel) */      /* wavefront: pick coupled / grouped on the device from the queue lengths */
     CGE_FLAG_DECOUPLED_SHADE = 1u << 6, /* wavefront: trace the shadow rays in the lane-decoupled wf_visibility_kernel (one ray
                                           per lane, idle lanes refilled through ballot + one atomic) and shade from its
                                           visibility bytes, instead of 16 coupled rays per lane inside wf_shade_kernel.

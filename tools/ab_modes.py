@@ -4,7 +4,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 pkg = importlib.import_module("computer-graphics-engine_b200")
-MODES = {"wave": 0, "coupled": pkg.FLAG_COUPLED_SHADE, "grouped": pkg.FLAG_GROUPED_SHADE, "decoupled": pkg.FLAG_DECOUPLED_SHADE, "thread": pkg.FLAG_PER_THREAD}
+W = pkg.FLAG_WAVEFRONT
+MODES = {"default": 0, "wave": W, "coupled": W | pkg.FLAG_COUPLED_SHADE, "grouped": W | pkg.FLAG_GROUPED_SHADE, "decoupled": W | pkg.FLAG_DECOUPLED_SHADE, "thread": pkg.FLAG_PER_THREAD}
 for spec in sys.argv[1:]:
     name, scale = (spec.split(":") + ["1.0"])[:2]
     full = pkg.configs.get(name)
