@@ -374,6 +374,9 @@ def main():
         stage_vals = [chain_ms, vis_ms, shade_ms, fold_ms]
         dom = int(np.argmax(stage_vals))
         dom_name, dom_ms = stage_names[dom], stage_vals[dom]
+        if dom_ms <= 0:  # point-light frame: the single per-thread kernel traces every ray of the frame
+            dom_name, dom_ms = "render_kernel", pipeline_ms
+            algo_bytes = ref_rays / world * bytes_per_ray + 12.0 * W * H / world
         # the dominant kernel traces the shadow rays (wf_vis_grouped_kernel, or wf_shade_kernel for point-light scenes)
         traffic = None
         tf = ROOT / "profiles" / "traffic.json"

@@ -256,3 +256,30 @@ def test_partition_matches_host_tile_list(cge):
                     expect[H - y1:H - y0, tx * 8:min(tx * 8 + 8, W)] = True
                 assert np.array_equal(touched, expect), (parts, k)
                 assert np.array_equal((rgb != -7.0).all(-1) | np.isnan(rgb).any(-1), expect)
+
+
+def test_concurrent_renders_on_one_scene(cge):
+    """cge_render is re-entrant on one cge_scene (the reference renders several cameras from concurrent threads sharing
+    scene + bvh, src/main.cpp:514-528): every call has its own stream and scratch."""
+    import threading
+    cfgs = [cge.configs.get("c3_teapot_soft", 320, 180), cge.configs.get("c3_teapot_soft", 256, 144),
+            cge.configs.get("c3_teapot_soft", 200, 120), cge.configs.get("c3_teapot_soft", 320, 180)]
+    for i, c in enumerate(cfgs):
+        c["camera"] = dict(c["camera"], rotation_deg=[25.0, 30.0 + 40.0 * i, 0.0])
+    with cge.Scene(cge.load_scene(cfgs[0])) as sc:
+        expect = [sc.render(c)[0] for c in cfgs]
+        got = [None] * len(cfgs)
+        errs = []
+
+        def work(i):
+            try:
+                for _ in range(5):
+                    got[i] = sc.render(cfgs[i])[0]
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(cfgs))]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errs
+        for a, b in zip(expect, got):
+            assert a.tobytes() == b.tobytes()
