@@ -79,6 +79,7 @@ class CgeStats(C.Structure):
 ABI_SYMBOLS = [
     "cge_abi_version", "cge_last_error", "cge_device_count", "cge_camera_from_trackball", "cge_scene_create",
     "cge_scene_update_lights", "cge_scene_destroy", "cge_scene_bvh_info", "cge_scene_bvh_export", "cge_render",
+    "cge_bvh_build_reference_order",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
     "cge_comm_destroy", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
@@ -102,6 +103,7 @@ def lib() -> C.CDLL:
         l.cge_scene_destroy.argtypes = [C.c_void_p]
         l.cge_scene_bvh_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
         l.cge_scene_bvh_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.cge_bvh_build_reference_order.argtypes = [C.POINTER(CgeSceneDesc), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] + [C.POINTER(C.c_uint32)] * 3
         l.cge_camera_from_trackball.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                                 C.POINTER(CgeCamera)]
         l.cge_render.argtypes = [C.c_void_p, C.POINTER(CgeCamera), C.POINTER(CgeParams), C.c_void_p, C.c_void_p,
@@ -182,18 +184,37 @@ class PinnedBuffer:
             self._ptr = None
 
 
+def scene_desc(flat: FlatScene):
+    """(cge_scene_desc, arrays to keep alive) for a flat scene."""
+    d = CgeSceneDesc()
+    keep = [np.ascontiguousarray(a) for a in (flat.meshes, flat.vertices, flat.triangles, flat.spheres,
+                                              flat.lights, flat.textures, flat.texels)]
+    d.n_meshes, d.n_vertices, d.n_triangles = len(flat.meshes), len(flat.vertices), len(flat.triangles)
+    d.n_spheres, d.n_lights, d.n_textures, d.n_texels = len(flat.spheres), len(flat.lights), len(flat.textures), len(flat.texels)
+    (d.meshes, d.vertices, d.triangles, d.spheres, d.lights, d.textures, d.texels) = [
+        a.ctypes.data if a.size else None for a in keep]
+    return d, keep
+
+
+def build_reference_bvh_host(flat: FlatScene):
+    """Host-only rebuild of the reference's tree (no GPU): (nodes, prim_order, root, levels, leaves)."""
+    d, keep = scene_desc(flat)
+    n_prims = flat.n_primitives
+    nodes = np.zeros(max(2 * n_prims, 1), scenefile.BVH_NODE_DT)
+    order = np.zeros(n_prims, "<u4")
+    n = C.c_uint32(len(nodes))
+    root, levels, leaves = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _check(lib().cge_bvh_build_reference_order(C.byref(d), _p(nodes), C.byref(n), _p(order) if n_prims else None, C.byref(root),
+                                               C.byref(levels), C.byref(leaves)))
+    return nodes[: n.value], order, root.value, levels.value, leaves.value
+
+
 class Scene:
     """A flattened scene + reference-order BVH resident in HBM on one GPU (``cge_scene``)."""
 
     def __init__(self, flat: FlatScene, device: int = 0, use_stored_bvh: bool = False):
         self.flat = flat
-        d = CgeSceneDesc()
-        self._keep = [np.ascontiguousarray(a) for a in (flat.meshes, flat.vertices, flat.triangles, flat.spheres,
-                                                        flat.lights, flat.textures, flat.texels)]
-        d.n_meshes, d.n_vertices, d.n_triangles = len(flat.meshes), len(flat.vertices), len(flat.triangles)
-        d.n_spheres, d.n_lights, d.n_textures, d.n_texels = len(flat.spheres), len(flat.lights), len(flat.textures), len(flat.texels)
-        (d.meshes, d.vertices, d.triangles, d.spheres, d.lights, d.textures, d.texels) = [
-            a.ctypes.data if a.size else None for a in self._keep]
+        d, self._keep = scene_desc(flat)
         if use_stored_bvh and len(flat.bvh_nodes):
             nodes = np.ascontiguousarray(flat.bvh_nodes)
             order = np.ascontiguousarray(flat.bvh_prim_order)

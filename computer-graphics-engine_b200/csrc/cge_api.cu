@@ -975,6 +975,34 @@ int cge_scene_bvh_info(const cge_scene* sc, uint32_t* nNodes, uint32_t* nLevels,
     return CGE_OK;
 }
 
+int cge_bvh_build_reference_order(const cge_scene_desc* d, cge_bvh_node* nodesOut, uint32_t* nNodesInOut, uint32_t* orderOut,
+    uint32_t* rootOut, uint32_t* nLevelsOut, uint32_t* nLeavesOut)
+{
+    if (!d || !nNodesInOut)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    if ((d->n_meshes && !d->meshes) || (d->n_vertices && !d->vertices) || (d->n_triangles && !d->triangles) || (d->n_spheres && !d->spheres))
+        return fail(CGE_ERR_INVALID_ARG, "count without array");
+    HostBvh bvh;
+    if (!build_reference_bvh(*d, bvh)) { // no primitives
+        *nNodesInOut = 0;
+        return CGE_OK;
+    }
+    if (nodesOut && *nNodesInOut < bvh.nodes.size())
+        return fail(CGE_ERR_INVALID_ARG, "nodes_out too small");
+    if (nodesOut)
+        std::memcpy(nodesOut, bvh.nodes.data(), bvh.nodes.size() * sizeof(cge_bvh_node));
+    if (orderOut)
+        std::memcpy(orderOut, bvh.prim_order.data(), bvh.prim_order.size() * sizeof(uint32_t));
+    *nNodesInOut = uint32_t(bvh.nodes.size());
+    if (rootOut)
+        *rootOut = bvh.root;
+    if (nLevelsOut)
+        *nLevelsOut = bvh.n_levels;
+    if (nLeavesOut)
+        *nLeavesOut = bvh.n_leaves;
+    return CGE_OK;
+}
+
 int cge_scene_bvh_export(const cge_scene* sc, cge_bvh_node* nodesOut, uint32_t* orderOut)
 {
     if (!sc)

@@ -233,6 +233,12 @@ int cge_scene_destroy(cge_scene* scene);
 /* Introspection used by BvhInterface::numLevels / numLeaves (src/bvh_interface.h:20,24) and by the tests. */
 int cge_scene_bvh_info(const cge_scene* scene, uint32_t* n_nodes, uint32_t* n_levels, uint32_t* n_leaves,
                        uint32_t* max_leaf_prims);
+/* Host-only (no GPU needed): rebuild the reference's tree for a scene description — BoundingVolumeHierarchy's constructor
+ * (src/bounding_volume_hierarchy.cpp:149-194) without the device upload.  nodes_out has room for *n_nodes_inout nodes; on
+ * return *n_nodes_inout is the node count (CGE_ERR_INVALID_ARG if the room was too small).  prim_order_out: n_triangles +
+ * n_spheres entries. */
+int cge_bvh_build_reference_order(const cge_scene_desc* desc, cge_bvh_node* nodes_out, uint32_t* n_nodes_inout,
+                                  uint32_t* prim_order_out, uint32_t* root_out, uint32_t* n_levels_out, uint32_t* n_leaves_out);
 /* Copy out the BVH the library built (for parity tests against the reference's tree). Either pointer may be NULL. */
 int cge_scene_bvh_export(const cge_scene* scene, cge_bvh_node* nodes_out, uint32_t* prim_order_out);
 

@@ -60,3 +60,32 @@ def test_product_never_touches_the_oracle():
         for line in text.splitlines():
             code = line.split("//")[0].split("#")[0] if f.suffix != ".py" else line.split("#")[0]
             assert "oracle/" not in code and "refharness" not in code and "libcge_ref" not in code, (f, line)
+
+
+def test_host_bvh_builder_equals_reference_tree(cge):
+    """The library's host-side BVH builder (no GPU involved) reproduces the reference's tree node for node and the same
+    primitive permutation for every fixture scene (goldens exported from the reference's own BoundingVolumeHierarchy)."""
+    g = np.load(ROOT / "tests" / "golden" / "reference_bvh.npz")
+    for f in sorted((ROOT / "tests" / "golden" / "scenes").glob("*.cges")):
+        flat = cge.scenefile.load(f)
+        nodes, order, root, levels, leaves = cge.build_reference_bvh_host(flat)
+        assert np.array_equal(order, g[f.stem + "_order"]), f.stem
+        assert nodes.tobytes() == g[f.stem + "_nodes"].tobytes(), f.stem
+        assert root == int(g[f.stem + "_root"])
+        assert leaves == int((nodes["is_leaf"] == 1).sum()) and levels == int(nodes["depth"].max()) + 1
+    # empty scene: no nodes, no error
+    nodes, order, root, levels, leaves = cge.build_reference_bvh_host(cge.scenefile.FlatScene())
+    assert len(nodes) == 0
+
+
+def test_host_bvh_builder_dragon_standin_against_live_reference(cge, ref, tmp_path):
+    flat = cge.standin.make("dragon", n=64)  # 49 154 triangles: exercises the MAX_DEPTH-16 multi-primitive leaves
+    path = tmp_path / "s.cges"
+    cge.scenefile.save(flat, path)
+    with ref.RefScene(path, cge.configs.FEAT_ACCEL_STRUCTURE) as rs:
+        out = tmp_path / "with_bvh.cges"
+        rs.write_with_bvh(out)
+    want = cge.scenefile.load(out)
+    nodes, order, root, levels, leaves = cge.build_reference_bvh_host(flat)
+    assert np.array_equal(order, want.bvh_prim_order) and nodes.tobytes() == want.bvh_nodes.tobytes() and root == want.bvh_root
+    assert levels == 16

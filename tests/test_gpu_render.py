@@ -283,3 +283,27 @@ def test_concurrent_renders_on_one_scene(cge):
         assert not errs
         for a, b in zip(expect, got):
             assert a.tobytes() == b.tobytes()
+
+
+def test_c5_full_size_rows_against_live_reference(cge, ref, tmp_path):
+    """BASELINE.json's headline config at its FULL size (868 334 triangles, 3840x2160, soft shadows, depth 3): the GPU frame
+    against the reference renderer on evenly spaced rows of the same frame (the whole frame is ~3 minutes of CPU)."""
+    cfg = cge.configs.get("c5_dragon")
+    flat = cge.standin.make("dragon")
+    path = tmp_path / "dragon.cges"
+    cge.scenefile.save(flat, path)
+    W, H = cfg["width"], cfg["height"]
+    stride = 270
+    with ref.RefScene(path, cfg["features"]) as rs:
+        ref_rgb, ref_ids, rst = rs.render(cfg, y_stride=stride)
+    with cge.Scene(flat) as sc:
+        rgb, ids, st = sc.render(cfg)
+        rgb_t, ids_t, _ = sc.render(cfg, flags=cge.FLAG_PER_THREAD)
+    assert np.array_equal(ids, ids_t) and rgb.tobytes() == rgb_t.tobytes()  # wavefront == per-thread kernel, whole frame
+    rows = [H - 1 - y for y in range(0, H, stride)]  # Screen rows of reference y = 0, stride, ...
+    a_rgb, a_ids = rgb[rows], ids[rows]
+    b_rgb, b_ids = ref_rgb[rows], ref_ids[rows]
+    assert (a_ids != b_ids).sum() <= max(1, int(ID_MISMATCH_BUDGET * a_ids.size))
+    err, nan_mm = compare_images(a_rgb, b_rgb)
+    assert nan_mm == 0
+    assert err <= RGB_TOL * max(1.0, float(np.nan_to_num(b_rgb, nan=0.0).max())), err
