@@ -319,6 +319,19 @@ def main():
 
     e2e_total_s, st_e, _, _ = timed(step_e2e, max(args.warmup, 1), args.steps)
     e2e_ms = e2e_total_s / args.steps * 1e3
+    # the same frame delivered as the reference's bitmap bytes (Screen::writeBitmapToFile's clamp -> u8x4 stage on the GPU,
+    # SURVEY 8(f) N3): 4 instead of 12 bytes per pixel cross PCIe
+    bitmap_ms = None
+    if world == 1:
+        pinned8 = pkg.PinnedBuffer((H, W, 4), np.uint8)
+
+        def step_bitmap():
+            scene.update_lights(lights)
+            _, stb = scene.render_rgba8(cfg, out=pinned8.array, camera=cam)
+            return stb
+        bt, _, _, _ = timed(step_bitmap, 1, args.steps)
+        bitmap_ms = bt / args.steps * 1e3
+        pinned8.close()
     e2e_value = ref_rays / e2e_ms / 1e3
     h2d_bytes = int(lights.nbytes + 36 + 64)  # light list + cge_camera + cge_params
     d2h_bytes = int(W * H * 12)
@@ -419,6 +432,8 @@ def main():
                            "bounce": float(cnt[3]), "shadow": float(cnt[4])},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes},
+        "e2e_bitmap_u8": None if bitmap_ms is None else {"value": ref_rays / bitmap_ms / 1e3, "unit": UNIT, "ms_per_step": bitmap_ms,
+                                                          "d2h_bytes_per_step": int(W * H * 4)},
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "scene_upload_s": upload_s,
         "clocks": clocks,

@@ -24,6 +24,7 @@ TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
 FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1, 2, 4, 8
 FLAG_DEBUG_CYCLES, FLAG_PER_THREAD, FLAG_DECOUPLED_SHADE = 16, 32, 64
 FLAG_COUPLED_SHADE, FLAG_GROUPED_SHADE, FLAG_AUTO_SHADE, FLAG_WAVEFRONT = 128, 256, 512, 1024
+FLAG_OUTPUT_RGBA8 = 2048
 UNIQUE_ID_BYTES = 128
 
 
@@ -269,6 +270,16 @@ class Scene:
         st = CgeStats()
         _check(lib().cge_render(self.handle, C.byref(cam), C.byref(p), _p(rgb), _p(ids), C.byref(st)))
         return rgb, ids, st.as_dict()
+
+    def render_rgba8(self, cfg: dict, out=None, traversal: int = TRAVERSAL_FAST, camera: CgeCamera | None = None):
+        """cge_render with CGE_FLAG_OUTPUT_RGBA8: the frame after the reference's bitmap output stage, (H, W, 4) uint8."""
+        cam = camera or camera_from_cfg(cfg)
+        p = params_from_cfg(cfg, traversal, False, (0, 1), FLAG_OUTPUT_RGBA8)
+        H, W = cfg["height"], cfg["width"]
+        rgba = out if out is not None else np.zeros((H, W, 4), np.uint8)
+        st = CgeStats()
+        _check(lib().cge_render(self.handle, C.byref(cam), C.byref(p), _p(rgba), None, C.byref(st)))
+        return rgba, st.as_dict()
 
     def render_device(self, cfg: dict, rgb_ptr: int, ids_ptr: int = 0, traversal: int = TRAVERSAL_FAST,
                       camera: CgeCamera | None = None, part=(0, 1), flags: int = 0) -> dict:

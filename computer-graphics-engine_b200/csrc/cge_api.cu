@@ -289,6 +289,23 @@ DevScene scene_for(const cge_scene* sc, const cge_params& p)
     return d;
 }
 
+// Output stage of Screen::writeBitmapToFile (reference src/screen.cpp:49-60): glm::clamp(color, 0, 1) -> vec4(c, 1) * 255 ->
+// glm::u8vec4 (float -> u8 truncation).  glm::clamp = min(max(x, 0), 1) lets NaN through and the x86 conversion of NaN to an
+// integer yields 0 in the low byte; reproduced as 0.
+__global__ void pack_rgba8_kernel(const float* __restrict__ rgb, uchar4* __restrict__ out, size_t pixels)
+{
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= pixels)
+        return;
+    auto conv = [](float v) -> unsigned char {
+        if (v != v)
+            return 0;
+        v = fminf(fmaxf(v, 0.0f), 1.0f);
+        return (unsigned char)__float2int_rz(__fmul_rn(v, 255.0f));
+    };
+    out[i] = make_uchar4(conv(rgb[i * 3]), conv(rgb[i * 3 + 1]), conv(rgb[i * 3 + 2]), 255);
+}
+
 unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
 {
     const unsigned nTiles = d.n_tiles_x * d.n_tiles_y;
@@ -1022,11 +1039,15 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     if (!cam || !rgbOut)
         return fail(CGE_ERR_INVALID_ARG, "null camera or output");
     const bool wantIds = (p->flags & CGE_FLAG_WANT_PRIM_IDS) && idsOut;
-    const bool devOut = p->flags & CGE_FLAG_RGB_DEVICE_PTR;
+    const bool rgba8 = p->flags & CGE_FLAG_OUTPUT_RGBA8;
+    const bool devOut = (p->flags & CGE_FLAG_RGB_DEVICE_PTR) && !rgba8;
+    if (rgba8 && ((p->flags & CGE_FLAG_RGB_DEVICE_PTR) || p->part_count > 1))
+        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_OUTPUT_RGBA8 writes a whole host frame");
     CGE_CUDA(cudaSetDevice(sc->device));
     const size_t pixels = size_t(p->width) * size_t(p->height);
     Scratch* s = nullptr;
-    rc = acquire_scratch(sc, devOut ? 1 : pixels, wantIds, 0, &s);
+    // rgba8: the float frame lives in the first 3/4 of a doubled scratch frame, the packed bytes in the ids buffer
+    rc = acquire_scratch(sc, devOut ? 1 : pixels, wantIds || rgba8, 0, &s);
     if (rc) {
         release_scratch(sc, s);
         return rc;
@@ -1038,7 +1059,14 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     cudaEventRecord(s->ev0, s->stream);
     rc = launch_render(sc, s, cam, p, dp, rgbDev, idsDev, &launches);
     cudaEventRecord(s->ev1, s->stream);
-    if (rc == CGE_OK && !devOut) {
+    if (rc == CGE_OK && rgba8) {
+        // ids (if wanted) leave first, then their buffer is reused for the packed pixels (4 bytes per pixel either way)
+        if (wantIds)
+            cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+        pack_rgba8_kernel<<<unsigned((pixels + 255) / 256), 256, 0, s->stream>>>(s->rgb, reinterpret_cast<uchar4*>(s->ids), pixels);
+        launches++;
+        cudaMemcpyAsync(rgbOut, s->ids, pixels * 4, cudaMemcpyDeviceToHost, s->stream);
+    } else if (rc == CGE_OK && !devOut) {
         if (dp.part_count <= 1) {
             cudaMemcpyAsync(rgbOut, s->rgb, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
             if (wantIds)

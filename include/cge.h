@@ -173,7 +173,10 @@ enum {
     CGE_FLAG_COUPLED_SHADE = 1u << 7,   /* wavefront: always 16 coupled shadow rays per lane (disable the small-launch heuristic) */
     CGE_FLAG_GROUPED_SHADE = 1u << 8,   /* wavefront: trace shadow rays 4 per lane into visibility bytes (the default for area lights) */
     CGE_FLAG_AUTO_SHADE = 1u << 9,
-    CGE_FLAG_WAVEFRONT = 1u << 10,      /* use the wavefront pipeline even for point-light frames (default there: per-thread kernel) */      /* wavefront: pick coupled / grouped on the device from the queue lengths */
+    CGE_FLAG_WAVEFRONT = 1u << 10,
+    CGE_FLAG_OUTPUT_RGBA8 = 1u << 11,   /* rgb_out is a uint8_t[W*H*4] RGBA buffer: the frame goes through the output stage of
+                                           Screen::writeBitmapToFile (src/screen.cpp:49-60: clamp to [0,1], *255, truncate, alpha
+                                           255; NaN -> 0) on the GPU, so the D2H copy is 4 instead of 12 bytes per pixel */      /* use the wavefront pipeline even for point-light frames (default there: per-thread kernel) */      /* wavefront: pick coupled / grouped on the device from the queue lengths */
     CGE_FLAG_DECOUPLED_SHADE = 1u << 6, /* wavefront: trace the shadow rays in the lane-decoupled wf_visibility_kernel (one ray
                                           per lane, idle lanes refilled through ballot + one atomic) and shade from its
                                           visibility bytes, instead of 16 coupled rays per lane inside wf_shade_kernel.

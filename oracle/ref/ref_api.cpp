@@ -840,6 +840,16 @@ int ref_intersect_rays(void* scene, void* bvhHandle, const float* ray7, uint32_t
     return 0;
 }
 
+// Screen::writeBitmapToFile (src/screen.cpp:49-60) applied to a caller-supplied float frame (Screen::pixels() order):
+// the reference's own clamp -> *255 -> u8x4 conversion and BMP writer, for the output-stage parity test.
+int ref_write_bmp(const float* rgb, int width, int height, const char* path)
+{
+    Screen screen { glm::ivec2(width, height), false };
+    std::memcpy(screen.pixels().data(), rgb, size_t(width) * size_t(height) * 3 * sizeof(float));
+    screen.writeBitmapToFile(path);
+    return 0;
+}
+
 int ref_has_counters(void)
 {
 #ifdef CGE_REF_NO_COUNTERS

@@ -266,6 +266,14 @@ def kat_reflection(in13):
     return out
 
 
+def write_bmp(rgb, path):
+    """The reference's Screen::writeBitmapToFile on a float frame (H, W, 3)."""
+    rgb = _f32(rgb)
+    l = lib()
+    l.ref_write_bmp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    l.ref_write_bmp(_p(rgb), rgb.shape[1], rgb.shape[0], str(path).encode())
+
+
 def export_prebuilt(scene_type: int, data_dir, out_path, features: int = 0, with_bvh: bool = False):
     rc = lib().ref_scene_export(0, scene_type, str(data_dir).encode(), features, int(with_bvh), str(out_path).encode())
     if rc:

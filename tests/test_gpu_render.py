@@ -307,3 +307,21 @@ def test_c5_full_size_rows_against_live_reference(cge, ref, tmp_path):
     err, nan_mm = compare_images(a_rgb, b_rgb)
     assert nan_mm == 0
     assert err <= RGB_TOL * max(1.0, float(np.nan_to_num(b_rgb, nan=0.0).max())), err
+
+
+def test_rgba8_output_stage_matches_reference_bitmap_writer(cge, ref, tmp_path):
+    """SURVEY 8(f) N3: Screen::writeBitmapToFile's clamp -> *255 -> u8x4 conversion done on the GPU before the D2H copy.
+    The reference's own writer (stb BMP) is applied to the same float frame and read back."""
+    from PIL import Image
+    for name, size in (("c1_cornell", (200, 200)), ("c4_monkey_mirror", (192, 108)), ("c3_teapot_soft", (160, 90))):
+        cfg = cge.configs.get(name, *size)
+        with cge.Scene(cge.load_scene(cfg)) as sc:
+            rgb, _, _ = sc.render(cfg, want_ids=False)
+            rgba, st = sc.render_rgba8(cfg)
+        assert np.isnan(rgb).any() or name != "c1_cornell"  # the Cornell frame exercises the NaN rule
+        bmp = tmp_path / f"{name}.bmp"
+        ref.write_bmp(rgb, bmp)
+        want = np.asarray(Image.open(bmp).convert("RGBA"))
+        assert want.shape == rgba.shape
+        assert np.array_equal(rgba[..., :3], want[..., :3]), name
+        assert (rgba[..., 3] == 255).all()
