@@ -84,7 +84,7 @@ struct PixelTracer {
     {
         cnt.shadow++;
         if (kFast)
-            return trace_fast<true, kCount>(s, o, d, 1.0f, &nbox, &ntri).prim >= 0;
+            return kCount ? trace_fast<true, kCount>(s, o, d, 1.0f, &nbox, &ntri).prim >= 0 : trace_shadow(s, o, d) >= 0;
         return trace_reference<kSpheres, kCount>(s, o, d, 1.0f, nbox, ntri).prim >= 0;
     }
     __device__ const float4* rows(const Hit& h) const { return (kFast ? s.ftris : s.tris) + size_t(h.prim) * kTriRows; }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_COOP) render_coop_kernel(DevScen
                 if (ls.shadowed) {
                     const vec3 so = shadow_origin(h);
                     cnt.shadow++;
-                    vis = trace_fast<true>(s, so, ls.pos - so, 1.0f).prim >= 0 ? 0.0f : 1.0f;
+                    vis = trace_shadow(s, so, ls.pos - so) >= 0 ? 0.0f : 1.0f;
                 }
                 term = compute_shading(ls.pos, ls.col, h) * vis;
             }

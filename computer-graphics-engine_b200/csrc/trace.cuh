@@ -202,4 +202,56 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
     return h;
 }
 
+// Shadow rays (src/light.cpp:60-72: closest hit with ray.t = 1 used as a boolean): is ANY triangle accepted with 0 <= t <= 1?
+// Lean specialisation of trace_fast<true>: the bound is the constant 1, so the stack needs no entry distances and no
+// re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris) or -1.
+__device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, const vec3 d)
+{
+    if (s.n_prims == 0)
+        return -1;
+    const vec3 inv = v3(d.x != 0.0f ? fdiv(1.0f, d.x) : 3.0e38f, d.y != 0.0f ? fdiv(1.0f, d.y) : 3.0e38f,
+        d.z != 0.0f ? fdiv(1.0f, d.z) : 3.0e38f);
+    unsigned stack[kFastStackSize];
+    int sp = 0;
+    constexpr unsigned kDone = 0x7fffffffu;
+    unsigned cur = s.froot;
+    while (cur != kDone) {
+        while (cur < kDone) {
+            const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+            const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
+            const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
+            const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
+            const float entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+            const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+            const bool hitL = entL <= extL * 1.000002f && entL <= 1.0001f;
+            const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
+            const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
+            const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
+            const float entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+            const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+            const bool hitR = entR <= extR * 1.000002f && entR <= 1.0001f;
+            const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+            const bool leftFirst = hitL && (!hitR || entL <= entR);
+            if (hitL && hitR)
+                stack[sp++] = leftFirst ? cr : cl;
+            if (hitL || hitR)
+                cur = leftFirst ? cl : cr;
+            else
+                cur = sp > 0 ? stack[--sp] : kDone;
+        }
+        if (cur == kDone)
+            break;
+        const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+        for (unsigned i = first; i < first + count; i++) {
+            float t;
+            float4 r5;
+            if (triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, 1.0f, t, r5))
+                return int(i);
+        }
+        cur = sp > 0 ? stack[--sp] : kDone;
+    }
+    return -1;
+}
+
 } // namespace cge

@@ -163,7 +163,7 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
                 v = vis[size_t(sg) * visStride] ? 1.0f : 0.0f;
             } else if (ls.shadowed) {
                 nshadow++;
-                v = trace_fast<true>(s, sp, ls.pos - sp, 1.0f).prim >= 0 ? 0.0f : 1.0f;
+                v = trace_shadow(s, sp, ls.pos - sp) >= 0 ? 0.0f : 1.0f;
             }
             result = result + c * v;
         } else if (samples) {
@@ -175,7 +175,7 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
                     v = vis[size_t(sg + si) * visStride] ? 1.0f : 0.0f;
                 } else {
                     nshadow++;
-                    v = trace_fast<true>(s, sp, ls.pos - sp, 1.0f).prim >= 0 ? 0.0f : 1.0f;
+                    v = trace_shadow(s, sp, ls.pos - sp) >= 0 ? 0.0f : 1.0f;
                 }
                 color = color + compute_shading(ls.pos, ls.col, h) * v;
             }
@@ -454,10 +454,10 @@ __global__ void __launch_bounds__(128, 8) wf_vis_grouped_kernel(DevScene s, DevP
                 if (occluder >= 0 && triangle_rows_hit(s.ftris + size_t(occluder) * kTriRows, o, d, 1.0f, t, r5)) {
                     v = 0;
                 } else {
-                    const Hit h = trace_fast<true>(s, o, d, 1.0f);
-                    if (h.prim >= 0) {
+                    const int blocker = trace_shadow(s, o, d);
+                    if (blocker >= 0) {
                         v = 0;
-                        occluder = h.prim;
+                        occluder = blocker;
                     }
                 }
             }
