@@ -101,6 +101,7 @@ struct cge_scene {
     uint32_t n_triangles = 0, n_spheres = 0;
     uint32_t accel_root_ref = 0, accel_root_count = 0;
     bool any_transparent = false;
+    bool colours_bounded = true; // every kd / ks / texel is finite and <= kColourBound in magnitude (zero-shading cull)
     std::vector<cge_light_desc> host_lights;
     std::mutex mu;
     std::vector<Scratch*> pool;
@@ -274,9 +275,39 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     return d;
 }
 
+// Magnitude below which a product of a material colour and a light colour cannot overflow: the zero-shading cull
+// (shade.cuh shading_is_zero) relies on (kd * Lc) * 0 and (ks * Lc) * 0 being +-0, not NaN.
+constexpr float kColourBound = 1e18f;
+bool bounded(const float* v, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+        if (!(std::fabs(v[i]) <= kColourBound))
+            return false;
+    return true;
+}
+bool light_colours_bounded(const std::vector<cge_light_desc>& lights)
+{
+    for (const auto& l : lights) {
+        // colour members per type (include/cge.h cge_light_desc); interpolated sample colours stay within 2x the corner colours
+        const int from = l.type == CGE_LIGHT_POINT ? 3 : l.type == CGE_LIGHT_SEGMENT ? 6 : 9;
+        const int to = l.type == CGE_LIGHT_POINT ? 6 : l.type == CGE_LIGHT_SEGMENT ? 12 : 21;
+        if (!bounded(l.v + from, size_t(to - from)))
+            return false;
+    }
+    return true;
+}
+
+// development aid: integer tunables can be overridden from the environment for A/B sweeps (tools/sweep_vis.py)
+int env_int(const char* name, int fallback)
+{
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : fallback;
+}
+
 DevScene scene_for(const cge_scene* sc, const cge_params& p)
 {
     DevScene d = sc->dev;
+    d.cull_zero_shading = sc->colours_bounded && light_colours_bounded(sc->host_lights) && env_int("CGE_ZERO_SHADING_CULL", 1);
     if (p.features & CGE_FEAT_ACCEL_STRUCTURE) {
         d.root_ref = sc->accel_root_ref;
         d.root_count = sc->accel_root_count;
@@ -865,6 +896,9 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     for (uint32_t t = 0; t < d->n_textures; t++)
         texs[t] = make_int4(d->textures[t].width, d->textures[t].height, int(d->textures[t].texel_offset), 0);
     std::vector<float> texels(d->texels, d->texels + size_t(d->n_texels) * 3);
+    sc->colours_bounded = bounded(texels.data(), texels.size());
+    for (size_t m = 0; m < mats.size(); m += 3) // kd.xyz and ks.xyz (shininess and transparency are not colours)
+        sc->colours_bounded = sc->colours_bounded && bounded(&mats[m].x, 3) && bounded(&mats[m + 1].x, 3);
     sc->host_lights.assign(d->lights, d->lights + d->n_lights);
     std::vector<float> lights = pack_lights(d->lights, d->n_lights);
 

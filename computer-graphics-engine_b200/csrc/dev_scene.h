@@ -61,6 +61,7 @@ struct DevScene {
     uint32_t root_ref, root_count; // reference-order tree root, same encoding as a child slot
     uint32_t froot;                // fast tree root (packed)
     uint32_t has_spheres;
+    uint32_t cull_zero_shading; // FAST traversal: skip the shadow ray of a light sample with n.l <= 0 (shade.cuh shading_is_zero)
 };
 
 struct DevCamera {

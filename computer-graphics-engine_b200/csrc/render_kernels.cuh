@@ -95,6 +95,10 @@ struct PixelTracer {
         if (!(p.features & CGE_FEAT_SHADING))
             return h.m.kd;
         const vec3 sp = shadow_origin(h);
+        const ShadeFrame frame = shade_frame(h);
+        // kFast only: a sample whose Phong term is exactly zero needs no shadow ray (shade.cuh shading_is_zero); the literal
+        // traversal traces every ray the reference traces so that its ray / box / triangle counters stay comparable
+        auto needed = [&](const LightSample& ls) { return !(kFast && shading_is_zero(s, frame, ls.pos)); };
         vec3 result = v3(0.0f);
         for (unsigned li = 0; li < s.n_lights; li++) {
             const float* L = s.lights + size_t(li) * kLightFloats;
@@ -105,14 +109,14 @@ struct PixelTracer {
                 const LightSample ls = sample_light(L, type, 0, p, pixel, ctr);
                 const vec3 c = compute_shading(ls.pos, ls.col, h);
                 float vis = 1.0f;
-                if (ls.shadowed)
+                if (ls.shadowed && needed(ls))
                     vis = occluded(sp, ls.pos - sp) ? 0.0f : 1.0f;
                 result = result + c * vis;
             } else if (samples) {
                 vec3 color = v3(0.0f);
                 for (unsigned si = 0; si < samples; si++) {
                     const LightSample ls = sample_light(L, type, int(si), p, pixel, ctr);
-                    const float vis = occluded(sp, ls.pos - sp) ? 0.0f : 1.0f;
+                    const float vis = needed(ls) && occluded(sp, ls.pos - sp) ? 0.0f : 1.0f;
                     color = color + compute_shading(ls.pos, ls.col, h) * vis;
                 }
                 // sampleSize, or sampleSizeA * sampleSizeB, as floats (src/light.cpp:137,155)
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_COOP) render_coop_kernel(DevScen
                 const unsigned spx = unsigned(sy) * unsigned(p.width) + unsigned(sx);
                 const LightSample ls = sample_light(L, type, int(si), p, spx, ctr);
                 float vis = 1.0f;
-                if (ls.shadowed) {
+                if (ls.shadowed && !shading_is_zero(s, shade_frame(h), ls.pos)) {
                     const vec3 so = shadow_origin(h);
                     cnt.shadow++;
                     vis = trace_shadow(s, so, ls.pos - so) >= 0 ? 0.0f : 1.0f;

@@ -97,10 +97,36 @@ __device__ void resolve_hit(const DevScene& s, unsigned features, const float4* 
     }
 }
 
+// The two ray-independent operands of computeShading (src/shading.cpp:12-17): the unit normal and the hit point.
+struct ShadeFrame {
+    vec3 n, p;
+};
+__device__ __forceinline__ ShadeFrame shade_frame(const HitRec& h)
+{
+    return ShadeFrame { normalize(h.normal), h.ray.d * h.ray.t + h.ray.o };
+}
+__device__ __forceinline__ float shade_n_dot_l(const ShadeFrame& f, vec3 lightPos)
+{
+    return dot(f.n, normalize(lightPos - f.p));
+}
+
+// A light sample whose Phong term is exactly zero needs no visibility test.  The reference multiplies the term by the 0/1
+// visibility and adds it (src/light.cpp: `color += shading * visibility`); when n.l <= 0 computeShading returns
+// (kd*Lc)*0 + (ks*Lc)*0 (src/shading.cpp:19-34: the specular branch needs n.l > 0), which is +-0 for finite products, so the
+// sum is the same bits whatever the shadow ray would have said.  DevScene::cull_zero_shading is set by the host only when
+// every kd / ks / texel / light colour is finite and small enough that those products cannot overflow; n.l is evaluated by
+// the same instructions as in compute_shading below (same inputs, no FMA), so the two always agree.  Only the FAST
+// traversal uses this (the literal traversal keeps the reference's ray and test counts).
+__device__ __forceinline__ bool shading_is_zero(const DevScene& s, const ShadeFrame& f, vec3 lightPos)
+{
+    return s.cull_zero_shading && shade_n_dot_l(f, lightPos) <= 0.0f;
+}
+
 __device__ __forceinline__ vec3 compute_shading(vec3 lightPos, vec3 lightColor, const HitRec& h)
 {
-    const vec3 n = normalize(h.normal);
-    const vec3 l = normalize(lightPos - (h.ray.d * h.ray.t + h.ray.o));
+    const ShadeFrame f = shade_frame(h);
+    const vec3 n = f.n;
+    const vec3 l = normalize(lightPos - f.p);
     const float nl = dot(n, l);
     float dd = nl;
     if (dd < 0.0f)

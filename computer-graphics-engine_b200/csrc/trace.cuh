@@ -202,6 +202,20 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
     return h;
 }
 
+// max / min of three: one FMNMX3 on sm_100 instead of two FMNMX
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // Shadow rays (src/light.cpp:60-72: closest hit with ray.t = 1 used as a boolean): is ANY triangle accepted with 0 <= t <= 1?
 // Lean specialisation of trace_fast<true>: the bound is the constant 1, so the stack needs no entry distances and no
 // re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris) or -1.
@@ -222,14 +236,14 @@ __device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, con
             const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
             const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
             const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
-            const float entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
-            const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+            const float entL = fmaxf(max3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), 0.0f);
+            const float extL = min3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1));
             const bool hitL = entL <= extL * 1.000002f && entL <= 1.0001f;
             const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
             const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
             const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
-            const float entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-            const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+            const float entR = fmaxf(max3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), 0.0f);
+            const float extR = min3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1));
             const bool hitR = entR <= extR * 1.000002f && entR <= 1.0001f;
             const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
             const bool leftFirst = hitL && (!hitR || entL <= entR);

@@ -148,6 +148,7 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
     unsigned long long& nshadow, const unsigned char* __restrict__ vis, size_t visStride)
 {
     const vec3 sp = kLookup ? v3(0.0f) : shadow_origin(h);
+    const ShadeFrame frame = shade_frame(h);
     vec3 result = v3(0.0f);
     unsigned sg = 0; // running sample index over all lights
     for (unsigned li = 0; li < s.n_lights; li++) {
@@ -161,7 +162,7 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
             float v = 1.0f;
             if (kLookup) {
                 v = vis[size_t(sg) * visStride] ? 1.0f : 0.0f;
-            } else if (ls.shadowed) {
+            } else if (ls.shadowed && !shading_is_zero(s, frame, ls.pos)) {
                 nshadow++;
                 v = trace_shadow(s, sp, ls.pos - sp) >= 0 ? 0.0f : 1.0f;
             }
@@ -173,6 +174,8 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
                 float v;
                 if (kLookup) {
                     v = vis[size_t(sg + si) * visStride] ? 1.0f : 0.0f;
+                } else if (shading_is_zero(s, frame, ls.pos)) {
+                    v = 1.0f;
                 } else {
                     nshadow++;
                     v = trace_shadow(s, sp, ls.pos - sp) >= 0 ? 0.0f : 1.0f;
@@ -202,6 +205,36 @@ __device__ __forceinline__ unsigned wf_draw_base(const DevParams& p, unsigned k,
         idx += 1u + b * ((1u << (nChain - i)) - 1u);
     }
     return idx * p.draws_per_hit;
+}
+
+// hit-record fields the zero-shading cull needs (shade.cuh shading_is_zero): incoming ray and normal of queue slot e, level k
+__device__ __forceinline__ ShadeFrame wf_load_frame(const WaveBuffers& wb, unsigned k, unsigned e)
+{
+    const float* b = wb.rec + (size_t(k) * kWaveRecFloats) * wb.cap + e;
+    const size_t c = wb.cap;
+    HitRec h;
+    h.ray.o = v3(b[0 * c], b[1 * c], b[2 * c]);
+    h.ray.d = v3(b[3 * c], b[4 * c], b[5 * c]);
+    h.ray.t = b[6 * c];
+    h.normal = v3(b[7 * c], b[8 * c], b[9 * c]);
+    return shade_frame(h);
+}
+
+// sample sg of one computeLightContribution call -> (light record, sample within the light, first draw of that light)
+__device__ __forceinline__ LightSample wf_sample(const DevScene& s, const DevParams& p, unsigned sg, unsigned pixel, unsigned ctrBase)
+{
+    unsigned li = 0, si = sg, samples = 0, draws = 0, type = 0, ctr = ctrBase;
+    const float* L = s.lights;
+    for (;; li++) {
+        L = s.lights + size_t(li) * kLightFloats;
+        type = __float_as_uint(__ldg(L));
+        light_counts(type, p, samples, draws);
+        if (si < samples)
+            break;
+        si -= samples;
+        ctr += draws;
+    }
+    return sample_light(L, type, int(si), p, pixel, ctr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -244,6 +277,7 @@ __global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevPa
     unsigned char* visOut = nullptr;                // this unit's sample 0
     size_t visStride = 0;
     vec3 o = v3(0.0f), d = v3(0.0f), inv = v3(0.0f);
+    ShadeFrame frame {};
     unsigned stack[kFastStackSize];
     int sp = 0;
     unsigned cur = kDone;
@@ -275,6 +309,8 @@ __global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevPa
                         ctrBase = wf_draw_base(p, k, path, m.y & 255u);
                         const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
                         o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
+                        if (s.cull_zero_shading)
+                            frame = wf_load_frame(wb, k, e);
                         visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
                         visStride = cnt;
                         sg = 0;
@@ -284,21 +320,9 @@ __global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevPa
                 haveUnit = false;
             }
             if (!busy && haveUnit && sg < S) {
-                // sample sg -> (light, sample within the light, first draw of that light)
-                unsigned li = 0, si = sg, samples = 0, draws = 0, type = 0, ctr = ctrBase;
-                const float* L = s.lights;
-                for (;; li++) {
-                    L = s.lights + size_t(li) * kLightFloats;
-                    type = __float_as_uint(__ldg(L));
-                    light_counts(type, p, samples, draws);
-                    if (si < samples)
-                        break;
-                    si -= samples;
-                    ctr += draws;
-                }
-                const LightSample ls = sample_light(L, type, int(si), p, pixel, ctr);
-                if (!ls.shadowed) {
-                    visOut[size_t(sg) * visStride] = 1; // the reference does not test this sample
+                const LightSample ls = wf_sample(s, p, sg, pixel, ctrBase);
+                if (!ls.shadowed || shading_is_zero(s, frame, ls.pos)) {
+                    visOut[size_t(sg) * visStride] = 1; // the reference does not test this sample, or its term is exactly zero
                     sg++;
                 } else {
                     d = ls.pos - o;
@@ -427,24 +451,16 @@ __global__ void __launch_bounds__(128, 8) wf_vis_grouped_kernel(DevScene s, DevP
         const unsigned ctrBase = wf_draw_base(p, k, path, m.y & 255u);
         const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
         const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
+        ShadeFrame frame {};
+        if (s.cull_zero_shading)
+            frame = wf_load_frame(wb, k, e);
         unsigned char* visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
         const unsigned sEnd = min(S, (g + 1u) * kGroup);
         int occluder = -1; // the triangle that blocked this lane's previous sample: tested first (occluder coherence)
         for (unsigned sg = g * kGroup; sg < sEnd; sg++) {
-            unsigned li = 0, si = sg, samples = 0, draws = 0, type = 0, ctr = ctrBase;
-            const float* L = s.lights;
-            for (;; li++) { // sample -> (light, sample within the light, first draw of that light)
-                L = s.lights + size_t(li) * kLightFloats;
-                type = __float_as_uint(__ldg(L));
-                light_counts(type, p, samples, draws);
-                if (si < samples)
-                    break;
-                si -= samples;
-                ctr += draws;
-            }
-            const LightSample ls = sample_light(L, type, int(si), p, m.x, ctr);
+            const LightSample ls = wf_sample(s, p, sg, m.x, ctrBase);
             unsigned char v = 1;
-            if (ls.shadowed) {
+            if (ls.shadowed && !shading_is_zero(s, frame, ls.pos)) {
                 nshadow++;
                 const vec3 d = ls.pos - o;
                 float t;

@@ -325,3 +325,35 @@ def test_rgba8_output_stage_matches_reference_bitmap_writer(cge, ref, tmp_path):
         assert want.shape == rgba.shape
         assert np.array_equal(rgba[..., :3], want[..., :3]), name
         assert (rgba[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("name", ["c1_cornell", "c3_teapot_soft", "c4_monkey_mirror"])
+def test_zero_shading_cull_changes_no_bit(cge, name, monkeypatch):
+    """FAST traversal skips the shadow ray of a light sample with n.l <= 0 (its Phong term is exactly zero, shade.cuh
+    shading_is_zero): fewer rays traced, the frame identical bit for bit in every kernel variant."""
+    w, h = SMALL[name]
+    cfg = cge.configs.get(name, w * 2, h * 2)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        for flags in (0, cge.FLAG_PER_THREAD, cge.FLAG_WAVEFRONT | cge.FLAG_GROUPED_SHADE, cge.FLAG_WAVEFRONT | cge.FLAG_COUPLED_SHADE):
+            monkeypatch.setenv("CGE_ZERO_SHADING_CULL", "0")
+            rgb0, ids0, st0 = sc.render(cfg, traversal=1, flags=flags)
+            monkeypatch.setenv("CGE_ZERO_SHADING_CULL", "1")
+            rgb1, ids1, st1 = sc.render(cfg, traversal=1, flags=flags)
+            assert rgb0.tobytes() == rgb1.tobytes() and np.array_equal(ids0, ids1)
+            assert st1["shadow_rays"] < st0["shadow_rays"] and st1["reference_rays"] == st0["reference_rays"]
+
+
+def test_zero_shading_cull_off_for_unbounded_colours(cge):
+    """(kd * Lc) * 0 is NaN when the product overflows: with a light colour beyond the bound the cull must stay off."""
+    import copy
+    cfg = cge.configs.get("c1_cornell", 96, 96)
+    flat = cge.load_scene(cfg)
+    with cge.Scene(flat) as sc:
+        _, _, st_on = sc.render(cfg, traversal=1)
+    hot = copy.deepcopy(flat)
+    assert int(hot.lights[0]["type"]) == 0  # the Cornell box has one point light: position, colour
+    hot.lights[0]["v"][3:6] = 3e38
+    with cge.Scene(hot) as sc:
+        _, _, st_hot = sc.render(cfg, traversal=1)
+        _, _, st_ref = sc.render(cfg, traversal=0)
+    assert st_hot["shadow_rays"] == st_ref["shadow_rays"] > st_on["shadow_rays"]
