@@ -56,7 +56,9 @@ class CgeParams(C.Structure):
         ("width", C.c_int32), ("height", C.c_int32), ("features", C.c_uint32), ("ray_depth", C.c_int32),
         ("segment_samples", C.c_int32), ("parallelogram_samples", C.c_int32), ("sampler", C.c_uint32),
         ("seed", C.c_uint32), ("traversal", C.c_uint32), ("flags", C.c_uint32),
-        ("part_index", C.c_uint32), ("part_count", C.c_uint32), ("reserved", C.c_uint32 * 4),
+        ("part_index", C.c_uint32), ("part_count", C.c_uint32),
+        ("rays_per_pixel_side", C.c_int32), ("bloom_scalar", C.c_float), ("bloom_threshold", C.c_float),
+        ("bloom_debug_option", C.c_int32),
     ]
 
 
@@ -80,7 +82,7 @@ class CgeStats(C.Structure):
 ABI_SYMBOLS = [
     "cge_abi_version", "cge_last_error", "cge_device_count", "cge_camera_from_trackball", "cge_scene_create",
     "cge_scene_update_lights", "cge_scene_destroy", "cge_scene_bvh_info", "cge_scene_bvh_export", "cge_render",
-    "cge_bvh_build_reference_order",
+    "cge_bvh_build_reference_order", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
     "cge_comm_destroy", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
@@ -107,6 +109,8 @@ def lib() -> C.CDLL:
         l.cge_bvh_build_reference_order.argtypes = [C.POINTER(CgeSceneDesc), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] + [C.POINTER(C.c_uint32)] * 3
         l.cge_camera_from_trackball.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                                 C.POINTER(CgeCamera)]
+        l.cge_ray_sample_positions.argtypes = [C.c_int32] * 5 + [C.c_uint32, C.c_void_p]
+        l.cge_bloom_weights.argtypes = [C.c_float, C.c_void_p]
         l.cge_render.argtypes = [C.c_void_p, C.POINTER(CgeCamera), C.POINTER(CgeParams), C.c_void_p, C.c_void_p,
                                  C.POINTER(CgeStats)]
         l.cge_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(CgeParams), C.c_void_p, C.c_void_p]
@@ -151,6 +155,20 @@ def camera_from_cfg(cfg: dict) -> CgeCamera:
     return out
 
 
+def ray_sample_positions(width: int, height: int, x: int, y: int, n: int, seed: int) -> np.ndarray:
+    """Host-only: the n*n NDC sample positions of the anti-aliasing feature for one pixel (include/cge.h)."""
+    out = np.zeros((n * n, 2), np.float32)
+    _check(lib().cge_ray_sample_positions(width, height, x, y, n, seed, _p(out)))
+    return out
+
+
+def bloom_weights(sigma: float = 1.0) -> np.ndarray:
+    """Host-only: the library's weightsGaussian(sigma) as a 3x3 array."""
+    out = np.zeros(9, np.float32)
+    _check(lib().cge_bloom_weights(sigma, _p(out)))
+    return out.reshape(3, 3)
+
+
 def params_from_cfg(cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool = True, part=(0, 1),
                     flags: int = 0) -> CgeParams:
     p = CgeParams()
@@ -164,6 +182,11 @@ def params_from_cfg(cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool =
     p.traversal = traversal
     p.flags = (FLAG_WANT_PRIM_IDS if want_ids else 0) | flags
     p.part_index, p.part_count = part
+    # globals of the two implemented ExtraFeatures, reference defaults (src/render.cpp:14,19-21)
+    p.rays_per_pixel_side = cfg.get("rays_per_pixel_side", 3)
+    p.bloom_scalar = cfg.get("bloom_scalar", 0.3)
+    p.bloom_threshold = cfg.get("bloom_threshold", 0.4)
+    p.bloom_debug_option = cfg.get("bloom_debug_option", 0)
     return p
 
 

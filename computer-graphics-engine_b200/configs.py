@@ -17,6 +17,9 @@ FEAT_SOFT_SHADOW = 1 << 3
 FEAT_NORMAL_INTERP = 1 << 4
 FEAT_TEXTURE_MAPPING = 1 << 5
 FEAT_ACCEL_STRUCTURE = 1 << 6
+# the two implemented ExtraFeatures (bit 16 + position in the reference's ExtraFeatures struct, src/common.h:54-65)
+FEAT_BLOOM_EFFECT = 1 << 19
+FEAT_MULTIPLE_RAYS_PER_PIXEL = 1 << 22
 
 SCENE_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden" / "scenes"
 

@@ -82,6 +82,8 @@ struct Scratch {
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
     size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0;
+    float* bloomTmp = nullptr; // thresholded copy of the frame (renderBloomFilter's screenThreshold)
+    size_t bloomPixels = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
     bool staged = false; // evA..evC recorded by the last launch
@@ -235,8 +237,12 @@ int validate_params(const cge_scene* sc, const cge_params* p)
         return fail(CGE_ERR_INVALID_ARG, "null scene or params");
     if (p->width <= 0 || p->height <= 0 || int64_t(p->width) * p->height > (int64_t(1) << 30))
         return fail(CGE_ERR_INVALID_ARG, "bad resolution");
-    if (p->features & CGE_FEAT_EXTRA_MASK)
-        return fail(CGE_ERR_UNSUPPORTED, "ExtraFeatures (reference src/common.h:54-65) are outside the GPU hot path");
+    if (p->features & CGE_FEAT_EXTRA_MASK & ~CGE_FEAT_EXTRA_SUPPORTED)
+        return fail(CGE_ERR_UNSUPPORTED,
+            "of the ExtraFeatures (reference src/common.h:54-65) only enableBloomEffect and enableMultipleRaysPerPixel are implemented");
+    if ((p->features & CGE_FEAT_MULTIPLE_RAYS_PER_PIXEL)
+        && (p->rays_per_pixel_side < 1 || p->rays_per_pixel_side > kCgeMaxRaysPerPixelSide))
+        return fail(CGE_ERR_INVALID_ARG, "rays_per_pixel_side must be in [1, 10] (the reference GUI range, src/main.cpp:195)");
     if (p->features & ~(0x7fu | CGE_FEAT_EXTRA_MASK))
         return fail(CGE_ERR_INVALID_ARG, "unknown feature bits");
     if (p->ray_depth < 0 || p->ray_depth > kMaxRayDepth)
@@ -272,6 +278,7 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     d.part_count = p.part_count > 1 ? p.part_count : 1;
     d.n_tiles_x = uint32_t((p.width + kTileW - 1) / kTileW);
     d.n_tiles_y = uint32_t((p.height + kTileH - 1) / kTileH);
+    d.aa_side = (p.features & CGE_FEAT_MULTIPLE_RAYS_PER_PIXEL) ? uint32_t(p.rays_per_pixel_side) : 0u;
     return d;
 }
 
@@ -337,6 +344,72 @@ __global__ void pack_rgba8_kernel(const float* __restrict__ rgb, uchar4* __restr
     out[i] = make_uchar4(conv(rgb[i * 3]), conv(rgb[i * 3 + 1]), conv(rgb[i * 3 + 2]), 255);
 }
 
+// ---- extra.enableBloomEffect: renderBloomFilter (reference src/render.cpp:158-196) ---------------------------------
+// weightsGaussian(sigma) (src/render.cpp:198-210) with the reference's types: the exponent is an int divided by a float,
+// exp is the DOUBLE function (the reference object file imports `exp`, not `expf`), the normalisation 2 * 3.1415 * sigma^2
+// is double, each weight is rounded to float, the float sum normalises.  Indexed [k + 1][j + 1] like the glm::mat3.
+struct BloomWeights {
+    float w[3][3];
+};
+BloomWeights weights_gaussian(float sigma)
+{
+    BloomWeights a {};
+    float sum = 0.0f;
+    for (int i = -1; i < 2; i++)
+        for (int k = -1; k < 2; k++) {
+            const float weight = float(std::exp(double(-(i * i + k * k) / (2 * sigma * sigma))) / (2 * 3.1415 * sigma * sigma));
+            a.w[i + 1][k + 1] = weight;
+            sum += weight;
+        }
+    for (auto& col : a.w)
+        for (float& v : col)
+            v = v / sum;
+    return a;
+}
+
+// pass 1 (:165-170): pixels darker than the threshold become black.  brightness is evaluated in DOUBLE (the literals
+// 0.2126 / 0.7152 / 0.0722 are doubles) and rounded to float before the float comparison; NaN brightness keeps the pixel.
+__global__ void bloom_threshold_kernel(const float* __restrict__ rgb, float* __restrict__ thr, size_t pixels, float threshold)
+{
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= pixels)
+        return;
+    const float r = rgb[i * 3], g = rgb[i * 3 + 1], b = rgb[i * 3 + 2];
+    const double br = __dadd_rn(__dadd_rn(__dmul_rn(0.2126, double(r)), __dmul_rn(0.7152, double(g))), __dmul_rn(0.0722, double(b)));
+    const bool dark = __double2float_rn(br) < threshold;
+    thr[i * 3] = dark ? 0.0f : r;
+    thr[i * 3 + 1] = dark ? 0.0f : g;
+    thr[i * 3 + 2] = dark ? 0.0f : b;
+}
+
+// pass 2 (:171-195): 3x3 Gaussian of the thresholded image added to every pixel EXCEPT the last column (x = W-1) and the
+// bottom screen row (y = H-1 in reference coordinates), which the reference's loop bounds leave untouched.  k (x offset)
+// outer, j (y offset) inner, products summed in that order.  In place: a pixel's own value is the only thing read from rgb.
+__global__ void bloom_apply_kernel(float* __restrict__ rgb, const float* __restrict__ thr, int W, int H, BloomWeights wg, float scalar,
+    int debugOption)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W - 1 || y >= H - 1)
+        return;
+    auto indexAt = [&](int xx, int yy) { return size_t(H - 1 - yy) * size_t(W) + size_t(xx); }; // src/screen.cpp:45
+    vec3 sum = v3(0.0f);
+    for (int k = -1; k < 2; k++)
+        for (int j = -1; j < 2; j++) {
+            if (x + k < 0 || x + k > W - 1 || y + j < 0 || y + j > H - 1)
+                continue;
+            const float* t = thr + indexAt(x + k, y + j) * 3;
+            sum = sum + v3(t[0], t[1], t[2]) * wg.w[k + 1][j + 1];
+        }
+    float* px = rgb + indexAt(x, y) * 3;
+    const vec3 bloom = sum * scalar;
+    vec3 out = v3(px[0], px[1], px[2]);
+    if (debugOption == 0)
+        out = out + bloom;
+    else if (debugOption == 1)
+        out = bloom;
+    px[0] = out.x, px[1] = out.y, px[2] = out.z;
+}
+
 unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
 {
     const unsigned nTiles = d.n_tiles_x * d.n_tiles_y;
@@ -383,14 +456,15 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
     v.count = (p.flags & CGE_FLAG_COUNT_TESTS) != 0;
     v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
     v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
-        && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count;
+        && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count && !dp.aa_side;
     const size_t cap = size_t(tiles_of(dp, dp.part_index, dp.part_count)) * 32;
     v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
     // The wavefront pays off when a pixel's cost is wildly non-uniform, i.e. with area lights (16+ shadow rays per evaluation,
     // 2^k evaluations at level k).  Point-light frames (<= 1 shadow ray per light and hit, recursion folded) are bounded per
     // pixel and launch-latency sensitive: there the single per-thread kernel is faster.
     const bool areaLights = dp.draws_per_hit > 0 || (p.flags & CGE_FLAG_WAVEFRONT);
-    v.wave = v.fast && !v.coop && !v.count && areaLights && (p.features & CGE_FEAT_SHADING)
+    // several camera rays per pixel (anti-aliasing) share one running draw counter: per-thread kernel only for now
+    v.wave = v.fast && !v.coop && !v.count && areaLights && !dp.aa_side && (p.features & CGE_FEAT_SHADING)
         && !(p.flags & (CGE_FLAG_PER_THREAD | CGE_FLAG_DEBUG_CYCLES)) && v.waveBytes <= kWaveScratchLimit && cap > 0;
     return v;
 }
@@ -597,6 +671,27 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
     if (err != cudaSuccess)
         return fail(CGE_ERR_CUDA, std::string("render_kernel launch: ") + cudaGetErrorString(err));
     *launches += 1;
+    return CGE_OK;
+}
+
+// extra.enableBloomEffect on a complete frame resident on this GPU (src/render.cpp:326-328)
+int apply_bloom(Scratch* s, const cge_params& p, float* frame, uint32_t* launches)
+{
+    const size_t pixels = size_t(p.width) * size_t(p.height);
+    if (s->bloomPixels < pixels) {
+        if (s->bloomTmp)
+            cudaFree(s->bloomTmp);
+        s->bloomTmp = nullptr;
+        s->bloomPixels = 0;
+        CGE_CUDA(cudaMalloc(&s->bloomTmp, pixels * 3 * sizeof(float)));
+        s->bloomPixels = pixels;
+    }
+    bloom_threshold_kernel<<<unsigned((pixels + 255) / 256), 256, 0, s->stream>>>(frame, s->bloomTmp, pixels, p.bloom_threshold);
+    const dim3 block(32, 8), grid(unsigned((p.width + 31) / 32), unsigned((p.height + 7) / 8));
+    bloom_apply_kernel<<<grid, block, 0, s->stream>>>(frame, s->bloomTmp, p.width, p.height, weights_gaussian(1.0f), p.bloom_scalar,
+        p.bloom_debug_option);
+    CGE_CUDA(cudaGetLastError());
+    *launches += 2;
     return CGE_OK;
 }
 
@@ -979,6 +1074,7 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.next);
         cudaFree(s->wave.dir);
         cudaFree(s->wave.vis);
+        cudaFree(s->bloomTmp);
         cudaFree(s->wave.counts);
         if (s->ev0)
             cudaEventDestroy(s->ev0);
@@ -1054,6 +1150,40 @@ int cge_bvh_build_reference_order(const cge_scene_desc* d, cge_bvh_node* nodesOu
     return CGE_OK;
 }
 
+// Host evaluation of PixelSampler (shade.cuh): same generator (sampler.h), same fp32 operations in the same order; this TU is
+// compiled with -ffp-contract=off so the host compiler cannot fuse them either.
+int cge_ray_sample_positions(int32_t W, int32_t H, int32_t x, int32_t y, int32_t n, uint32_t seed, float* ndcOut)
+{
+    if (W <= 0 || H <= 0 || x < 0 || y < 0 || x >= W || y >= H || n < 1 || n > kCgeMaxRaysPerPixelSide || !ndcOut)
+        return fail(CGE_ERR_INVALID_ARG, "bad pixel, frame size or rays_per_pixel_side");
+    CgeMt19937Head mt(cge_aa_seed(seed, uint32_t(y) * uint32_t(W) + uint32_t(x)));
+    const float px = float(x) / float(W) * 2.0f - 1.0f, py = float(y) / float(H) * 2.0f - 1.0f;
+    const float bx = (1.0f / float(W) * 2.0f) / float(n), by = (1.0f / float(H) * 2.0f) / float(n);
+    auto uniform = [&](float b) {
+        float u = float(mt.next()) / 4294967296.0f;
+        if (u >= 1.0f)
+            u = 0.99999994f;
+        return u * (b - 0.0f) + 0.0f;
+    };
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            const float jy = uniform(by);
+            const float jx = uniform(bx);
+            *ndcOut++ = (px + float(i) * bx) + jx;
+            *ndcOut++ = (py + float(j) * by) + jy;
+        }
+    return CGE_OK;
+}
+
+int cge_bloom_weights(float sigma, float* out9)
+{
+    if (!out9)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    const BloomWeights w = weights_gaussian(sigma);
+    std::memcpy(out9, w.w, sizeof(w.w));
+    return CGE_OK;
+}
+
 int cge_scene_bvh_export(const cge_scene* sc, cge_bvh_node* nodesOut, uint32_t* orderOut)
 {
     if (!sc)
@@ -1077,6 +1207,9 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     const bool devOut = (p->flags & CGE_FLAG_RGB_DEVICE_PTR) && !rgba8;
     if (rgba8 && ((p->flags & CGE_FLAG_RGB_DEVICE_PTR) || p->part_count > 1))
         return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_OUTPUT_RGBA8 writes a whole host frame");
+    if ((p->features & CGE_FEAT_BLOOM_EFFECT) && p->part_count > 1)
+        return fail(CGE_ERR_UNSUPPORTED,
+            "the bloom filter reads neighbouring pixels: render the whole frame, or use cge_render_distributed");
     CGE_CUDA(cudaSetDevice(sc->device));
     const size_t pixels = size_t(p->width) * size_t(p->height);
     Scratch* s = nullptr;
@@ -1092,6 +1225,8 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     uint32_t launches = 0;
     cudaEventRecord(s->ev0, s->stream);
     rc = launch_render(sc, s, cam, p, dp, rgbDev, idsDev, &launches);
+    if (rc == CGE_OK && (p->features & CGE_FEAT_BLOOM_EFFECT))
+        rc = apply_bloom(s, *p, rgbDev, &launches);
     cudaEventRecord(s->ev1, s->stream);
     if (rc == CGE_OK && rgba8) {
         // ids (if wanted) leave first, then their buffer is reused for the packed pixels (4 bytes per pixel either way)
@@ -1587,6 +1722,9 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     }
     if (rc == CGE_OK && nr != ncclSuccess)
         rc = fail(CGE_ERR_NCCL, std::string("nccl gather: ") + api->GetErrorString(nr));
+    // the bloom filter is the one cross-pixel step of the path: it runs on rank 0 once the gathered frame is complete
+    if (rc == CGE_OK && comm->rank == 0 && (p.features & CGE_FEAT_BLOOM_EFFECT))
+        rc = apply_bloom(s, p, frame, &launches);
     if (rc == CGE_OK && comm->rank == 0 && !devOut) {
         cudaMemcpyAsync(rgbOut, s->rgb, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
         if (wantIds && idsOut)

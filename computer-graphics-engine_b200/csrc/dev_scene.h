@@ -88,6 +88,7 @@ struct DevParams {
     // wavefront shadow-ray granularity: 0 auto (decided on the device from the queue lengths), 1 coupled, 2 grouped, 3 decoupled
     uint32_t shade_mode;
     uint32_t grouped_below_chunks; // auto: trace 4 rays per lane when the launch has fewer 32-evaluation chunks than this
+    uint32_t aa_side;              // raysPerPixelSide when extra.enableMultipleRaysPerPixel is set, else 0
 };
 
 } // namespace cge

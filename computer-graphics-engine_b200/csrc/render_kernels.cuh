@@ -135,7 +135,8 @@ struct PixelTracer {
     //   no random draws  ->  L_k = (direct_k + L_{k+1}) + L_{k+1}, folded from the tail;
     //   soft shadows     ->  every copy draws its own jitter, so the 2^k direct terms of level k are evaluated in
     //                        the reference's depth-first order with a running draw counter.
-    __device__ vec3 final_color(Ray ray, unsigned pixel, int& primId)
+    // ctr: index of the pixel's next rand() draw; a pixel with several camera rays (anti-aliasing) keeps counting across them
+    __device__ vec3 final_color(Ray ray, unsigned pixel, int& primId, unsigned& ctr)
     {
         HitRec recs[kMaxLevels];
         vec3 directs[kMaxLevels];
@@ -182,7 +183,6 @@ struct PixelTracer {
         }
         vec3 acc[kMaxLevels];
         unsigned char state[kMaxLevels];
-        unsigned ctr = 0;
         int level = 0;
         acc[0] = direct(recs[0], pixel, ctr);
         ctr += p.draws_per_hit;
@@ -256,8 +256,31 @@ __global__ void __launch_bounds__(128, CGE_MINB_THREAD) render_kernel(DevScene s
             const long long t0 = p.debug_cycles ? clock64() : 0;
             const unsigned b0 = pt.nbox;
             const Ray ray = generate_ray(cam, x, y, p.width, p.height);
+            const unsigned pixel = unsigned(y) * unsigned(p.width) + unsigned(x);
             int primId;
-            const vec3 c = pt.final_color(ray, unsigned(y) * unsigned(p.width) + unsigned(x), primId);
+            unsigned ctr = 0;
+            vec3 c;
+            if (p.aa_side) {
+                // extra.enableMultipleRaysPerPixel (src/render.cpp:295-303,322): n*n jittered rays summed in order,
+                // color /= n*n; colorSum += color; finalColor = colorSum / float(weight = 1)
+                PixelSampler ps(p, x, y);
+                vec3 color = v3(0.0f);
+                for (int i = 0; i < int(p.aa_side); i++)
+                    for (int j = 0; j < int(p.aa_side); j++) {
+                        int subId;
+                        color = color + pt.final_color(ps.ray(cam, i, j), pixel, subId, ctr);
+                    }
+                color = color / float(int(p.aa_side * p.aa_side));
+                c = (v3(0.0f) + color) / 1.0f;
+                primId = -1;
+                if (ids) { // the id map stays that of the un-jittered pixel-corner ray (not a ray the reference traces: not counted)
+                    const Hit h = pt.closest(ray);
+                    if (h.prim >= 0)
+                        primId = int(h.gid & ~kSphereBit);
+                }
+            } else {
+                c = pt.final_color(ray, pixel, primId, ctr);
+            }
             if (p.debug_cycles) // development aid: per-pixel cost map in place of the primitive ids
                 primId = kCount ? int(pt.nbox - b0) : int((clock64() - t0) >> 4);
             store_pixel(p, rgb, ids, x, y, c, primId);
@@ -277,7 +300,8 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(DevScene s, DevParams p
         const float* q = rays7 + size_t(i) * 7;
         Ray ray { v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), q[6] };
         int primId;
-        const vec3 c = pt.final_color(ray, i, primId);
+        unsigned ctr = 0;
+        const vec3 c = pt.final_color(ray, i, primId, ctr);
         rgb[i * 3 + 0] = c.x;
         rgb[i * 3 + 1] = c.y;
         rgb[i * 3 + 2] = c.z;

@@ -226,11 +226,9 @@ __device__ __forceinline__ void light_counts(unsigned type, const DevParams& p, 
     }
 }
 
-__device__ __forceinline__ Ray generate_ray(const DevCamera& c, int x, int y, int W, int H)
+// Trackball::generateRay(pixel) (framework/src/trackball.cpp:101-110) for a position in normalised device coordinates
+__device__ __forceinline__ Ray generate_ray_ndc(const DevCamera& c, float px, float py)
 {
-    // src/render.cpp:286-289 (pixel CORNER, y up) + framework/src/trackball.cpp:101-110
-    const float px = fsub(fmul(fdiv(float(x), float(W)), 2.0f), 1.0f);
-    const float py = fsub(fmul(fdiv(float(y), float(H)), 2.0f), 1.0f);
     const vec3 camDir = normalize(v3(fmul(-px, c.half_w), fmul(py, c.half_h), 1.0f));
     Ray r;
     r.o = v3(c.ox, c.oy, c.oz);
@@ -238,5 +236,44 @@ __device__ __forceinline__ Ray generate_ray(const DevCamera& c, int x, int y, in
     r.t = FLT_MAX;
     return r;
 }
+
+__device__ __forceinline__ Ray generate_ray(const DevCamera& c, int x, int y, int W, int H)
+{
+    // src/render.cpp:286-289 (pixel CORNER, y up)
+    const float px = fsub(fmul(fdiv(float(x), float(W)), 2.0f), 1.0f);
+    const float py = fsub(fmul(fdiv(float(y), float(H)), 2.0f), 1.0f);
+    return generate_ray_ndc(c, px, py);
+}
+
+// getRaySamples (src/render.cpp:211-227): the n x n jittered camera rays of one pixel, in the reference's order (i over x
+// outer, j over y inner).  g++ evaluates the arguments of `glm::vec2(xJitter(gen), yJitter(gen))` right to left, so the
+// FIRST draw of a sample is its y jitter (pinned against the compiled reference, tests/test_oracle_pins.py).
+struct PixelSampler {
+    CgeMt19937Head mt;
+    float px, py, bx, by; // pixel corner and the size of one stratum (pixelBox) in NDC
+    __device__ PixelSampler(const DevParams& p, int x, int y)
+        : mt(cge_aa_seed(p.seed, unsigned(y) * unsigned(p.width) + unsigned(x)))
+    {
+        const float n = float(p.aa_side);
+        px = fsub(fmul(fdiv(float(x), float(p.width)), 2.0f), 1.0f);
+        py = fsub(fmul(fdiv(float(y), float(p.height)), 2.0f), 1.0f);
+        bx = fdiv(fmul(fdiv(1.0f, float(p.width)), 2.0f), n);
+        by = fdiv(fmul(fdiv(1.0f, float(p.height)), 2.0f), n);
+    }
+    // std::uniform_real_distribution<float>(0, b)(gen) as libstdc++ evaluates it: generate_canonical * (b - a) + a
+    __device__ float uniform(float b)
+    {
+        float u = fdiv(__uint2float_rn(mt.next()), 4294967296.0f);
+        if (u >= 1.0f)
+            u = 0.99999994f; // nextafter(1, 0)
+        return fadd(fmul(u, fsub(b, 0.0f)), 0.0f);
+    }
+    __device__ Ray ray(const DevCamera& c, int i, int j)
+    {
+        const float jy = uniform(by);
+        const float jx = uniform(bx);
+        return generate_ray_ndc(c, fadd(fadd(px, fmul(float(i), bx)), jx), fadd(fadd(py, fmul(float(j), by)), jy));
+    }
+};
 
 } // namespace cge

@@ -110,6 +110,11 @@ struct Scene {
 // the reference's tunables are mutable globals (src/light.cpp:12-13); kept as such on the host side, passed by value below
 inline int segmentLightSamples = 25;
 inline int parallelogramLightDirectionSamples = 5;
+// likewise the globals of the two implemented ExtraFeatures (src/render.cpp:14,19-21; extern in src/render.h:10-13,24)
+inline int raysPerPixelSide = 3;
+inline float bloomScalar = .3f;
+inline float bloomThreshold = .4f;
+inline int bloomDebugOption = 0;
 
 inline void check(int rc, const char* what)
 {
@@ -129,7 +134,8 @@ inline uint32_t featureBits(const Features& f)
     b |= f.enableAccelStructure ? CGE_FEAT_ACCEL_STRUCTURE : 0;
     const bool* e = reinterpret_cast<const bool*>(&f.extra);
     for (int i = 0; i < 10; i++)
-        b |= e[i] ? (1u << (16 + i)) : 0; // refused by the library (CGE_ERR_UNSUPPORTED), never silently ignored
+        b |= e[i] ? (1u << (16 + i)) : 0; // bloom and multiple rays per pixel are implemented; the library refuses the others
+                                          // (CGE_ERR_UNSUPPORTED), never silently ignores them
     return b;
 }
 
@@ -322,6 +328,10 @@ inline cge_params makeParams(const ivec2& res, const Features& features, int ray
     p.parallelogram_samples = parallelogramLightDirectionSamples;
     p.sampler = CGE_SAMPLER_HASH;
     p.traversal = CGE_TRAVERSAL_FAST;
+    p.rays_per_pixel_side = raysPerPixelSide;
+    p.bloom_scalar = bloomScalar;
+    p.bloom_threshold = bloomThreshold;
+    p.bloom_debug_option = bloomDebugOption;
     return p;
 }
 

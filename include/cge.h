@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CGE_ABI_VERSION 1
+#define CGE_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------------------ */
 enum {
@@ -49,8 +49,12 @@ enum {
     CGE_FEAT_NORMAL_INTERP = 1u << 4,   /* enableNormalInterp     */
     CGE_FEAT_TEXTURE_MAPPING = 1u << 5, /* enableTextureMapping   */
     CGE_FEAT_ACCEL_STRUCTURE = 1u << 6, /* enableAccelStructure   */
-    /* ExtraFeatures (src/common.h:54-65) occupy bits 16..25 in declaration order; any of them set makes
-       cge_render return CGE_ERR_UNSUPPORTED instead of silently rendering something else. */
+    /* ExtraFeatures (src/common.h:54-65) occupy bits 16..25 in declaration order.  Two are implemented (SURVEY.md 8f N2:
+       the ones that are per-pixel multipliers of the same kernels); any OTHER extra bit makes cge_render return
+       CGE_ERR_UNSUPPORTED instead of silently rendering something else. */
+    CGE_FEAT_BLOOM_EFFECT = 1u << 19,            /* extra.enableBloomEffect           (src/render.cpp:158-210,326-328) */
+    CGE_FEAT_MULTIPLE_RAYS_PER_PIXEL = 1u << 22, /* extra.enableMultipleRaysPerPixel  (src/render.cpp:211-227,295-303) */
+    CGE_FEAT_EXTRA_SUPPORTED = (1u << 19) | (1u << 22),
     CGE_FEAT_EXTRA_MASK = 0x03ff0000u
 };
 
@@ -200,7 +204,11 @@ typedef struct cge_params {
     /* image partition for multi-GPU: this call renders only tiles t with t % part_count == part_index
        (tiles are 8x4 pixels, numbered row-major).  part_count <= 1 renders the whole frame. */
     uint32_t part_index, part_count;
-    uint32_t reserved[4];
+    /* the globals the two implemented ExtraFeatures read; ignored unless the feature bit is set */
+    int32_t rays_per_pixel_side;  /* raysPerPixelSide = 3   (src/render.cpp:14; GUI range 1..10, src/main.cpp:195)   */
+    float bloom_scalar;           /* bloomScalar = .3f      (src/render.cpp:19)                                      */
+    float bloom_threshold;        /* bloomThreshold = .4f   (src/render.cpp:20)                                      */
+    int32_t bloom_debug_option;   /* bloomDebugOption = 0   (src/render.cpp:21): 0 image + bloom, 1 bloom only, 2 image */
 } cge_params;
 
 typedef struct cge_stats {
@@ -242,6 +250,14 @@ int cge_scene_bvh_info(const cge_scene* scene, uint32_t* n_nodes, uint32_t* n_le
  * n_spheres entries. */
 int cge_bvh_build_reference_order(const cge_scene_desc* desc, cge_bvh_node* nodes_out, uint32_t* n_nodes_inout,
                                   uint32_t* prim_order_out, uint32_t* root_out, uint32_t* n_levels_out, uint32_t* n_leaves_out);
+/* Host-only (no GPU needed): the host-side arithmetic of the two implemented ExtraFeatures, exposed for parity tests.
+ * cge_ray_sample_positions: the n*n sample positions of getRaySamples (src/render.cpp:211-227) for pixel (x, y) of a
+ * width x height frame, in normalised device coordinates (what the reference passes to Trackball::generateRay), drawn from
+ * the hash-seeded MT19937 stream the device code uses (csrc/sampler.h).  ndc_out: n*n (x, y) pairs.
+ * cge_bloom_weights: weightsGaussian(sigma) (src/render.cpp:198-210) as 9 floats, index [k + 1][j + 1]. */
+int cge_ray_sample_positions(int32_t width, int32_t height, int32_t x, int32_t y, int32_t rays_per_pixel_side, uint32_t seed,
+                             float* ndc_out);
+int cge_bloom_weights(float sigma, float* weights9_out);
 /* Copy out the BVH the library built (for parity tests against the reference's tree). Either pointer may be NULL. */
 int cge_scene_bvh_export(const cge_scene* scene, cge_bvh_node* nodes_out, uint32_t* prim_order_out);
 

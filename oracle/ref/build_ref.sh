@@ -61,7 +61,7 @@ WRAPS="-Wl,--wrap=_Z24intersectRayWithTriangleRKN3glm3vecILi3EfLNS_9qualifierE0E
        -Wl,--wrap=_Z21intersectRayWithShapeRK6SphereR3RayR7HitInfo
        -Wl,--wrap=_ZNK12BvhInterface9intersectER3RayR7HitInfoRK8Features"
 g++ -shared -fopenmp -o "$OUT/libcge_ref.so" $OBJ/ref_api.o $COMMON "$R/prebuilt/libIntersect_linux_x64.a" \
-    $WRAPS -Wl,--wrap=rand -Wl,-Bsymbolic -ldl
+    $WRAPS -Wl,--wrap=rand -Wl,--wrap=_ZNSt13random_device9_M_getvalEv -Wl,-Bsymbolic -ldl
 g++ -shared -fopenmp -o "$OUT/libcge_ref_plain.so" $OBJ/ref_api_plain.o $COMMON "$R/prebuilt/libIntersect_linux_x64.a" \
-    -Wl,--wrap=rand -Wl,-Bsymbolic -ldl
+    -Wl,--wrap=rand -Wl,--wrap=_ZNSt13random_device9_M_getvalEv -Wl,-Bsymbolic -ldl
 echo "built $OUT/libcge_ref.so $OUT/libcge_ref_plain.so"

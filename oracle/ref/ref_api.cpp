@@ -62,6 +62,9 @@
 
 #include "cge_scene_file.h"
 
+// defined in src/render.cpp:158 with external linkage, not declared in render.h
+void renderBloomFilter(Screen& screen, const Features& features);
+
 // ------------------------------------------------------------------------------------------------------
 // ld --wrap interposers
 // ------------------------------------------------------------------------------------------------------
@@ -101,6 +104,18 @@ int __wrap_rand(void)
         return __real_rand();
     return int(hashSample(g_seed, tls.pixel, tls.counter++));
 }
+}
+
+// getRaySamples (src/render.cpp:212-214) seeds a fresh std::mt19937 per pixel from std::random_device, which is
+// non-deterministic.  The only out-of-line piece is std::random_device::_M_getval() (libstdc++.so): wrapped, it returns a
+// hash of (seed, pixel), so the reference's own mt19937 + uniform_real_distribution run on a reproducible seed.
+// Must stay in sync with cge_aa_seed in computer-graphics-engine_b200/csrc/sampler.h.
+extern "C" unsigned int __real__ZNSt13random_device9_M_getvalEv(void*);
+extern "C" unsigned int __wrap__ZNSt13random_device9_M_getvalEv(void* self)
+{
+    if (g_samplerMode == 0)
+        return __real__ZNSt13random_device9_M_getvalEv(self);
+    return hashSample(g_seed ^ 0x52444556u, tls.pixel, 0u);
 }
 
 #ifndef CGE_REF_NO_COUNTERS
@@ -672,6 +687,10 @@ struct ref_render_params {
     int32_t x0, y0, x1, y1;
     // bounded sample for timing: render only rows y with (y - y0) % y_stride == 0 (0/1 = every row).
     int32_t y_stride;
+    // ExtraFeatures globals (src/render.cpp:14,19-21), applied when the corresponding feature bit (16 + index in ExtraFeatures) is set
+    int32_t rays_per_pixel_side;
+    float bloom_scalar, bloom_threshold;
+    int32_t bloom_debug_option;
 };
 struct ref_render_stats {
     uint64_t rays, box_tests, tri_tests, sphere_tests;
@@ -688,6 +707,13 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
     parallelogramLightDirectionSamples = p->parallelogram_samples;
     g_samplerMode = int(p->sampler);
     g_seed = p->seed;
+    if (p->rays_per_pixel_side > 0)
+        raysPerPixelSide = p->rays_per_pixel_side;
+    if (features.extra.enableBloomEffect) {
+        bloomScalar = p->bloom_scalar;
+        bloomThreshold = p->bloom_threshold;
+        bloomDebugOption = p->bloom_debug_option;
+    }
     if (p->threads > 0)
         omp_set_num_threads(p->threads);
     else
@@ -728,6 +754,20 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
                     };
                     tls.pixel = uint32_t(y) * uint32_t(W) + uint32_t(x);
                     tls.counter = 0;
+                    if (features.extra.enableMultipleRaysPerPixel) {
+                        // src/render.cpp:290-303,322 with the reference's own getRaySamples
+                        const glm::vec2 pixelSize { 1 / float(W) * 2.f, 1 / float(H) * 2.f };
+                        auto colorSum = glm::vec3(0.f);
+                        size_t weight = 0;
+                        auto color = glm::vec3(0.f);
+                        for (auto& ray : getRaySamples(normalizedPixelPos, pixelSize, camera, raysPerPixelSide))
+                            color += getFinalColor(rs->scene, bvh, ray, features, p->ray_depth);
+                        color /= raysPerPixelSide * raysPerPixelSide;
+                        colorSum += color;
+                        weight++;
+                        screen.setPixel(x, y, colorSum / float(weight));
+                        continue;
+                    }
                     const Ray cameraRay = camera.generateRay(normalizedPixelPos);
                     screen.setPixel(x, y, getFinalColor(rs->scene, bvh, cameraRay, features, p->ray_depth));
                 }
@@ -738,6 +778,8 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
             g_spheres += tls.spheres;
         }
     }
+    if (!p->use_render_ray_tracing && features.extra.enableBloomEffect)
+        renderBloomFilter(screen, features); // src/render.cpp:326-328 (renderRayTracing applies it itself)
     const auto t1 = std::chrono::high_resolution_clock::now();
     if (stats) {
         stats->ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -858,6 +900,37 @@ int ref_has_counters(void)
     return 1;
 #endif
 }
+// weightsGaussian(sigma) (src/render.cpp:198-210), column-major 3x3 as glm stores it
+void ref_weights_gaussian(float sigma, float* out9)
+{
+    const glm::mat3 m = weightsGaussian(sigma);
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++)
+            out9[c * 3 + r] = m[c][r];
+}
+
+// getRaySamples (src/render.cpp:211-227) for one pixel with the hash-seeded std::mt19937: n*n rays as (origin, direction)
+int ref_ray_samples(const ref_render_params* p, int x, int y, float* ray6)
+{
+    g_samplerMode = 1;
+    g_seed = p->seed;
+    const int W = p->width, H = p->height;
+    Window window { "oracle", glm::ivec2(W, H), OpenGLVersion::GL2, false };
+    Trackball camera { &window, p->fovy, p->dist };
+    camera.setCamera(glm::vec3(p->look_at[0], p->look_at[1], p->look_at[2]),
+        glm::vec3(p->rotation[0], p->rotation[1], p->rotation[2]), p->dist);
+    const glm::vec2 pos { float(x) / float(W) * 2.0f - 1.0f, float(y) / float(H) * 2.0f - 1.0f };
+    const glm::vec2 pixelSize { 1 / float(W) * 2.f, 1 / float(H) * 2.f };
+    tls.pixel = uint32_t(y) * uint32_t(W) + uint32_t(x);
+    tls.counter = 0;
+    int k = 0;
+    for (auto& r : getRaySamples(pos, pixelSize, camera, p->rays_per_pixel_side)) {
+        const float v[6] = { r.origin.x, r.origin.y, r.origin.z, r.direction.x, r.direction.y, r.direction.z };
+        std::memcpy(ray6 + 6 * k++, v, sizeof(v));
+    }
+    return k;
+}
+
 int ref_num_procs(void) { return omp_get_num_procs(); }
 
 } // extern "C"

@@ -3,6 +3,7 @@ the five configs (float RGB + primary-hit primitive ids + ray/box/triangle count
 libIntersect functions, and the reference-built BVH of each fixture scene.
 
     python tests/golden/make_golden.py            (build container; needs oracle/_ref built)
+    python tests/golden/make_golden.py extras     (only extras.npz: the ExtraFeatures cases of tests/extras_cases.py)
 """
 import importlib
 import sys
@@ -38,6 +39,25 @@ def scene_file_for(cfg, tmpdir):
     return pkg.configs.scene_path(cfg)
 
 
+def extras():
+    """tests/golden/extras.npz: the two implemented ExtraFeatures rendered by the unmodified reference (hash-seeded
+    std::mt19937 via the wrapped std::random_device), its Gaussian weights and its getRaySamples for a few pixels."""
+    import extras_cases
+    out = {"weights_sigma1": refharness.weights_gaussian(1.0)}
+    for key in extras_cases.CASES:
+        cfg = extras_cases.cfg_for(key)
+        with refharness.RefScene(pkg.configs.scene_path(cfg), cfg["features"]) as rs:
+            rgb, _, _ = rs.render(cfg, threads=0, want_ids=False)
+        out[key + "_rgb"] = rgb
+        print(key, cfg["width"], cfg["height"], hex(cfg["features"]), "max", float(np.nanmax(rgb)))
+    for n in (1, 2, 3, 10):
+        cfg = pkg.configs.get("c1_cornell", 64, 48)
+        cfg.update(rays_per_pixel_side=n, seed=7 + n)
+        out[f"ray_samples_n{n}"] = np.stack([refharness.ray_samples(cfg, x, y) for x, y in ((0, 0), (10, 20), (63, 47))])
+    np.savez_compressed(OUT / "extras.npz", **out)
+    print("wrote extras.npz")
+
+
 def main():
     import tempfile
     tmp = tempfile.mkdtemp()
@@ -71,4 +91,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["extras"]:
+        extras()
+    else:
+        main()
+        extras()

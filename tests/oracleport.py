@@ -39,8 +39,17 @@ def lib():
         l.oracle_kat_barycentric.argtypes = [C.c_void_p] * 3 + [C.c_uint32]
         l.oracle_kat_shading.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         l.oracle_kat_reflection.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        l.oracle_bloom.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32]
         _lib = l
     return _lib
+
+
+def bloom(rgb, scalar: float, threshold: float, debug_option: int = 0) -> np.ndarray:
+    """The restated renderBloomFilter (reference src/render.cpp:158-196) applied to a frame in Screen::pixels() order."""
+    out = np.ascontiguousarray(rgb, dtype=np.float32).copy()
+    h, w = out.shape[:2]
+    lib().oracle_bloom(_p(out), w, h, scalar, threshold, debug_option)
+    return out
 
 
 class OracleScene:

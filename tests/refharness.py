@@ -23,6 +23,8 @@ class RefRenderParams(C.Structure):
         ("want_ids", C.c_int32), ("fovy", C.c_float), ("look_at", C.c_float * 3), ("dist", C.c_float),
         ("rotation", C.c_float * 3), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
         ("y_stride", C.c_int32),
+        ("rays_per_pixel_side", C.c_int32), ("bloom_scalar", C.c_float), ("bloom_threshold", C.c_float),
+        ("bloom_debug_option", C.c_int32),
     ]
 
 
@@ -73,6 +75,8 @@ def lib(plain: bool = False):
         l.ref_kat_barycentric.argtypes = [C.c_void_p] * 3 + [C.c_uint32]
         l.ref_kat_shading.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         l.ref_kat_reflection.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        l.ref_weights_gaussian.argtypes = [C.c_float, C.c_void_p]
+        l.ref_ray_samples.argtypes = [C.POINTER(RefRenderParams), C.c_int, C.c_int, C.c_void_p]
         _libs[key] = l
     return _libs[key]
 
@@ -141,6 +145,11 @@ class RefScene:
         if window:
             p.x0, p.y0, p.x1, p.y1 = window
         p.y_stride = y_stride
+        # ExtraFeatures globals (reference src/render.cpp:14,19-21 defaults)
+        p.rays_per_pixel_side = cfg.get("rays_per_pixel_side", 3)
+        p.bloom_scalar = cfg.get("bloom_scalar", 0.3)
+        p.bloom_threshold = cfg.get("bloom_threshold", 0.4)
+        p.bloom_debug_option = cfg.get("bloom_debug_option", 0)
         return p
 
     def render(self, cfg: dict, threads: int = 0, want_ids: bool = True, window=None,
@@ -177,6 +186,24 @@ class RefScene:
         self.l.ref_intersect_rays(self.scene, self.bvh, _p(rays7), n, self.features if features is None else features,
                                   _p(hit), _p(t), _p(nrm), _p(mat), _p(ids))
         return hit, t, nrm, mat, ids
+
+
+def weights_gaussian(sigma: float = 1.0) -> np.ndarray:
+    """The reference's weightsGaussian(sigma) (src/render.cpp:198-210) as a 3x3 array indexed [k + 1][j + 1]."""
+    out = np.zeros(9, np.float32)
+    lib().ref_weights_gaussian(sigma, _p(out))
+    return out.reshape(3, 3)
+
+
+def ray_samples(cfg: dict, x: int, y: int) -> np.ndarray:
+    """The reference's getRaySamples (src/render.cpp:211-227) for pixel (x, y) with the hash-seeded std::mt19937:
+    (n*n, 6) origin + direction."""
+    p = RefScene.make_params(None, cfg)
+    n = p.rays_per_pixel_side
+    out = np.zeros((n * n, 6), np.float32)
+    got = lib().ref_ray_samples(C.byref(p), x, y, _p(out))
+    assert got == n * n
+    return out
 
 
 def camera(cfg: dict) -> CgeCamera:

@@ -209,8 +209,8 @@ def test_edge_cases(cge):
     with cge.Scene(cge.load_scene(cfg)) as sc:
         rgb, ids, st = sc.render(cfg)
         assert st["primary_rays"] == 33 * 17
-        # ExtraFeatures must be refused, not silently ignored
-        bad = dict(cfg, features=cfg["features"] | (1 << 19))
+        # ExtraFeatures other than bloom / multiple rays per pixel must be refused, not silently ignored
+        bad = dict(cfg, features=cfg["features"] | (1 << 16))
         with pytest.raises(cge.CgeError) as e:
             sc.render(bad)
         assert e.value.code == cge.ERR_UNSUPPORTED
