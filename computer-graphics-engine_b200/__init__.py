@@ -82,7 +82,7 @@ class CgeStats(C.Structure):
 ABI_SYMBOLS = [
     "cge_abi_version", "cge_last_error", "cge_device_count", "cge_camera_from_trackball", "cge_scene_create",
     "cge_scene_update_lights", "cge_scene_destroy", "cge_scene_bvh_info", "cge_scene_bvh_export", "cge_render",
-    "cge_bvh_build_reference_order", "cge_ray_sample_positions", "cge_bloom_weights",
+    "cge_bvh_build_reference_order", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
     "cge_comm_destroy", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
         l.cge_bvh_build_reference_order.argtypes = [C.POINTER(CgeSceneDesc), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] + [C.POINTER(C.c_uint32)] * 3
         l.cge_camera_from_trackball.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                                 C.POINTER(CgeCamera)]
+        l.cge_fast_bvh_build.argtypes = [C.POINTER(CgeSceneDesc), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] \
+            + [C.POINTER(C.c_uint32)] * 3 + [C.POINTER(C.c_float)]
         l.cge_ray_sample_positions.argtypes = [C.c_int32] * 5 + [C.c_uint32, C.c_void_p]
         l.cge_bloom_weights.argtypes = [C.c_float, C.c_void_p]
         l.cge_render.argtypes = [C.c_void_p, C.POINTER(CgeCamera), C.POINTER(CgeParams), C.c_void_p, C.c_void_p,
@@ -231,6 +233,24 @@ def build_reference_bvh_host(flat: FlatScene):
     _check(lib().cge_bvh_build_reference_order(C.byref(d), _p(nodes), C.byref(n), _p(order) if n_prims else None, C.byref(root),
                                                C.byref(levels), C.byref(leaves)))
     return nodes[: n.value], order, root.value, levels.value, leaves.value
+
+
+FAST_NODE_DT = np.dtype([("left_lower", "<f4", (3,)), ("left_upper", "<f4", (3,)), ("right_lower", "<f4", (3,)),
+                         ("right_upper", "<f4", (3,)), ("left", "<u4"), ("right", "<u4")])
+
+
+def build_fast_bvh(flat: FlatScene, on_gpu: bool, device: int = 0) -> dict:
+    """The FAST traversal tree by the GPU builder (the one scenes use) or the host builder (its checker; no GPU needed)."""
+    d, keep = scene_desc(flat)
+    n_prims = flat.n_primitives
+    nodes = np.zeros(max(n_prims, 1), FAST_NODE_DT)
+    order = np.zeros(n_prims, "<u4")
+    n = C.c_uint32(len(nodes))
+    root, depth, leaves, ms = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_float()
+    _check(lib().cge_fast_bvh_build(C.byref(d), int(on_gpu), device, _p(nodes), C.byref(n), _p(order) if n_prims else None,
+                                    C.byref(root), C.byref(depth), C.byref(leaves), C.byref(ms)))
+    return {"nodes": nodes[: n.value], "order": order, "root": root.value, "depth": depth.value, "leaves": leaves.value,
+            "build_ms": ms.value}
 
 
 class Scene:

@@ -15,6 +15,6 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function \
     -Xptxas -v $EXTRA \
     -I"$REPO/include" -I"$HERE" \
-    -shared -o "$OUT" "$HERE/cge_api.cu" "$HERE/bvh_build.cpp" "$HERE/bvh_sah.cpp" -ldl 2> "$LOG" || { cat "$LOG" >&2; exit 1; }
+    -shared -o "$OUT" "$HERE/cge_api.cu" "$HERE/bvh_sah_gpu.cu" "$HERE/bvh_build.cpp" "$HERE/bvh_sah.cpp" -ldl 2> "$LOG" || { cat "$LOG" >&2; exit 1; }
 grep -E "error|warning" "$LOG" | grep -v "ptxas info" | head -20 >&2 || true
 echo "built $OUT"

@@ -97,6 +97,8 @@ struct cge_scene {
     DevScene dev {};
     DevBuf<float4> nodes, tris, fnodes, ftris, shade, materials;
     FastBvh fast;
+    bool fast_built_on_gpu = false;
+    float fast_build_ms = 0.0f; // device time of the GPU SAH build
     DevBuf<int4> textures;
     DevBuf<float> texels, lights;
     HostBvh bvh;
@@ -915,9 +917,16 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     // ---- fast tree (binned SAH, <= 4 primitives per leaf) for CGE_TRAVERSAL_FAST; triangles-only scenes ---------------
     std::vector<float4> ftris, fnodes;
     if (haveBvh && d->n_spheres == 0) {
-        if (!build_sah_bvh(*d, sc->fast) || sc->fast.depth > uint32_t(kFastStackSize - 2)) {
+        // built on the GPU (bvh_sah_gpu.cu); the host builder produces the identical tree and serves scenes with non-finite
+        // coordinates.  CGE_SAH_BUILD=host forces it (A/B timing, tests).
+        const char* forced = std::getenv("CGE_SAH_BUILD");
+        const bool onGpu = sah_gpu_supported(*d) && !(forced && std::string(forced) == "host");
+        std::string buildErr;
+        const bool ok = onGpu ? build_sah_bvh_gpu(*d, sc->fast, &sc->fast_build_ms, &buildErr) : build_sah_bvh(*d, sc->fast);
+        sc->fast_built_on_gpu = onGpu;
+        if (!ok || sc->fast.depth > uint32_t(kFastStackSize - 2)) {
             delete sc;
-            return fail(CGE_ERR_UNSUPPORTED, "fast BVH build failed");
+            return fail(ok ? CGE_ERR_UNSUPPORTED : CGE_ERR_CUDA, buildErr.empty() ? "fast BVH build failed" : buildErr);
         }
         ftris = in_order(sc->fast.prim_order);
         fnodes.resize(sc->fast.nodes.size() * kNodeRows);
@@ -1181,6 +1190,50 @@ int cge_bloom_weights(float sigma, float* out9)
         return fail(CGE_ERR_INVALID_ARG, "null argument");
     const BloomWeights w = weights_gaussian(sigma);
     std::memcpy(out9, w.w, sizeof(w.w));
+    return CGE_OK;
+}
+
+// The FAST traversal tree alone, by either builder (parity test of the GPU builder against the host builder).
+int cge_fast_bvh_build(const cge_scene_desc* d, int onGpu, int device, cge_fast_node* nodesOut, uint32_t* nNodesInOut, uint32_t* orderOut,
+    uint32_t* rootOut, uint32_t* depthOut, uint32_t* nLeavesOut, float* buildMsOut)
+{
+    if (!d || !nNodesInOut || (d->n_triangles && (!d->triangles || !d->vertices || !d->meshes)))
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cge_fast_node) == sizeof(FastNode), "cge_fast_node mirrors FastNode");
+    FastBvh fb;
+    float ms = 0.0f;
+    if (onGpu) {
+        int nDev = 0;
+        if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+            cudaGetLastError();
+            return fail(CGE_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+        }
+        if (!sah_gpu_supported(*d))
+            return fail(CGE_ERR_UNSUPPORTED, "the GPU builder takes triangle scenes with finite coordinates");
+        CGE_CUDA(cudaSetDevice(device));
+        std::string err;
+        if (!build_sah_bvh_gpu(*d, fb, &ms, &err))
+            return fail(CGE_ERR_CUDA, err);
+    } else if (!build_sah_bvh(*d, fb)) {
+        return fail(CGE_ERR_INVALID_ARG, "scene has no primitives");
+    }
+    const uint32_t room = *nNodesInOut;
+    *nNodesInOut = uint32_t(fb.nodes.size());
+    if (rootOut)
+        *rootOut = fb.root;
+    if (depthOut)
+        *depthOut = fb.depth;
+    if (nLeavesOut)
+        *nLeavesOut = fb.n_leaves;
+    if (buildMsOut)
+        *buildMsOut = ms;
+    if (nodesOut) {
+        if (room < fb.nodes.size())
+            return fail(CGE_ERR_INVALID_ARG, "nodes_out too small");
+        std::memcpy(nodesOut, fb.nodes.data(), fb.nodes.size() * sizeof(FastNode));
+    }
+    if (orderOut)
+        std::memcpy(orderOut, fb.prim_order.data(), fb.prim_order.size() * sizeof(uint32_t));
     return CGE_OK;
 }
 

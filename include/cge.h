@@ -250,6 +250,19 @@ int cge_scene_bvh_info(const cge_scene* scene, uint32_t* n_nodes, uint32_t* n_le
  * n_spheres entries. */
 int cge_bvh_build_reference_order(const cge_scene_desc* desc, cge_bvh_node* nodes_out, uint32_t* n_nodes_inout,
                                   uint32_t* prim_order_out, uint32_t* root_out, uint32_t* n_levels_out, uint32_t* n_leaves_out);
+/* The tree CGE_TRAVERSAL_FAST walks (binned SAH, <= 4 primitives per leaf; csrc/sah_split.h specifies it), built by the GPU
+ * builder (on_gpu != 0, the one cge_scene_create uses) or by the host builder (on_gpu == 0, no GPU needed).  Both must return
+ * the same tree bit for bit.  Inner nodes in depth-first pre-order; child reference: bit 31 = leaf (bits 28..30 = count - 1,
+ * bits 0..27 = first primitive in prim_order_out), else inner-node index.  nodes_out has room for *n_nodes_inout nodes (at
+ * most n_triangles); either output pointer may be NULL.  build_ms_out: device time of the GPU build kernels. */
+typedef struct cge_fast_node {
+    float left_lower[3], left_upper[3];
+    float right_lower[3], right_upper[3];
+    uint32_t left, right;
+} cge_fast_node;
+int cge_fast_bvh_build(const cge_scene_desc* desc, int on_gpu, int device, cge_fast_node* nodes_out, uint32_t* n_nodes_inout,
+                       uint32_t* prim_order_out, uint32_t* root_out, uint32_t* depth_out, uint32_t* n_leaves_out,
+                       float* build_ms_out);
 /* Host-only (no GPU needed): the host-side arithmetic of the two implemented ExtraFeatures, exposed for parity tests.
  * cge_ray_sample_positions: the n*n sample positions of getRaySamples (src/render.cpp:211-227) for pixel (x, y) of a
  * width x height frame, in normalised device coordinates (what the reference passes to Trackball::generateRay), drawn from
