@@ -70,6 +70,8 @@ struct DevBuf {
     }
 };
 
+constexpr unsigned kMaxBands = 8;
+
 struct Scratch {
     float* rgb = nullptr;
     int* ids = nullptr;
@@ -85,8 +87,15 @@ struct Scratch {
     float* bloomTmp = nullptr; // thresholded copy of the frame (renderBloomFilter's screenThreshold)
     size_t bloomPixels = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
-    bool staged = false; // evA..evC recorded by the last launch
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t stage[5] = {}; // wavefront stage boundaries: chain | shadow rays | shading | fold |
+    bool staged = false;       // stage[] recorded by the last launch
+    // a frame rendered in concurrent bands (cge_render) uses one Scratch per band: kernels done / output copied
+    cudaEvent_t bandDone = nullptr, copyDone = nullptr;
+    // band b runs on a stream of priority (greatest - b), so that earlier bands win the SMs and finish (and leave for the
+    // host) first while later bands fill the SMs they leave idle; created on first use, `stream` points at one of them or at
+    // `baseStream` for the duration of a call
+    cudaStream_t baseStream = nullptr, prioStream[kMaxBands] = {};
     bool busy = false;
 };
 } // namespace
@@ -188,13 +197,14 @@ int acquire_scratch(cge_scene* sc, size_t pixels, bool wantIds, size_t gatherPix
     *out = s;
     if (!s->stream) {
         CGE_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->baseStream = s->stream;
         CGE_CUDA(cudaEventCreate(&s->ev0));
         CGE_CUDA(cudaEventCreate(&s->ev1));
         CGE_CUDA(cudaEventCreate(&s->ev2));
-        CGE_CUDA(cudaEventCreate(&s->evA));
-        CGE_CUDA(cudaEventCreate(&s->evB));
-        CGE_CUDA(cudaEventCreate(&s->evC));
-        CGE_CUDA(cudaEventCreate(&s->evD));
+        for (auto& ev : s->stage)
+            CGE_CUDA(cudaEventCreate(&ev));
+        CGE_CUDA(cudaEventCreateWithFlags(&s->bandDone, cudaEventDisableTiming));
+        CGE_CUDA(cudaEventCreateWithFlags(&s->copyDone, cudaEventDisableTiming));
         CGE_CUDA(cudaMalloc(&s->tileCounter, 64));
         CGE_CUDA(cudaMalloc(&s->counters, sizeof(Counters)));
     }
@@ -229,6 +239,8 @@ void release_scratch(cge_scene* sc, Scratch* s)
 {
     if (!s)
         return;
+    if (s->baseStream)
+        s->stream = s->baseStream;
     std::lock_guard<std::mutex> lk(sc->mu);
     s->busy = false;
 }
@@ -281,6 +293,9 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     d.n_tiles_x = uint32_t((p.width + kTileW - 1) / kTileW);
     d.n_tiles_y = uint32_t((p.height + kTileH - 1) / kTileH);
     d.aa_side = (p.features & CGE_FEAT_MULTIPLE_RAYS_PER_PIXEL) ? uint32_t(p.rays_per_pixel_side) : 0u;
+    const uint32_t nTiles = d.n_tiles_x * d.n_tiles_y;
+    d.tile_first = 0;
+    d.tile_count = nTiles > d.part_index ? (nTiles - d.part_index + d.part_count - 1) / d.part_count : 0;
     return d;
 }
 
@@ -459,7 +474,7 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
     v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
     v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
         && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count && !dp.aa_side;
-    const size_t cap = size_t(tiles_of(dp, dp.part_index, dp.part_count)) * 32;
+    const size_t cap = size_t(dp.tile_count) * 32;
     v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
     // The wavefront pays off when a pixel's cost is wildly non-uniform, i.e. with area lights (16+ shadow rays per evaluation,
     // 2^k evaluations at level k).  Point-light frames (<= 1 shadow ray per light and hit, recursion folded) are bounded per
@@ -542,9 +557,10 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         cam->half_width, cam->half_height };
     CGE_CUDA(cudaMemsetAsync(s->tileCounter, 0, 64, s->stream));
     CGE_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream));
-    const Variant v = choose_variant(ds, *p, dp);
     s->staged = false;
-    const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
+    const Variant v = choose_variant(ds, *p, dp);
+    cudaEvent_t* stage = s->stage;
+    const unsigned myTiles = dp.tile_count;
     cudaError_t err = cudaSuccess;
     auto grid_for = [&](int perSm) {
         // persistent CTAs: a multiple of the SM count, never more CTAs than there are 4-tile batches
@@ -604,10 +620,10 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         if (err == cudaSuccess)
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
         if (err == cudaSuccess) {
-            cudaEventRecord(s->evA, s->stream);
+            cudaEventRecord(stage[0], s->stream);
             wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
             err = cudaGetLastError();
-            cudaEventRecord(s->evB, s->stream);
+            cudaEventRecord(stage[1], s->stream);
         }
         if (err == cudaSuccess && decoupled) {
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_visibility_kernel, 128, 0);
@@ -625,7 +641,7 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
                 *launches += 1;
             }
         }
-        cudaEventRecord(s->evC, s->stream);
+        cudaEventRecord(stage[2], s->stream);
         if (err == cudaSuccess && wp.shade_mode <= 1) {
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel<false>, 128, 0);
             if (err == cudaSuccess) {
@@ -642,12 +658,13 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
                 *launches += 1;
             }
         }
-        cudaEventRecord(s->evD, s->stream);
-        s->staged = true;
+        cudaEventRecord(stage[3], s->stream);
         if (err == cudaSuccess) {
             wf_fold_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(wp, s->wave, rgbDev);
             err = cudaGetLastError();
         }
+        cudaEventRecord(stage[4], s->stream);
+        s->staged = true;
         *launches += 1; // chain + fold (the caller adds one)
     } else if (v.coop) {
         auto kern = render_coop_kernel;
@@ -697,33 +714,116 @@ int apply_bloom(Scratch* s, const cge_params& p, float* frame, uint32_t* launche
     return CGE_OK;
 }
 
-int fill_stats(Scratch* s, cge_stats* st, uint32_t launches)
+// Number of concurrent bands of a launch (a frame in cge_render, a rank's partition in cge_render_distributed).  Measured on
+// B200 (tools/sweep_bands.py): the wavefront pipeline gains from ~1 Mpixel up (its stages have long tails), the
+// single per-thread kernel only through the overlapped copy of a host-output frame; small launches are launch-latency bound
+// and stay in one piece.
+unsigned nBandsFor(const cge_scene* sc, const cge_params& p, const DevParams& dp, bool hostCopy)
+{
+    const size_t pixels = size_t(dp.tile_count) * 32;
+    unsigned n = 1;
+    const bool wave = choose_variant(scene_for(sc, p), p, dp).wave;
+    if (wave)
+        n = pixels >= (size_t(3) << 20) ? 4 : pixels >= (size_t(3) << 18) ? 2 : 1;
+    else if (hostCopy)
+        n = pixels >= (size_t(2) << 20) ? 4 : 1;
+    n = unsigned(std::max(env_int("CGE_BANDS", int(n)), 1));
+    return std::min<unsigned>({ n, kMaxBands, std::max(dp.n_tiles_y, 1u), std::max(dp.tile_count, 1u) });
+}
+
+int use_band_stream(Scratch* s, unsigned band)
+{
+    int least = 0, greatest = 0;
+    CGE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest)); // numerically lower = higher priority
+    const int prio = std::min(greatest + int(band), least);
+    if (!s->prioStream[band])
+        CGE_CUDA(cudaStreamCreateWithPriority(&s->prioStream[band], cudaStreamNonBlocking, prio));
+    s->stream = s->prioStream[band];
+    return CGE_OK;
+}
+
+// One Scratch (stream, queues, counters) per band; bands[0] is the caller's.  Returns with rc != OK after releasing the helpers.
+int acquire_bands(cge_scene* sc, Scratch* primary, unsigned nBands, std::vector<Scratch*>& bands)
+{
+    bands.assign(1, primary);
+    for (unsigned b = 1; b < nBands; b++) {
+        Scratch* h = nullptr;
+        const int rc = acquire_scratch(sc, 1, false, 0, &h);
+        if (h)
+            bands.push_back(h);
+        if (rc != CGE_OK) {
+            for (unsigned k = 1; k < bands.size(); k++)
+                release_scratch(sc, bands[k]);
+            bands.resize(1);
+            return rc;
+        }
+    }
+    return CGE_OK;
+}
+
+// Render entries [first[b], first[b] + count[b]) of the launch's tile list as concurrent pipelines, band b on bands[b]'s
+// stream.  The persistent kernels of one band drain while another band's kernels fill the freed SMs, which hides the tail
+// every stage otherwise leaves (the slowest 8x4 tile of the chain kernel alone runs 0.8 ms on config C5).  staggered: band b
+// gets stream priority (greatest - b), so that the bands finish one after the other and `after(b, scratch)` - which must
+// record scratch->bandDone when the band's kernels are queued - can start the band's copy while later bands are traced;
+// otherwise all bands share the top priority, which hides the tails best.  On return the primary stream has waited for the
+// kernels of every band; ev0 must already be recorded on it.
+template <typename After>
+int launch_bands(cge_scene* sc, const std::vector<Scratch*>& bands, const std::vector<uint2>& ranges, bool staggered, const cge_camera* cam,
+    const cge_params* p, const DevParams& dp, float* rgbDev, int* idsDev, uint32_t* launches, After&& after)
+{
+    Scratch* s = bands[0];
+    for (unsigned b = 0; b < bands.size(); b++) {
+        Scratch* sb = bands[b];
+        if (b) {
+            const int rc = use_band_stream(sb, staggered ? b : 0);
+            if (rc != CGE_OK)
+                return rc;
+            cudaStreamWaitEvent(sb->stream, s->ev0, 0);
+        }
+        DevParams bp = dp;
+        bp.tile_first = ranges[b].x;
+        bp.tile_count = ranges[b].y;
+        const int rc = launch_render(sc, sb, cam, p, bp, rgbDev, idsDev, launches);
+        if (rc != CGE_OK)
+            return rc;
+        after(b, sb);
+    }
+    for (unsigned b = 1; b < bands.size(); b++)
+        cudaStreamWaitEvent(s->stream, bands[b]->bandDone, 0);
+    return CGE_OK;
+}
+
+// bands: the Scratch of every band of the frame, the primary one (which holds ev0..ev2) first
+int fill_stats(const std::vector<Scratch*>& bands, cge_stats* st, uint32_t launches)
 {
     if (!st)
         return CGE_OK;
-    Counters c {};
-    CGE_CUDA(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
-    CGE_CUDA(cudaStreamSynchronize(s->stream));
+    Scratch* s = bands[0];
     std::memset(st, 0, sizeof(*st));
-    st->primary_rays = c.primary;
-    st->bounce_rays = c.bounce;
-    st->shadow_rays = c.shadow;
-    st->reference_rays = c.reference;
-    st->box_tests = c.box;
-    st->tri_tests = c.tri;
-    st->reference_shadow_rays = c.reference_shadow;
     float ms = 0.f;
+    for (Scratch* b : bands) {
+        Counters c {};
+        CGE_CUDA(cudaMemcpyAsync(&c, b->counters, sizeof(c), cudaMemcpyDeviceToHost, b->stream));
+        CGE_CUDA(cudaStreamSynchronize(b->stream));
+        st->primary_rays += c.primary;
+        st->bounce_rays += c.bounce;
+        st->shadow_rays += c.shadow;
+        st->reference_rays += c.reference;
+        st->box_tests += c.box;
+        st->tri_tests += c.tri;
+        st->reference_shadow_rays += c.reference_shadow;
+        if (b->staged) // summed over the bands (which overlap in time when there are several)
+            for (int k = 0; k < 4; k++) {
+                CGE_CUDA(cudaEventElapsedTime(&ms, b->stage[k], b->stage[k + 1]));
+                st->stage_ms[k] += ms;
+            }
+    }
     CGE_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     st->kernel_ms = ms;
     CGE_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev2));
     st->total_ms = ms;
     st->kernel_launches = launches;
-    if (s->staged) {
-        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[0], s->evA, s->evB));
-        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[1], s->evB, s->evC));
-        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[2], s->evC, s->evD));
-        CGE_CUDA(cudaEventElapsedTime(&st->stage_ms[3], s->evD, s->ev1));
-    }
     return CGE_OK;
 }
 
@@ -1091,14 +1191,16 @@ int cge_scene_destroy(cge_scene* sc)
             cudaEventDestroy(s->ev1);
         if (s->ev2)
             cudaEventDestroy(s->ev2);
-        if (s->evA)
-            cudaEventDestroy(s->evA);
-        if (s->evB)
-            cudaEventDestroy(s->evB);
-        if (s->evC)
-            cudaEventDestroy(s->evC);
-        if (s->evD)
-            cudaEventDestroy(s->evD);
+        for (auto& ev : s->stage)
+            if (ev)
+                cudaEventDestroy(ev);
+        for (auto& ps : s->prioStream)
+            if (ps)
+                cudaStreamDestroy(ps);
+        if (s->bandDone)
+            cudaEventDestroy(s->bandDone);
+        if (s->copyDone)
+            cudaEventDestroy(s->copyDone);
         if (s->stream)
             cudaStreamDestroy(s->stream);
         delete s;
@@ -1276,12 +1378,61 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     float* rgbDev = devOut ? rgbOut : s->rgb;
     int* idsDev = wantIds ? (devOut ? idsOut : s->ids) : nullptr;
     uint32_t launches = 0;
+    // A large frame is rendered as several horizontal bands of tile rows (launch_bands); a band that is finished travels to
+    // the host while the others are still traced.  Not with bloom (it needs the complete frame), not when the ids share their
+    // buffer with the packed pixels, and a partition (part_count > 1) is left to cge_render_distributed.
+    unsigned nBands = 1;
+    if (dp.part_count <= 1 && !(p->features & CGE_FEAT_BLOOM_EFFECT) && !(rgba8 && wantIds))
+        nBands = nBandsFor(sc, *p, dp, !devOut);
+    std::vector<Scratch*> bands;
+    rc = acquire_bands(sc, s, nBands, bands);
+    if (rc == CGE_OK && nBands > 1)
+        rc = use_band_stream(s, 0);
+    if (rc != CGE_OK) {
+        for (Scratch* b : bands)
+            release_scratch(sc, b);
+        return rc;
+    }
     cudaEventRecord(s->ev0, s->stream);
-    rc = launch_render(sc, s, cam, p, dp, rgbDev, idsDev, &launches);
-    if (rc == CGE_OK && (p->features & CGE_FEAT_BLOOM_EFFECT))
-        rc = apply_bloom(s, *p, rgbDev, &launches);
-    cudaEventRecord(s->ev1, s->stream);
-    if (rc == CGE_OK && rgba8) {
+    if (nBands > 1) {
+        std::vector<uint2> ranges;
+        std::vector<unsigned> rows; // tile-row boundaries of the bands
+        for (unsigned b = 0; b <= nBands; b++)
+            rows.push_back(unsigned(uint64_t(dp.n_tiles_y) * b / nBands));
+        for (unsigned b = 0; b < nBands; b++)
+            ranges.push_back(make_uint2(rows[b] * dp.n_tiles_x, (rows[b + 1] - rows[b]) * dp.n_tiles_x));
+        rc = launch_bands(sc, bands, ranges, !devOut, cam, p, dp, rgbDev, idsDev, &launches, [&](unsigned b, Scratch* sb) {
+            // tile rows [r0, r1) = reference rows y in [4 r0, min(4 r1, H)) = frame rows [H - yEnd, H - yBeg) (Screen's y flip)
+            const int yBeg = int(rows[b]) * kTileH, yEnd = std::min(int(rows[b + 1]) * kTileH, p->height);
+            const size_t first = size_t(p->height - yEnd) * size_t(p->width), count = size_t(yEnd - yBeg) * size_t(p->width);
+            if (rgba8) {
+                pack_rgba8_kernel<<<unsigned((count + 255) / 256), 256, 0, sb->stream>>>(s->rgb + first * 3,
+                    reinterpret_cast<uchar4*>(s->ids) + first, count);
+                launches++;
+            }
+            cudaEventRecord(sb->bandDone, sb->stream);
+            if (rgba8) {
+                cudaMemcpyAsync(reinterpret_cast<uchar4*>(rgbOut) + first, reinterpret_cast<uchar4*>(s->ids) + first, count * 4,
+                    cudaMemcpyDeviceToHost, sb->stream);
+            } else if (!devOut) {
+                cudaMemcpyAsync(rgbOut + first * 3, s->rgb + first * 3, count * 3 * sizeof(float), cudaMemcpyDeviceToHost, sb->stream);
+                if (wantIds)
+                    cudaMemcpyAsync(idsOut + first, s->ids + first, count * sizeof(int), cudaMemcpyDeviceToHost, sb->stream);
+            }
+            cudaEventRecord(sb->copyDone, sb->stream);
+        });
+        cudaEventRecord(s->ev1, s->stream);
+        for (unsigned b = 1; b < bands.size(); b++)
+            cudaStreamWaitEvent(s->stream, bands[b]->copyDone, 0);
+    } else {
+        rc = launch_render(sc, s, cam, p, dp, rgbDev, idsDev, &launches);
+        if (rc == CGE_OK && (p->features & CGE_FEAT_BLOOM_EFFECT))
+            rc = apply_bloom(s, *p, rgbDev, &launches);
+        cudaEventRecord(s->ev1, s->stream);
+    }
+    if (nBands > 1) {
+        // every band is already on its way
+    } else if (rc == CGE_OK && rgba8) {
         // ids (if wanted) leave first, then their buffer is reused for the packed pixels (4 bytes per pixel either way)
         if (wantIds)
             cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
@@ -1297,8 +1448,7 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
             // partial frame: copy back only the rows of tiles this partition touched would need a gather;
             // callers that partition (cge_render_distributed) use the packed path instead.  Here: full copy of the
             // scratch frame is wrong for untouched pixels, so copy tile rows individually.
-            const unsigned myTiles = tiles_of(dp, dp.part_index, dp.part_count);
-            for (unsigned k = 0; k < myTiles; k++) {
+            for (unsigned k = 0; k < dp.tile_count; k++) {
                 const unsigned tile = dp.part_index + k * dp.part_count;
                 const int x0 = int(tile % dp.n_tiles_x) * kTileW, y0 = int(tile / dp.n_tiles_x) * kTileH;
                 const int w = std::min(kTileW, p->width - x0);
@@ -1315,9 +1465,15 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (rc == CGE_OK && e != cudaSuccess)
         rc = fail(CGE_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    for (unsigned b = 1; b < bands.size(); b++) {
+        const cudaError_t eb = cudaStreamSynchronize(bands[b]->stream);
+        if (rc == CGE_OK && eb != cudaSuccess)
+            rc = fail(CGE_ERR_CUDA, std::string("render: ") + cudaGetErrorString(eb));
+    }
     if (rc == CGE_OK)
-        rc = fill_stats(s, st, launches);
-    release_scratch(sc, s);
+        rc = fill_stats(bands, st, launches);
+    for (Scratch* b : bands)
+        release_scratch(sc, b);
     return rc;
 }
 
@@ -1730,11 +1886,33 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     }
     ncclComm_t nc = static_cast<ncclComm_t>(comm->nccl);
     uint32_t launches = 0;
+    // every rank renders its interleaved tile subset straight into the full-frame layout of its own scratch frame, as
+    // concurrent bands of its tile list when the share is large enough (launch_bands: the stage tails do not shrink with the
+    // partition, so they weigh more the more GPUs share the frame)
+    const unsigned nBands = nBandsFor(sc, p, dp, false);
+    std::vector<Scratch*> bands;
+    rc = acquire_bands(sc, s, nBands, bands);
+    if (rc == CGE_OK && nBands > 1)
+        rc = use_band_stream(s, 0);
+    if (rc != CGE_OK) {
+        for (Scratch* b : bands)
+            release_scratch(sc, b);
+        return rc;
+    }
     cudaEventRecord(s->ev0, s->stream);
-    // every rank renders its interleaved tile subset straight into the full-frame layout of its own scratch frame
     float* frame = (comm->rank == 0 && devOut) ? rgbOut : s->rgb;
     int* frameIds = wantIds ? ((comm->rank == 0 && devOut && idsOut) ? idsOut : s->ids) : nullptr;
-    rc = launch_render(sc, s, cam, &p, dp, frame, frameIds, &launches);
+    if (nBands > 1) {
+        std::vector<uint2> ranges;
+        for (unsigned b = 0; b < nBands; b++) {
+            const unsigned f0 = unsigned(uint64_t(myTiles) * b / nBands), f1 = unsigned(uint64_t(myTiles) * (b + 1) / nBands);
+            ranges.push_back(make_uint2(f0, f1 - f0));
+        }
+        rc = launch_bands(sc, bands, ranges, false, cam, &p, dp, frame, frameIds, &launches,
+            [&](unsigned, Scratch* sb) { cudaEventRecord(sb->bandDone, sb->stream); });
+    } else {
+        rc = launch_render(sc, s, cam, &p, dp, frame, frameIds, &launches);
+    }
     cudaEventRecord(s->ev1, s->stream);
     ncclResult_t nr = ncclSuccess;
     if (rc == CGE_OK && R > 1) {
@@ -1787,9 +1965,12 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (rc == CGE_OK && e != cudaSuccess)
         rc = fail(CGE_ERR_CUDA, std::string("render_distributed: ") + cudaGetErrorString(e));
+    for (unsigned b = 1; b < bands.size(); b++)
+        cudaStreamSynchronize(bands[b]->stream);
     if (rc == CGE_OK)
-        rc = fill_stats(s, st, launches);
-    release_scratch(sc, s);
+        rc = fill_stats(bands, st, launches);
+    for (Scratch* b : bands)
+        release_scratch(sc, b);
     return rc;
 }
 

@@ -80,6 +80,9 @@ struct DevParams {
     uint32_t shadow_rays_per_hit; // shadow rays one computeLightContribution call traces
     uint32_t samples_per_hit;     // shading evaluations per call (point: 1, segment: N, parallelogram: N*N)
     uint32_t part_index, part_count;
+    // this launch renders entries [tile_first, tile_first + tile_count) of the partition's tile list (entry k = tile
+    // part_index + k * part_count); the whole list unless the frame is rendered in bands (cge_api.cu cge_render)
+    uint32_t tile_first, tile_count;
     uint32_t n_tiles_x, n_tiles_y;
     // cooperative kernel only
     uint32_t levels;          // ray_depth + 1 when recursive, else 1

@@ -218,16 +218,14 @@ struct PixelTracer {
 
 __device__ __forceinline__ bool next_tile(const DevParams& p, unsigned* tileCounter, unsigned lane, int& x, int& y)
 {
-    const unsigned nTiles = p.n_tiles_x * p.n_tiles_y;
-    const unsigned myTiles = (nTiles > p.part_index) ? (nTiles - p.part_index + p.part_count - 1) / p.part_count : 0;
     unsigned k = 0;
     if (lane == 0)
         k = atomicAdd(tileCounter, 1u);
     k = __shfl_sync(0xffffffffu, k, 0);
-    if (k >= myTiles)
+    if (k >= p.tile_count)
         return false;
-    // multi-GPU: the tile list is interleaved across ranks, this launch renders tiles part_index + k * part_count
-    const unsigned tile = p.part_index + k * p.part_count;
+    // multi-GPU: the tile list is interleaved across ranks, entry k of this rank's list is tile part_index + k * part_count
+    const unsigned tile = p.part_index + (p.tile_first + k) * p.part_count;
     x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
     y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
     return true;

@@ -357,3 +357,24 @@ def test_zero_shading_cull_off_for_unbounded_colours(cge):
         _, _, st_hot = sc.render(cfg, traversal=1)
         _, _, st_ref = sc.render(cfg, traversal=0)
     assert st_hot["shadow_rays"] == st_ref["shadow_rays"] > st_on["shadow_rays"]
+
+
+@pytest.mark.parametrize("name", ["c3_teapot_soft", "c4_monkey_mirror"])
+def test_concurrent_bands_change_no_bit(cge, name, monkeypatch):
+    """cge_render renders large frames as concurrent bands of tile rows, each a pipeline on its own stream (cge_api.cu
+    launch_bands): the frame, the ids, the packed bitmap and the ray counters must not depend on the number of bands."""
+    cfg = cge.configs.get(name)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        monkeypatch.setenv("CGE_BANDS", "1")
+        rgb1, ids1, st1 = sc.render(cfg, traversal=1)
+        rgba1, _ = sc.render_rgba8(cfg)
+        for bands in ("3", "8", None):
+            if bands is None:
+                monkeypatch.delenv("CGE_BANDS")
+            else:
+                monkeypatch.setenv("CGE_BANDS", bands)
+            rgb, ids, st = sc.render(cfg, traversal=1)
+            rgba, _ = sc.render_rgba8(cfg)
+            assert rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1) and rgba.tobytes() == rgba1.tobytes()
+            for k in ("primary_rays", "bounce_rays", "shadow_rays", "reference_rays", "reference_shadow_rays"):
+                assert st[k] == st1[k], k

@@ -16,10 +16,17 @@ if rank == 0:
 dist.broadcast(idt, 0)
 comm = pkg.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, local)
 ok = True
-for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_soft:0.5", "c5_dragon:0.25"]):
+# "+bloom" / "+aa" after a config name switch the implemented ExtraFeatures on (bloom runs on rank 0 after the gather)
+for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_soft:0.5", "c5_dragon:0.25", "c1_cornell+bloom+aa:0.5"]):
     name, scale = (spec.split(":") + ["1.0"])[:2]
+    name, *extras = name.split("+")
     full = pkg.configs.get(name)
     cfg = pkg.configs.get(name, int(full["width"] * float(scale)), int(full["height"] * float(scale)))
+    if "bloom" in extras:
+        cfg["features"] |= pkg.configs.FEAT_BLOOM_EFFECT
+    if "aa" in extras:
+        cfg["features"] |= pkg.configs.FEAT_MULTIPLE_RAYS_PER_PIXEL
+        cfg["rays_per_pixel_side"] = 2
     with pkg.Scene(pkg.load_scene(cfg), device=local) as sc:
         rgb, ids, st = comm.render(sc, cfg, want_ids=True)
         dist.barrier()
@@ -27,7 +34,7 @@ for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_s
             rgb1, ids1, st1 = sc.render(cfg, want_ids=True)
             same = rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1)
             ok &= same
-            print(json.dumps({"cfg": name, "w": cfg["width"], "h": cfg["height"], "ranks": world, "bit_identical_to_1gpu": bool(same),
+            print(json.dumps({"cfg": spec, "w": cfg["width"], "h": cfg["height"], "ranks": world, "bit_identical_to_1gpu": bool(same),
                               "dist_total_ms": round(st["total_ms"], 3), "dist_kernel_ms_rank0": round(st["kernel_ms"], 3),
                               "single_kernel_ms": round(st1["kernel_ms"], 3), "launches_rank0": st["kernel_launches"]}), flush=True)
         dist.barrier()
