@@ -105,6 +105,7 @@ struct cge_scene {
     int sm_count = 0;
     DevScene dev {};
     DevBuf<float4> nodes, tris, fnodes, ftris, shade, materials;
+    DevBuf<uint4> qnodes;
     FastBvh fast;
     bool fast_built_on_gpu = false;
     float fast_build_ms = 0.0f; // device time of the GPU SAH build
@@ -297,6 +298,49 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     d.tile_first = 0;
     d.tile_count = nTiles > d.part_index ? (nTiles - d.part_index + d.part_count - 1) / d.part_count : 0;
     return d;
+}
+
+// Boxes of the fast tree on the 15-bit grid of dev_scene.h: plane = lo + m * ext with m = 1 + q / 32768.  The grid spans the
+// scene bounds padded by 1/256 of their extent; lower planes are rounded down and upper planes up, then moved one more step
+// outwards (the margin that absorbs the device-side rounding, trace.cuh).  Evaluated in double against the float lo / ext the
+// device will use.
+[[maybe_unused]] void quantise_fast_nodes(const FastBvh& fb, std::vector<uint4>& out, float lo[3], float ext[3])
+{
+    double smin[3] = { 1e300, 1e300, 1e300 }, smax[3] = { -1e300, -1e300, -1e300 };
+    for (const FastNode& n : fb.nodes)
+        for (int k = 0; k < 3; k++)
+            for (float v : { n.l_lo[k], n.r_lo[k], n.l_hi[k], n.r_hi[k] })
+                if (std::isfinite(v)) { // a box around non-finite vertices gets the whole grid below
+                    smin[k] = std::min(smin[k], double(v));
+                    smax[k] = std::max(smax[k], double(v));
+                }
+    for (int k = 0; k < 3; k++)
+        if (smin[k] > smax[k])
+            smin[k] = smax[k] = 0.0;
+    for (int k = 0; k < 3; k++) {
+        const double e = std::max(smax[k] - smin[k], 1e-6 * (std::fabs(smin[k]) + std::fabs(smax[k]) + 1.0));
+        ext[k] = float(e * (1.0 + 2.0 / 256.0));
+        lo[k] = float(smin[k] - e / 256.0 - double(ext[k])); // grid point m = 1 sits e / 256 below the scene minimum
+    }
+    auto grid = [&](int k, double v, bool upper) {
+        if (!std::isfinite(v))
+            return uint32_t(0x8000u | (upper ? 32767u : 0u));
+        const double x = ((v - double(lo[k])) / double(ext[k]) - 1.0) * 32768.0;
+        long q = upper ? long(std::ceil(x)) + 1 : long(std::floor(x)) - 1;
+        q = std::min(std::max(q, 0l), 32767l);
+        return uint32_t(0x8000u | uint32_t(q));
+    };
+    out.resize(fb.nodes.size() * 2);
+    for (size_t i = 0; i < fb.nodes.size(); i++) {
+        const FastNode& n = fb.nodes[i];
+        uint32_t l[3], r[3];
+        for (int k = 0; k < 3; k++) {
+            l[k] = grid(k, n.l_lo[k], false) | (grid(k, n.l_hi[k], true) << 16);
+            r[k] = grid(k, n.r_lo[k], false) | (grid(k, n.r_hi[k], true) << 16);
+        }
+        out[2 * i] = make_uint4(l[0], l[1], l[2], n.left);
+        out[2 * i + 1] = make_uint4(r[0], r[1], r[2], n.right);
+    }
 }
 
 // Magnitude below which a product of a material colour and a light colour cannot overflow: the zero-shading cull
@@ -1040,6 +1084,14 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
         }
     }
 
+    // ---- the fast tree once more with quantised boxes (dev_scene.h qnodes), for the shadow rays ----------------------------
+    std::vector<uint4> qnodes;
+    float qlo[3] = { 0, 0, 0 }, qext[3] = { 1, 1, 1 };
+#if CGE_QNODES
+    if (!sc->fast.nodes.empty())
+        quantise_fast_nodes(sc->fast, qnodes, qlo, qext);
+#endif
+
     // ---- inner nodes: each carries both child boxes ----------------------------------------------------------
     std::vector<float4> nodes;
     if (haveBvh) {
@@ -1114,6 +1166,7 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     up(sc->nodes, nodes);
     up(sc->tris, tris);
     up(sc->fnodes, fnodes);
+    up(sc->qnodes, qnodes);
     up(sc->ftris, ftris);
     up(sc->shade, shade);
     up(sc->materials, mats);
@@ -1128,6 +1181,11 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     sc->dev.nodes = sc->nodes.p;
     sc->dev.tris = sc->tris.p;
     sc->dev.fnodes = sc->fnodes.p;
+    sc->dev.qnodes = sc->qnodes.p;
+    for (int k = 0; k < 3; k++) {
+        sc->dev.qlo[k] = qlo[k];
+        sc->dev.qext[k] = qext[k];
+    }
     sc->dev.ftris = sc->ftris.p;
     sc->dev.froot = sc->fast.root;
     sc->dev.shade = sc->shade.p;
@@ -1208,6 +1266,7 @@ int cge_scene_destroy(cge_scene* sc)
     sc->nodes.release();
     sc->tris.release();
     sc->fnodes.release();
+    sc->qnodes.release();
     sc->ftris.release();
     sc->shade.release();
     sc->materials.release();
@@ -1401,16 +1460,29 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
             rows.push_back(unsigned(uint64_t(dp.n_tiles_y) * b / nBands));
         for (unsigned b = 0; b < nBands; b++)
             ranges.push_back(make_uint2(rows[b] * dp.n_tiles_x, (rows[b + 1] - rows[b]) * dp.n_tiles_x));
-        rc = launch_bands(sc, bands, ranges, !devOut, cam, p, dp, rgbDev, idsDev, &launches, [&](unsigned b, Scratch* sb) {
-            // tile rows [r0, r1) = reference rows y in [4 r0, min(4 r1, H)) = frame rows [H - yEnd, H - yBeg) (Screen's y flip)
+        // frame rows of band b: tile rows [r0, r1) = reference rows y in [4 r0, min(4 r1, H)) = rows [H - yEnd, H - yBeg) (y flip)
+        auto span = [&](unsigned b, size_t& first, size_t& count) {
             const int yBeg = int(rows[b]) * kTileH, yEnd = std::min(int(rows[b + 1]) * kTileH, p->height);
-            const size_t first = size_t(p->height - yEnd) * size_t(p->width), count = size_t(yEnd - yBeg) * size_t(p->width);
+            first = size_t(p->height - yEnd) * size_t(p->width);
+            count = size_t(yEnd - yBeg) * size_t(p->width);
+        };
+        rc = launch_bands(sc, bands, ranges, !devOut, cam, p, dp, rgbDev, idsDev, &launches, [&](unsigned b, Scratch* sb) {
             if (rgba8) {
+                size_t first, count;
+                span(b, first, count);
                 pack_rgba8_kernel<<<unsigned((count + 255) / 256), 256, 0, sb->stream>>>(s->rgb + first * 3,
                     reinterpret_cast<uchar4*>(s->ids) + first, count);
                 launches++;
             }
             cudaEventRecord(sb->bandDone, sb->stream);
+        });
+        cudaEventRecord(s->ev1, s->stream); // every band's kernels (launch_bands made this stream wait for them)
+        // The copies are queued only now that every band's kernels are: into pageable host memory cudaMemcpyAsync blocks the
+        // calling thread until the copy is done, which would otherwise hold back the launch of the next band.
+        for (unsigned b = 0; b < nBands && rc == CGE_OK; b++) {
+            Scratch* sb = bands[b];
+            size_t first, count;
+            span(b, first, count);
             if (rgba8) {
                 cudaMemcpyAsync(reinterpret_cast<uchar4*>(rgbOut) + first, reinterpret_cast<uchar4*>(s->ids) + first, count * 4,
                     cudaMemcpyDeviceToHost, sb->stream);
@@ -1420,8 +1492,7 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
                     cudaMemcpyAsync(idsOut + first, s->ids + first, count * sizeof(int), cudaMemcpyDeviceToHost, sb->stream);
             }
             cudaEventRecord(sb->copyDone, sb->stream);
-        });
-        cudaEventRecord(s->ev1, s->stream);
+        }
         for (unsigned b = 1; b < bands.size(); b++)
             cudaStreamWaitEvent(s->stream, bands[b]->copyDone, 0);
     } else {

@@ -15,6 +15,13 @@
 //             reference-order tree: q3 = { left ref, right ref, left count, right count }; count == 0 -> ref is an
 //             inner-node index, count > 0 -> leaf holding primitives [ref, ref+count) of `tris`.
 //             fast tree: q3 = { left, right, 0, 0 } packed as in bvh_sah.h (bit 31 leaf, bits 28..30 count-1).
+//   qnodes    2 x uint4 per inner node of the fast tree (32 B = one sector): { Lx, Ly, Lz, left } { Rx, Ry, Rz, right }, each
+//             box word = lower | upper << 16 of one axis.  A 16-bit value is 0x8000 | q with q on a 15-bit grid over the
+//             (padded) scene bounds, so that ONE byte permute with the constant 0x3F000000 turns it into the float
+//             m = 1 + q / 32768 and the plane is qlo + m * qext; the slab test folds that affine map into the per-ray FFMA
+//             constants (trace.cuh).  Boxes are rounded outwards by at least one grid step, which also covers the rounding
+//             of that arithmetic.  Shadow rays only need a conservative gate and are bound by L1 traffic (4 x LDG.128 per
+//             visit with up to 32 different nodes per warp): half the bytes per visit.
 //   tris / ftris     6 x float4 per primitive (96 B), in the LEAF ORDER of the respective tree:
 //               r0 = n.xyz, D                 plane of trianglePlane (libIntersect I1), bit-identical: same ops, no FMA
 //               r1 = v0.xyz, e0.x             e0 = cross(v2 - v0, n)   first edge test of pointInTriangle (I3)
@@ -50,6 +57,7 @@ struct DevScene {
     const float4* nodes;
     const float4* tris;
     const float4* fnodes;
+    const uint4* qnodes; // the FAST tree again, 32 B per inner node, boxes on a 15-bit grid (below): walked by shadow rays
     const float4* ftris;
     const float4* shade;
     const float4* materials;
@@ -61,6 +69,7 @@ struct DevScene {
     uint32_t root_ref, root_count; // reference-order tree root, same encoding as a child slot
     uint32_t froot;                // fast tree root (packed)
     uint32_t has_spheres;
+    float qlo[3], qext[3]; // quantisation grid of qnodes: coordinate = qlo + m * qext, m in [1, 2)
     uint32_t cull_zero_shading; // FAST traversal: skip the shadow ray of a light sample with n.l <= 0 (shade.cuh shading_is_zero)
 };
 

@@ -216,6 +216,97 @@ __device__ __forceinline__ float min3(float a, float b, float c)
     return r;
 }
 
+// ---- slab test with one FFMA per plane ------------------------------------------------------------------------------
+// t(b) = (b - o) / d is evaluated as fma(b, inv, c) with inv = 1/d and c = -(o * inv) precomputed per ray: 6 FFMA per box instead
+// of 6 FADD + 6 FMUL, and because the sign of inv tells which plane of a slab is the near one, the 6 min/max that sort
+// t(lo), t(hi) become 6 selects.  The price is cancellation: fma(b, inv, c) differs from the exact quotient by up to
+// 2^-23 |t| + 2^-24 |o * inv|, and the second term is not small when the ray is almost parallel to a slab (|inv| huge).
+// It is absorbed PER AXIS into the constants - near planes use c - s, far planes c + s with s = 2^-22 |o * inv| - so that an
+// axis with a huge |inv| widens only its own interval (by a few ulps of the plane coordinate, where it cannot matter) and
+// the others keep their precision.  A global slack (tried first) let such rays into almost every nearby
+// box.  As before the result only has to be conservative: it gates which leaves are reached, never a hit decision.
+// d == 0 (or so small that 1/d overflows) uses inv = 1e18: t(b) is then +-huge outside the slab and ~0 inside it.
+struct SlabRay {
+    vec3 inv, cNear, cFar;
+    bool nx, ny, nz; // inv < 0: the upper plane is the near one
+};
+__device__ __forceinline__ SlabRay slab_ray(const vec3 o, const vec3 d)
+{
+    SlabRay r;
+    auto recip = [](float v) { return fabsf(v) > 1e-18f ? fdiv(1.0f, v) : 1e18f; };
+    r.inv = v3(recip(d.x), recip(d.y), recip(d.z));
+    const vec3 c = v3(-fmul(o.x, r.inv.x), -fmul(o.y, r.inv.y), -fmul(o.z, r.inv.z));
+    const vec3 s = v3(fabsf(c.x) * 2.384185791015625e-07f, fabsf(c.y) * 2.384185791015625e-07f, fabsf(c.z) * 2.384185791015625e-07f);
+    r.cNear = v3(c.x - s.x, c.y - s.y, c.z - s.z);
+    r.cFar = v3(c.x + s.x, c.y + s.y, c.z + s.z);
+    r.nx = r.inv.x < 0.0f, r.ny = r.inv.y < 0.0f, r.nz = r.inv.z < 0.0f;
+    return r;
+}
+// entry / exit distance of the ray through the box [lo, hi]; the box is hit within [0, bound] iff
+// ent <= ext * 1.000002f && ent <= bound (the multiplicative slack covers the relative part of the error)
+__device__ __forceinline__ void slab_box(const SlabRay& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float& ent,
+    float& ext)
+{
+    const float tnx = __fmaf_rn(r.nx ? hix : lox, r.inv.x, r.cNear.x), tfx = __fmaf_rn(r.nx ? lox : hix, r.inv.x, r.cFar.x);
+    const float tny = __fmaf_rn(r.ny ? hiy : loy, r.inv.y, r.cNear.y), tfy = __fmaf_rn(r.ny ? loy : hiy, r.inv.y, r.cFar.y);
+    const float tnz = __fmaf_rn(r.nz ? hiz : loz, r.inv.z, r.cNear.z), tfz = __fmaf_rn(r.nz ? loz : hiz, r.inv.z, r.cFar.z);
+    ent = fmaxf(max3(tnx, tny, tnz), 0.0f);
+    ext = min3(tfx, tfy, tfz);
+}
+
+#ifndef CGE_PREFETCH
+#define CGE_PREFETCH 0 // 1: prefetch the far child when pushed, 2: both children on arrival - both measured slower
+#endif
+// pull the record a child reference points at (inner node: 64 B; leaf: its first triangle's plane row) towards L1
+__device__ __forceinline__ void prefetch_child(const DevScene& s, unsigned ref)
+{
+    const void* p = ref < 0x7fffffffu ? static_cast<const void*>(s.fnodes + size_t(ref) * kNodeRows)
+                                      : static_cast<const void*>(s.ftris + size_t(ref & 0x0fffffffu) * kTriRows);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// ---- quantised nodes (dev_scene.h qnodes) ---------------------------------------------------------------------------------
+// plane = qlo + m * qext  =>  t(plane) = (plane - o) * inv = fma(m, qext * inv, (qlo - o) * inv): the dequantisation costs nothing
+// beyond the byte permute that builds m.  The constants carry no slack: every box was rounded outwards by >= 1 grid step
+// (qext / 32768), two orders of magnitude more than the rounding of this expression (<= ~4e-7 qext |inv| for an origin inside
+// the scene bounds, where every shadow ray starts).
+#ifndef CGE_QNODES
+#define CGE_QNODES 0 // 1: shadow rays walk the 32-byte quantised nodes.  Measured on B200: the 15-bit grid inflates the
+                     // leaf-level boxes of the 868K-triangle scene enough to cost more visits than the halved traffic saves
+                     // (C5 shadow pass 13.8 -> 14.5 ms; C3 0.84 -> 0.81 ms): off by default, the float nodes are walked.
+#endif
+struct SlabRayQ {
+    vec3 a, c;                 // t = fma(m, a, c) per axis
+    unsigned nearSel[3], farSel[3]; // byte-permute selectors: which half of an axis word is the near / far plane
+};
+__device__ __forceinline__ SlabRayQ slab_ray_q(const DevScene& s, const vec3 o, const vec3 d)
+{
+    SlabRayQ r;
+    auto recip = [](float v) { return fabsf(v) > 1e-18f ? fdiv(1.0f, v) : 1e18f; };
+    const vec3 inv = v3(recip(d.x), recip(d.y), recip(d.z));
+    r.a = v3(fmul(s.qext[0], inv.x), fmul(s.qext[1], inv.y), fmul(s.qext[2], inv.z));
+    r.c = v3(fmul(fsub(s.qlo[0], o.x), inv.x), fmul(fsub(s.qlo[1], o.y), inv.y), fmul(fsub(s.qlo[2], o.z), inv.z));
+    // result bytes (3..0) = { 0x3F, half.hi, half.lo, 0x00 } from { K = 0x3F000000 : word }: lower half 0x7104, upper half 0x7324
+    const float iv[3] = { inv.x, inv.y, inv.z };
+    for (int k = 0; k < 3; k++) {
+        r.nearSel[k] = iv[k] < 0.0f ? 0x7324u : 0x7104u;
+        r.farSel[k] = iv[k] < 0.0f ? 0x7104u : 0x7324u;
+    }
+    return r;
+}
+__device__ __forceinline__ void slab_box_q(const SlabRayQ& r, unsigned wx, unsigned wy, unsigned wz, float& ent, float& ext)
+{
+    constexpr unsigned K = 0x3F000000u;
+    const float tnx = __fmaf_rn(__uint_as_float(__byte_perm(wx, K, r.nearSel[0])), r.a.x, r.c.x);
+    const float tfx = __fmaf_rn(__uint_as_float(__byte_perm(wx, K, r.farSel[0])), r.a.x, r.c.x);
+    const float tny = __fmaf_rn(__uint_as_float(__byte_perm(wy, K, r.nearSel[1])), r.a.y, r.c.y);
+    const float tfy = __fmaf_rn(__uint_as_float(__byte_perm(wy, K, r.farSel[1])), r.a.y, r.c.y);
+    const float tnz = __fmaf_rn(__uint_as_float(__byte_perm(wz, K, r.nearSel[2])), r.a.z, r.c.z);
+    const float tfz = __fmaf_rn(__uint_as_float(__byte_perm(wz, K, r.farSel[2])), r.a.z, r.c.z);
+    ent = fmaxf(max3(tnx, tny, tnz), 0.0f);
+    ext = min3(tfx, tfy, tfz);
+}
+
 // Shadow rays (src/light.cpp:60-72: closest hit with ray.t = 1 used as a boolean): is ANY triangle accepted with 0 <= t <= 1?
 // Lean specialisation of trace_fast<true>: the bound is the constant 1, so the stack needs no entry distances and no
 // re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris) or -1.
@@ -223,32 +314,46 @@ __device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, con
 {
     if (s.n_prims == 0)
         return -1;
-    const vec3 inv = v3(d.x != 0.0f ? fdiv(1.0f, d.x) : 3.0e38f, d.y != 0.0f ? fdiv(1.0f, d.y) : 3.0e38f,
-        d.z != 0.0f ? fdiv(1.0f, d.z) : 3.0e38f);
+#if CGE_QNODES
+    const SlabRayQ sr = slab_ray_q(s, o, d);
+#else
+    const SlabRay sr = slab_ray(o, d);
+#endif
     unsigned stack[kFastStackSize];
     int sp = 0;
     constexpr unsigned kDone = 0x7fffffffu;
     unsigned cur = s.froot;
     while (cur != kDone) {
         while (cur < kDone) {
+            float entL, extL, entR, extR;
+#if CGE_QNODES
+            const uint4* nd = s.qnodes + size_t(cur) * 2;
+            const uint4 q0 = __ldg(nd), q1 = __ldg(nd + 1);
+            slab_box_q(sr, q0.x, q0.y, q0.z, entL, extL);
+            slab_box_q(sr, q1.x, q1.y, q1.z, entR, extR);
+            const unsigned cl = q0.w, cr = q1.w;
+#else
             const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
-            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-            const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
-            const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
-            const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
-            const float entL = fmaxf(max3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), 0.0f);
-            const float extL = min3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1));
-            const bool hitL = entL <= extL * 1.000002f && entL <= 1.0001f;
-            const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
-            const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
-            const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
-            const float entR = fmaxf(max3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), 0.0f);
-            const float extR = min3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1));
-            const bool hitR = entR <= extR * 1.000002f && entR <= 1.0001f;
+            const float4 q3 = ldg4(nd + 3);
+            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2);
+#if CGE_PREFETCH == 2
+            prefetch_child(s, __float_as_uint(q3.x));
+            prefetch_child(s, __float_as_uint(q3.y));
+#endif
+            slab_box(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
+            slab_box(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
             const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+#endif
+            const bool hitL = entL <= extL * 1.000002f && entL <= 1.0001f;
+            const bool hitR = entR <= extR * 1.000002f && entR <= 1.0001f;
             const bool leftFirst = hitL && (!hitR || entL <= entR);
-            if (hitL && hitR)
-                stack[sp++] = leftFirst ? cr : cl;
+            if (hitL && hitR) {
+                const unsigned far = leftFirst ? cr : cl;
+                stack[sp++] = far;
+#if CGE_PREFETCH == 1
+                prefetch_child(s, far);
+#endif
+            }
             if (hitL || hitR)
                 cur = leftFirst ? cl : cr;
             else

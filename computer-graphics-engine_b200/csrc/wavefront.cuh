@@ -61,7 +61,10 @@ __device__ __forceinline__ size_t wf_dir_off(const DevParams& p, unsigned cap, u
     return size_t(unitsBefore) * 3u * cap;
 }
 
-__global__ void __launch_bounds__(128, 6) wf_chain_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb, float* __restrict__ rgb,
+#ifndef CGE_MINB_CHAIN
+#define CGE_MINB_CHAIN 6
+#endif
+__global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_chain_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb, float* __restrict__ rgb,
     int* __restrict__ ids, Counters* __restrict__ gcnt)
 {
     const unsigned lane = threadIdx.x & 31;
@@ -414,8 +417,11 @@ __global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevPa
 // 16-rays-per-lane granularity: on a 1/8 tile partition of C5 the coupled shade kernel left the SMs idle a third of its run
 // time (profiles/, smsp__cycles_active 5.3 M of 8.0 M).  Results go to the visibility bytes; wf_shade_kernel<true> shades.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef CGE_MINB_VIS
+#define CGE_MINB_VIS 12 // resident 128-thread CTAs per SM the shadow-ray kernel is compiled for (A/B in DESIGN.md 5.5)
+#endif
 template <unsigned kGroup>
-__global__ void __launch_bounds__(128, 8) wf_vis_grouped_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
+__global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_grouped_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
 {
     const unsigned lane = threadIdx.x & 31;
     const bool fold = p.draws_per_hit == 0;
