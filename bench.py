@@ -426,7 +426,7 @@ def main():
                                     "achieved_gbs": (ref_rays / world * bytes_per_ray + 12.0 * W * H / world) / (pipeline_ms * 1e-3) / 1e9},
                     "note": "algorithmic bytes are those of the reference's EXHAUSTIVE traversal (SURVEY.md 8d); the fast tree "
                             "performs ~3x fewer box and ~40x fewer triangle tests and the working set is largely L2-resident, "
-                            "so this fraction is not a DRAM utilisation (ncu: DRAM ~7% of peak) - the operative bound is "
+                            "so this fraction is not a DRAM utilisation (ncu: DRAM ~4% of peak) - the operative bound is "
                             "issue/latency inside the SM, DESIGN.md 5.6"}
 
     line = {

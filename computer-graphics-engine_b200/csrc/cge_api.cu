@@ -768,7 +768,7 @@ unsigned nBandsFor(const cge_scene* sc, const cge_params& p, const DevParams& dp
     unsigned n = 1;
     const bool wave = choose_variant(scene_for(sc, p), p, dp).wave;
     if (wave)
-        n = pixels >= (size_t(3) << 20) ? 4 : pixels >= (size_t(3) << 18) ? 2 : 1;
+        n = pixels >= (size_t(3) << 20) ? 4 : pixels >= (size_t(3) << 19) ? 2 : 1; // a 1 Mpixel share (C5 on 8 GPUs) is faster in one piece
     else if (hostCopy)
         n = pixels >= (size_t(2) << 20) ? 4 : 1;
     n = unsigned(std::max(env_int("CGE_BANDS", int(n)), 1));
