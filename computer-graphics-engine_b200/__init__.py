@@ -25,6 +25,7 @@ FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1,
 FLAG_DEBUG_CYCLES, FLAG_PER_THREAD, FLAG_DECOUPLED_SHADE = 16, 32, 64
 FLAG_COUPLED_SHADE, FLAG_GROUPED_SHADE, FLAG_AUTO_SHADE, FLAG_WAVEFRONT = 128, 256, 512, 1024
 FLAG_OUTPUT_RGBA8 = 2048
+FLAG_CHAIN_PER_LEVEL = 4096
 UNIQUE_ID_BYTES = 128
 
 

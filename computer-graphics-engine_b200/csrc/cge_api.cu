@@ -83,7 +83,7 @@ struct Scratch {
     size_t gatherPixels = 0;
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
-    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0;
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveBounce = 0;
     float* bloomTmp = nullptr; // thresholded copy of the frame (renderBloomFilter's screenThreshold)
     size_t bloomPixels = 0;
     cudaStream_t stream = nullptr;
@@ -496,7 +496,7 @@ constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than thi
 
 struct WaveSizes {
     size_t recFloats, meta, next, dirFloats, vis;
-    size_t bytes() const { return recFloats * 4 + meta * 8 + next * 4 + dirFloats * 4 + vis; }
+    size_t bytes() const { return recFloats * 4 + meta * 8 * 2 + next * 4 + dirFloats * 4 + vis; } // meta + bounce queue
 };
 WaveSizes wave_sizes(const DevParams& dp, size_t cap)
 {
@@ -656,17 +656,40 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         if (err == cudaSuccess && wp.shade_mode != 1)
             err = grow(s->wave.vis, s->waveVis, ws.vis, 1);
         if (err == cudaSuccess && !s->wave.counts)
-            err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 32 * sizeof(unsigned));
+            err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 64 * sizeof(unsigned));
         if (err == cudaSuccess)
-            err = cudaMemsetAsync(s->wave.counts, 0, 32 * sizeof(unsigned), s->stream);
+            err = cudaMemsetAsync(s->wave.counts, 0, 64 * sizeof(unsigned), s->stream);
         s->wave.cap = unsigned(cap);
         int perSm = 0;
         if (err == cudaSuccess)
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
-        if (err == cudaSuccess) {
+            err = (p->flags & CGE_FLAG_CHAIN_PER_LEVEL) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_primary_kernel, 128, 0)
+                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
+        if (err == cudaSuccess && !(p->flags & CGE_FLAG_CHAIN_PER_LEVEL)) {
             cudaEventRecord(stage[0], s->stream);
             wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
             err = cudaGetLastError();
+            cudaEventRecord(stage[1], s->stream);
+        } else if (err == cudaSuccess) {
+            // opt-in: one launch per recursion level (wavefront.cuh); a level whose queue is empty returns at once
+            err = grow(s->wave.bounce, s->waveBounce, ws.meta, sizeof(uint2));
+            cudaEventRecord(stage[0], s->stream);
+            if (err == cudaSuccess) {
+                wf_primary_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
+                err = cudaGetLastError();
+            }
+            int perSmB = 0;
+            if (err == cudaSuccess)
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmB, wf_bounce_kernel, 128, 0);
+            for (unsigned level = 1; level < wp.levels && err == cudaSuccess; level++) {
+                wf_bounce_kernel<<<grid_for(perSmB), 128, 0, s->stream>>>(ds, wp, s->wave, level, s->counters);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
+            if (err == cudaSuccess && wp.levels > 1) {
+                wf_chain_finalize_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(s->wave);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
             cudaEventRecord(stage[1], s->stream);
         }
         if (err == cudaSuccess && decoupled) {
@@ -1241,6 +1264,7 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.next);
         cudaFree(s->wave.dir);
         cudaFree(s->wave.vis);
+        cudaFree(s->wave.bounce);
         cudaFree(s->bloomTmp);
         cudaFree(s->wave.counts);
         if (s->ev0)

@@ -36,7 +36,9 @@ struct WaveBuffers {
     unsigned* next;
     float* dir;
     unsigned char* vis; // one byte per (level, copy, sample, slot): 1 = light sample visible
-    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] ray counter
+    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] ray counter,
+                        // [32..47] bounce-queue length per level, [48..63] bounce-queue chunk counter per level
+    uint2* bounce;      // [level][cap]: (level-0 slot of the pixel, slot of its hit at level - 1): the rays wf_bounce_kernel traces
     unsigned cap;
 };
 
@@ -142,6 +144,169 @@ __global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_chain_kernel(DevScene 
         }
     }
     flush_counters(cnt, gcnt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The chain stage as one launch per recursion level - opt-in (CGE_FLAG_CHAIN_PER_LEVEL), measured slower than wf_chain_kernel.
+// The idea: in wf_chain_kernel a lane owns a pixel's whole mirror chain, so the unit of work is up to `levels` closest-hit
+// rays in sequence, only the lanes whose hit reflects stay busy at the deeper levels, and the kernel's tail is the slowest
+// tile whatever the size of the launch (0.59 ms of a 3.1 ms frame on a 1/8 share of C5).  Here a lane traces ONE ray:
+// wf_primary_kernel the camera rays (tiles from the atomic counter), wf_bounce_kernel the reflected rays of level k, 32 per
+// warp from the bounce queue level k - 1 appended to (ballot + one atomic per warp).  A reflected ray is recomputed from the
+// stored hit record, so a queue entry is two indices.  The chain length of a pixel is only known where its chain ends: that
+// lane writes the tag into the pixel's level-0 meta entry and wf_chain_finalize_kernel copies it to the deeper levels'
+// entries, which restores exactly the arrays wf_chain_kernel produces (same records, same links; slot ORDER differs, which
+// nothing depends on).  Measured on B200, C5 (profiles/): primary 0.70 + bounce levels 0.74 + 0.39 + 0.25 ms =
+// 2.1 ms against 1.33 ms for wf_chain_kernel (one rank's 1/8 share: 0.91 vs 0.49 ms): every level pays its own tail, and
+// the incoherent reflected rays no longer overlap with other tiles' cheap camera rays.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ChainHitOut {
+    unsigned slot;
+    bool reflects;
+};
+
+// Append the hits of a warp to the level's queue and write their records; lanes without a hit pass hit = false.
+__device__ __forceinline__ ChainHitOut wf_store_hit(const DevScene& s, const DevParams& p, const WaveBuffers& wb, unsigned level, bool hit,
+    const Hit& h, Ray ray, unsigned pixel, unsigned lane)
+{
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    unsigned base = 0;
+    if (lane == 0 && ballot)
+        base = atomicAdd(wb.counts + level, unsigned(__popc(ballot)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    ChainHitOut out { 0u, false };
+    if (!hit)
+        return out;
+    out.slot = base + unsigned(__popc(ballot & below));
+    ray.t = h.t;
+    HitRec r;
+    resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
+    float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + out.slot;
+    const size_t c = wb.cap;
+    b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
+    b[3 * c] = r.ray.d.x, b[4 * c] = r.ray.d.y, b[5 * c] = r.ray.d.z;
+    b[6 * c] = r.ray.t;
+    b[7 * c] = r.normal.x, b[8 * c] = r.normal.y, b[9 * c] = r.normal.z;
+    b[10 * c] = r.m.kd.x, b[11 * c] = r.m.kd.y, b[12 * c] = r.m.kd.z;
+    b[13 * c] = r.m.ks.x, b[14 * c] = r.m.ks.y, b[15 * c] = r.m.ks.z;
+    b[16 * c] = r.m.shininess;
+    const vec3 so = shadow_origin(r);
+    b[17 * c] = so.x, b[18 * c] = so.y, b[19 * c] = so.z;
+    wb.meta[size_t(level) * wb.cap + out.slot] = make_uint2(pixel, 0u); // .y: wf_chain_finalize_kernel (level 0: the chain's end)
+    const bool recursive = p.features & CGE_FEAT_RECURSIVE;
+    out.reflects = recursive && int(level) < p.ray_depth && !(r.m.ks.x == 0.0f && r.m.ks.y == 0.0f && r.m.ks.z == 0.0f);
+    return out;
+}
+
+// Lanes whose hit reflects enqueue the next level's ray; lanes whose chain ends here record (n, missEnd) for their pixel.
+__device__ __forceinline__ void wf_continue_or_end(const DevParams& p, const WaveBuffers& wb, unsigned level, bool live, bool hit,
+    const ChainHitOut& ho, unsigned e0, unsigned lane, Counters& cnt)
+{
+    const unsigned below = (1u << lane) - 1u;
+    const bool goesOn = live && hit && ho.reflects;
+    const unsigned ballot = __ballot_sync(0xffffffffu, goesOn);
+    unsigned base = 0;
+    if (lane == 0 && ballot)
+        base = atomicAdd(wb.counts + 32 + level + 1, unsigned(__popc(ballot)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (goesOn) {
+        wb.bounce[size_t(level + 1) * wb.cap + base + unsigned(__popc(ballot & below))] = make_uint2(e0, ho.slot);
+    } else if (live) {
+        const int n = hit ? int(level) + 1 : int(level); // hit levels of this pixel's chain
+        const bool missEnd = !hit;
+        reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
+        if (n > 0)
+            wb.meta[e0].y = unsigned(n) | (missEnd ? 256u : 0u);
+    }
+}
+
+__global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_primary_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb,
+    float* __restrict__ rgb, int* __restrict__ ids, Counters* __restrict__ gcnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    Counters cnt {};
+    int x, y;
+    while (next_tile(p, wb.counts + 16, lane, x, y)) {
+        const bool live = x < p.width && y < p.height;
+        const unsigned pixel = unsigned(y) * unsigned(p.width) + unsigned(x);
+        Ray ray {};
+        Hit h {};
+        bool hit = false;
+        if (live) {
+            ray = generate_ray(cam, x, y, p.width, p.height);
+            h = trace_fast<false>(s, ray.o, ray.d, ray.t);
+            cnt.primary++;
+            hit = h.prim >= 0;
+        }
+        const ChainHitOut ho = wf_store_hit(s, p, wb, 0, hit, h, ray, pixel, lane);
+        if (live && hit && ids)
+            ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = int(h.gid);
+        if (live && !hit)
+            store_pixel(p, rgb, ids, x, y, v3(0.0f), -1); // primary miss: black (reference src/render.cpp:148)
+        wf_continue_or_end(p, wb, 0, live, hit, ho, ho.slot, lane, cnt);
+    }
+    flush_counters(cnt, gcnt);
+}
+
+__global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_bounce_kernel(DevScene s, DevParams p, WaveBuffers wb, unsigned level,
+    Counters* __restrict__ gcnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned total = wb.counts[32 + level];
+    Counters cnt {};
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0)
+            chunk = atomicAdd(wb.counts + 48 + level, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((unsigned long long)chunk * 32ull >= total)
+            break;
+        const unsigned i = chunk * 32u + lane;
+        const bool live = i < total;
+        uint2 item = make_uint2(0u, 0u);
+        unsigned pixel = 0;
+        Ray ray {};
+        Hit h {};
+        bool hit = false;
+        if (live) {
+            item = wb.bounce[size_t(level) * wb.cap + i];
+            // the reflected ray of the hit at level - 1, from its record (computeReflectionRay, src/shading.cpp:40-62)
+            const float* b = wb.rec + (size_t(level - 1) * kWaveRecFloats) * wb.cap + item.y;
+            const size_t c = wb.cap;
+            HitRec prev;
+            prev.ray.o = v3(b[0 * c], b[1 * c], b[2 * c]);
+            prev.ray.d = v3(b[3 * c], b[4 * c], b[5 * c]);
+            prev.ray.t = b[6 * c];
+            prev.normal = v3(b[7 * c], b[8 * c], b[9 * c]);
+            prev.m.ks = v3(b[13 * c], b[14 * c], b[15 * c]);
+            reflection_ray(prev, ray); // ks != 0 was checked when the entry was queued
+            pixel = wb.meta[size_t(level - 1) * wb.cap + item.y].x;
+            h = trace_fast<false>(s, ray.o, ray.d, ray.t);
+            cnt.bounce++;
+            hit = h.prim >= 0;
+        }
+        const ChainHitOut ho = wf_store_hit(s, p, wb, level, hit, h, ray, pixel, lane);
+        if (live && hit)
+            wb.next[size_t(level - 1) * wb.cap + item.y] = ho.slot;
+        wf_continue_or_end(p, wb, level, live, hit, ho, item.x, lane, cnt);
+    }
+    flush_counters(cnt, gcnt);
+}
+
+// the tag (chain length | missEnd << 8) of every pixel, copied from its level-0 entry to the entries of its deeper levels
+__global__ void __launch_bounds__(128) wf_chain_finalize_kernel(WaveBuffers wb)
+{
+    const unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e0 >= wb.counts[0])
+        return;
+    const unsigned tag = wb.meta[e0].y;
+    const int n = int(tag & 255u);
+    unsigned slot = e0;
+    for (int k = 1; k < n; k++) {
+        slot = wb.next[size_t(k - 1) * wb.cap + slot];
+        wb.meta[size_t(k) * wb.cap + slot].y = tag;
+    }
 }
 
 // computeLightContribution for one (pixel, level, copy): same arithmetic and order as PixelTracer::direct.

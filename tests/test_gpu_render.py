@@ -43,7 +43,7 @@ def assert_parity(name, rgb, ids, ref_rgb, ref_ids, id_budget=ID_MISMATCH_BUDGET
 
 
 # (traversal, flags): literal traversal with test counters / fast tree per-thread kernel / fast tree cooperative kernel
-MODES = {"reference": (0, 4), "fast-default": (1, 0), "fast-wave": (1, 1024), "fast-wave-decoupled": (1, 1024 | 64), "fast-wave-grouped": (1, 1024 | 256), "fast-wave-coupled": (1, 1024 | 128), "fast-wave-auto": (1, 1024 | 512), "fast-thread": (1, 32), "fast-coop": (1, 8)}
+MODES = {"reference": (0, 4), "fast-default": (1, 0), "fast-wave": (1, 1024), "fast-wave-decoupled": (1, 1024 | 64), "fast-wave-grouped": (1, 1024 | 256), "fast-wave-coupled": (1, 1024 | 128), "fast-wave-auto": (1, 1024 | 512), "fast-wave-chain-per-level": (1, 1024 | 4096), "fast-thread": (1, 32), "fast-coop": (1, 8)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
@@ -167,7 +167,7 @@ def test_full_size_properties(cge, name):
         assert st_f["reference_rays"] == st_r["reference_rays"]
         # wavefront, per-thread and cooperative kernels walk the same tree with the same arithmetic: identical bits
         W = cge.FLAG_WAVEFRONT
-        for fl in (cge.FLAG_PER_THREAD, cge.FLAG_COOPERATIVE, W, W | cge.FLAG_DECOUPLED_SHADE, W | cge.FLAG_GROUPED_SHADE, W | cge.FLAG_COUPLED_SHADE, W | cge.FLAG_AUTO_SHADE):
+        for fl in (cge.FLAG_PER_THREAD, cge.FLAG_COOPERATIVE, W, W | cge.FLAG_DECOUPLED_SHADE, W | cge.FLAG_GROUPED_SHADE, W | cge.FLAG_COUPLED_SHADE, W | cge.FLAG_AUTO_SHADE, W | cge.FLAG_CHAIN_PER_LEVEL):
             rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=fl)
             assert st_t["reference_rays"] == st_f["reference_rays"] and st_t["gpu_rays"] == st_f["gpu_rays"]
             assert np.array_equal(ids_t, ids_f) and rgb_t.tobytes() == rgb_f.tobytes()
