@@ -115,6 +115,7 @@ inline int raysPerPixelSide = 3;
 inline float bloomScalar = .3f;
 inline float bloomThreshold = .4f;
 inline int bloomDebugOption = 0;
+inline uint32_t samplerSeed = 0; // seed of the hash sampler that stands in for rand() / std::random_device (csrc/sampler.h)
 
 inline void check(int rc, const char* what)
 {
@@ -152,11 +153,59 @@ public:
     [[nodiscard]] int indexAt(int x, int y) const { return (m_resolution.y - 1 - y) * m_resolution.x + x; }
     [[nodiscard]] const std::vector<vec3>& pixels() const { return m_textureData; }
     [[nodiscard]] std::vector<vec3>& pixels() { return m_textureData; }
+    // void writeBitmapToFile(const std::filesystem::path&) (src/screen.cpp:49-60): clamp -> vec4(c, 1) * 255 -> u8vec4 on the
+    // host, then the same file stb's stbi_write_bmp(path, w, h, 4, data) writes (writeBmpRgba below).
+    inline void writeBitmapToFile(const std::string& filePath) const;
 
 private:
     ivec2 m_resolution;
     std::vector<vec3> m_textureData;
 };
+
+// The file stb_image_write produces for comp = 4 (the reference's writer, framework/third_party/stb, stbi_write_bmp_core):
+// 14-byte file header + 108-byte BITMAPV4HEADER (32 bpp, BI_BITFIELDS, masks R 00ff0000 G 0000ff00 B 000000ff A ff000000, all
+// other fields zero), rows bottom-up, pixels as B G R A.  rgba: width * height * 4 bytes, row 0 = top (Screen::pixels() order).
+inline void writeBmpRgba(const std::string& path, int width, int height, const uint8_t* rgba)
+{
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f)
+        throw std::runtime_error("cannot write " + path);
+    auto u16 = [&](uint32_t v) { const uint8_t b[2] = { uint8_t(v), uint8_t(v >> 8) }; std::fwrite(b, 1, 2, f); };
+    auto u32 = [&](uint32_t v) { const uint8_t b[4] = { uint8_t(v), uint8_t(v >> 8), uint8_t(v >> 16), uint8_t(v >> 24) }; std::fwrite(b, 1, 4, f); };
+    std::fputc('B', f), std::fputc('M', f);
+    u32(14u + 108u + uint32_t(width) * uint32_t(height) * 4u), u16(0), u16(0), u32(14 + 108);
+    u32(108), u32(uint32_t(width)), u32(uint32_t(height)), u16(1), u16(32), u32(3);
+    for (int k = 0; k < 5; k++)
+        u32(0); // image size, x / y pixels per metre, colours used, important colours
+    u32(0x00ff0000u), u32(0x0000ff00u), u32(0x000000ffu), u32(0xff000000u);
+    for (int k = 0; k < 13; k++)
+        u32(0); // colour-space type, 9 endpoint words, 3 gamma words
+    std::vector<uint8_t> row(size_t(width) * 4);
+    for (int y = height - 1; y >= 0; y--) {
+        const uint8_t* src = rgba + size_t(y) * size_t(width) * 4;
+        for (int x = 0; x < width; x++) {
+            row[4 * x + 0] = src[4 * x + 2], row[4 * x + 1] = src[4 * x + 1], row[4 * x + 2] = src[4 * x + 0], row[4 * x + 3] = src[4 * x + 3];
+        }
+        std::fwrite(row.data(), 1, row.size(), f);
+    }
+    std::fclose(f);
+}
+
+inline void Screen::writeBitmapToFile(const std::string& filePath) const
+{
+    std::vector<uint8_t> bytes(m_textureData.size() * 4);
+    auto conv = [](float v) -> uint8_t { // glm::clamp = min(max(x, 0), 1) lets NaN through; NaN -> u8 gives 0 on x86
+        if (v != v)
+            return 0;
+        v = std::fmin(std::fmax(v, 0.0f), 1.0f);
+        return uint8_t(v * 255.0f);
+    };
+    for (size_t i = 0; i < m_textureData.size(); i++) {
+        bytes[4 * i] = conv(m_textureData[i].x), bytes[4 * i + 1] = conv(m_textureData[i].y), bytes[4 * i + 2] = conv(m_textureData[i].z);
+        bytes[4 * i + 3] = 255;
+    }
+    writeBmpRgba(filePath, m_resolution.x, m_resolution.y, bytes.data());
+}
 
 class Trackball {
 public:
@@ -327,6 +376,7 @@ inline cge_params makeParams(const ivec2& res, const Features& features, int ray
     p.segment_samples = segmentLightSamples;
     p.parallelogram_samples = parallelogramLightDirectionSamples;
     p.sampler = CGE_SAMPLER_HASH;
+    p.seed = samplerSeed;
     p.traversal = CGE_TRAVERSAL_FAST;
     p.rays_per_pixel_side = raysPerPixelSide;
     p.bloom_scalar = bloomScalar;
@@ -347,6 +397,21 @@ inline void renderRayTracing(const Scene& scene, const Trackball& camera, const 
     const cge_params p = makeParams(screen.resolution(), features, rayDepth);
     static_assert(sizeof(vec3) == 12);
     check(cge_render(bvh.handle(), &cam, &p, reinterpret_cast<float*>(screen.pixels().data()), nullptr, stats), "cge_render");
+}
+
+// renderRayTracing followed by Screen::writeBitmapToFile as the CLI does (src/main.cpp:520-524), with the clamp -> u8x4
+// conversion done on the GPU before the read-back (CGE_FLAG_OUTPUT_RGBA8: 4 instead of 12 bytes per pixel cross PCIe).
+inline void renderRayTracingToBitmap(const Scene& scene, const Trackball& camera, const BvhInterface& bvh, const ivec2& resolution,
+    const Features& features, const std::string& filePath, int rayDepth = 5, cge_stats* stats = nullptr)
+{
+    const std::vector<cge_light_desc> lights = flattenLights(scene);
+    check(cge_scene_update_lights(bvh.handle(), lights.data(), uint32_t(lights.size())), "cge_scene_update_lights");
+    const cge_camera cam = camera.camera();
+    cge_params p = makeParams(resolution, features, rayDepth);
+    p.flags |= CGE_FLAG_OUTPUT_RGBA8;
+    std::vector<uint8_t> rgba(size_t(resolution.x) * size_t(resolution.y) * 4);
+    check(cge_render(bvh.handle(), &cam, &p, reinterpret_cast<float*>(rgba.data()), nullptr, stats), "cge_render");
+    writeBmpRgba(filePath, resolution.x, resolution.y, rgba.data());
 }
 
 // glm::vec3 getFinalColor(const Scene&, const BvhInterface&, Ray, const Features&, int rayDepth = 0)     (src/render.h:35)

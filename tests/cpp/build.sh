@@ -5,3 +5,6 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 REPO=$(cd "$HERE/../.." && pwd)
 g++ -std=c++17 -O2 -Wall -I"$REPO/include" -I"$REPO/computer-graphics-engine_b200/host" "$HERE/drop_in_main.cpp" \
     -L"$REPO/computer-graphics-engine_b200" -lcge -Wl,-rpath,"$REPO/computer-graphics-engine_b200" -o "$HERE/drop_in_main"
+g++ -std=c++17 -O2 -Wall -pthread -I"$REPO/include" -I"$REPO/computer-graphics-engine_b200/host" \
+    "$REPO/computer-graphics-engine_b200/host/cge_cli.cpp" \
+    -L"$REPO/computer-graphics-engine_b200" -lcge -Wl,-rpath,"$REPO/computer-graphics-engine_b200" -o "$HERE/cge_cli"
