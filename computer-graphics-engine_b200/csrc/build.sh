@@ -12,7 +12,7 @@ OUT=${CGE_OUT:-$PKG/libcge.so}
 LOG=${OUT%.so}_ptxas.log   # registers / spills / shared memory per kernel (-Xptxas -v)
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -fmad=false -prec-div=true -prec-sqrt=true \
-    -Xcompiler -fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function \
+    -Xcompiler -fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function,-pthread \
     -Xptxas -v $EXTRA \
     -I"$REPO/include" -I"$HERE" \
     -shared -o "$OUT" "$HERE/cge_api.cu" "$HERE/bvh_sah_gpu.cu" "$HERE/bvh_build.cpp" "$HERE/bvh_sah.cpp" -ldl 2> "$LOG" || { cat "$LOG" >&2; exit 1; }

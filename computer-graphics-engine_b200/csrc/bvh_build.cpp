@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <thread>
 
 namespace cge {
 namespace {
@@ -13,17 +14,31 @@ struct Prim {
     float lo[3], hi[3];
 };
 
+// nodes a subtree over n primitives at `depth` will have: the shape of the median-split tree depends on n and depth only
+uint32_t subtree_nodes(uint32_t n, uint32_t depth)
+{
+    if (depth + 1 == 16 || n == 1)
+        return 1;
+    return 1 + subtree_nodes(n / 2, depth + 1) + subtree_nodes(n - n / 2, depth + 1);
+}
+
 struct Builder {
     std::vector<Prim> prims;
     HostBvh* out;
 
-    uint32_t create(uint32_t beg, uint32_t end, uint32_t depth)
+    // Builds the subtree over [beg, end) into nodes [base, base + subtree_nodes) in the reference's order (children before the
+    // parent, left subtree first: src/bounding_volume_hierarchy.cpp:142-146 pushes both children, then the node) and returns
+    // the subtree root's index.  The two halves of a split touch disjoint ranges of `prims` and of `nodes`, so the top
+    // kParallelDepth levels hand their left half to another thread: same calls of std::nth_element on the same data as the
+    // sequential recursion, hence the same permutation.
+    static constexpr uint32_t kParallelDepth = 4;
+    uint32_t create(uint32_t beg, uint32_t end, uint32_t depth, uint32_t base)
     {
-        out->n_levels = std::max(out->n_levels, depth + 1);
         cge_bvh_node node {};
         node.depth = depth;
         node.beg = beg;
         node.end = end;
+        const uint32_t self = base + subtree_nodes(end - beg, depth) - 1;
         if (depth + 1 == 16 || beg + 1 == end) {
             for (int k = 0; k < 3; k++) {
                 node.lower[k] = prims[beg].lo[k];
@@ -35,17 +50,23 @@ struct Builder {
                     node.upper[k] = std::max(node.upper[k], prims[i].hi[k]);
                 }
             node.is_leaf = 1;
-            out->n_leaves++;
-            out->max_leaf_prims = std::max(out->max_leaf_prims, end - beg);
-            out->nodes.push_back(node);
-            return uint32_t(out->nodes.size() - 1);
+            out->nodes[self] = node;
+            return self;
         }
         const uint32_t mid = beg + (end - beg) / 2;
         const int axis = int(depth % 3);
         std::nth_element(prims.begin() + beg, prims.begin() + mid, prims.begin() + end,
             [axis](const Prim& a, const Prim& b) { return a.center[axis] < b.center[axis]; });
-        const uint32_t left = create(beg, mid, depth + 1);
-        const uint32_t right = create(mid, end, depth + 1);
+        const uint32_t leftNodes = subtree_nodes(mid - beg, depth + 1);
+        uint32_t left = 0, right = 0;
+        if (depth < kParallelDepth && end - beg > 4096) {
+            std::thread worker([&]() { left = create(beg, mid, depth + 1, base); });
+            right = create(mid, end, depth + 1, base + leftNodes);
+            worker.join();
+        } else {
+            left = create(beg, mid, depth + 1, base);
+            right = create(mid, end, depth + 1, base + leftNodes);
+        }
         // min/max are exact, so the union of the children's boxes equals the box over all primitives of the range
         for (int k = 0; k < 3; k++) {
             node.lower[k] = std::min(out->nodes[left].lower[k], out->nodes[right].lower[k]);
@@ -54,8 +75,8 @@ struct Builder {
         node.is_leaf = 0;
         node.left = left;
         node.right = right;
-        out->nodes.push_back(node);
-        return uint32_t(out->nodes.size() - 1);
+        out->nodes[self] = node;
+        return self;
     }
 };
 
@@ -99,8 +120,15 @@ bool build_reference_bvh(const cge_scene_desc& d, HostBvh& out)
     }
     if (b.prims.empty())
         return false;
-    out.nodes.reserve(std::min<size_t>(2 * b.prims.size(), 65536));
-    out.root = b.create(0, uint32_t(b.prims.size()), 0);
+    out.nodes.resize(subtree_nodes(uint32_t(b.prims.size()), 0));
+    out.root = b.create(0, uint32_t(b.prims.size()), 0, 0);
+    for (const cge_bvh_node& n : out.nodes) {
+        out.n_levels = std::max(out.n_levels, n.depth + 1);
+        if (n.is_leaf) {
+            out.n_leaves++;
+            out.max_leaf_prims = std::max(out.max_leaf_prims, n.end - n.beg);
+        }
+    }
     out.prim_order.resize(b.prims.size());
     for (size_t i = 0; i < b.prims.size(); i++)
         out.prim_order[i] = b.prims[i].id;
