@@ -115,93 +115,6 @@ __device__ Hit trace_reference(const DevScene& s, const vec3 o, const vec3 d, fl
     return h;
 }
 
-// Fast tree.  Triangles only (scenes with spheres are always walked by trace_reference, see cge_api.cu).
-template <bool kAnyHit, bool kCount = false>
-__device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax, unsigned* nbox = nullptr, unsigned* ntri = nullptr)
-{
-    Hit h { tmax, -1, 0u };
-    if (s.n_prims == 0)
-        return h;
-    unsigned bestRank = 0;
-    // Reciprocal direction for the slab test.  For an axis with d == 0 the archive's box function substitutes the
-    // constants [FLT_MIN, FLT_MAX] whatever the origin (SURVEY.md Appendix A, I5), i.e. it never rejects on that axis.
-    // That quirk only ADDS box visits: a triangle can be hit only where the ray really passes, so every accepted hit
-    // lies inside the geometric slabs of all its ancestors' boxes.  The fast tree therefore uses ordinary slab
-    // semantics; a huge finite reciprocal (not inf) keeps 0 * inv == 0 instead of NaN when the origin lies exactly
-    // on a box face.
-    const vec3 inv = v3(d.x != 0.0f ? fdiv(1.0f, d.x) : 3.0e38f, d.y != 0.0f ? fdiv(1.0f, d.y) : 3.0e38f,
-        d.z != 0.0f ? fdiv(1.0f, d.z) : 3.0e38f);
-
-    uint2 stack[kFastStackSize]; // (child ref, entry distance bits): re-culled against the best t when popped
-    int sp = 0;
-    constexpr unsigned kDone = 0x7fffffffu; // not a valid inner-node index
-    unsigned cur = s.froot;
-    auto pop = [&]() -> unsigned {
-        while (sp > 0) {
-            const uint2 e = stack[--sp];
-            if (__uint_as_float(e.y) > h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f)
-                continue;
-            return e.x;
-        }
-        return kDone;
-    };
-    // "while-while" traversal: all lanes of a warp walk inner nodes together, then all process their leaves together,
-    // so the two code paths are not interleaved lane by lane.
-    while (cur != kDone) {
-        while (cur < kDone) { // inner node (leaf references have bit 31 set)
-            const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
-            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-            if (kCount)
-                *nbox += 2;
-            // a box is skipped only if it starts clearly beyond the best hit so far; the slab test carries a small
-            // multiplicative slack so that rounding can only ADD visits relative to the exact arithmetic
-            const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
-            const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
-            const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
-            const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
-            const float entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
-            const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
-            const bool hitL = entL <= extL * 1.000002f && entL <= bound;
-            const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
-            const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
-            const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
-            const float entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-            const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
-            const bool hitR = entR <= extR * 1.000002f && entR <= bound;
-            const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
-            const bool leftFirst = hitL && (!hitR || entL <= entR);
-            if (hitL && hitR)
-                stack[sp++] = leftFirst ? make_uint2(cr, __float_as_uint(entR)) : make_uint2(cl, __float_as_uint(entL));
-            if (hitL || hitR)
-                cur = leftFirst ? cl : cr;
-            else
-                cur = pop();
-        }
-        if (cur == kDone)
-            break;
-        const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
-        if (kCount)
-            *ntri += count;
-        for (unsigned i = first; i < first + count; i++) {
-            float t;
-            float4 r5;
-            if (!triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, h.t, t, r5))
-                continue;
-            const unsigned rank = __float_as_uint(r5.z);
-            if (t == h.t && h.prim >= 0 && rank < bestRank)
-                continue; // an equal-t triangle the reference visits later is already held
-            h.t = t;
-            h.prim = int(i);
-            h.gid = __float_as_uint(r5.w);
-            bestRank = rank;
-            if (kAnyHit)
-                return h;
-        }
-        cur = pop();
-    }
-    return h;
-}
-
 // max / min of three: one FMNMX3 on sm_100 instead of two FMNMX
 __device__ __forceinline__ float max3(float a, float b, float c)
 {
@@ -252,6 +165,85 @@ __device__ __forceinline__ void slab_box(const SlabRay& r, float lox, float loy,
     const float tnz = __fmaf_rn(r.nz ? hiz : loz, r.inv.z, r.cNear.z), tfz = __fmaf_rn(r.nz ? loz : hiz, r.inv.z, r.cFar.z);
     ent = fmaxf(max3(tnx, tny, tnz), 0.0f);
     ext = min3(tfx, tfy, tfz);
+}
+
+// Fast tree.  Triangles only (scenes with spheres are always walked by trace_reference, see cge_api.cu).
+template <bool kAnyHit, bool kCount = false>
+__device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax, unsigned* nbox = nullptr, unsigned* ntri = nullptr)
+{
+    Hit h { tmax, -1, 0u };
+    if (s.n_prims == 0)
+        return h;
+    unsigned bestRank = 0;
+    // Reciprocal direction for the slab test.  For an axis with d == 0 the archive's box function substitutes the
+    // constants [FLT_MIN, FLT_MAX] whatever the origin (SURVEY.md Appendix A, I5), i.e. it never rejects on that axis.
+    // That quirk only ADDS box visits: a triangle can be hit only where the ray really passes, so every accepted hit
+    // lies inside the geometric slabs of all its ancestors' boxes.  The fast tree therefore uses ordinary slab
+    // semantics; a huge finite reciprocal (not inf) keeps 0 * inv == 0 instead of NaN when the origin lies exactly
+    // on a box face.
+    const SlabRay sr = slab_ray(o, d); // one FFMA per slab plane, per-axis slack (below)
+
+    uint2 stack[kFastStackSize]; // (child ref, entry distance bits): re-culled against the best t when popped
+    int sp = 0;
+    constexpr unsigned kDone = 0x7fffffffu; // not a valid inner-node index
+    unsigned cur = s.froot;
+    auto pop = [&]() -> unsigned {
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) > h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f)
+                continue;
+            return e.x;
+        }
+        return kDone;
+    };
+    // "while-while" traversal: all lanes of a warp walk inner nodes together, then all process their leaves together,
+    // so the two code paths are not interleaved lane by lane.
+    while (cur != kDone) {
+        while (cur < kDone) { // inner node (leaf references have bit 31 set)
+            const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+            const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+            if (kCount)
+                *nbox += 2;
+            // a box is skipped only if it starts clearly beyond the best hit so far; the slab test carries a small
+            // multiplicative slack so that rounding can only ADD visits relative to the exact arithmetic
+            const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
+            float entL, extL, entR, extR;
+            slab_box(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
+            slab_box(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+            const bool hitL = entL <= extL * 1.000002f && entL <= bound;
+            const bool hitR = entR <= extR * 1.000002f && entR <= bound;
+            const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+            const bool leftFirst = hitL && (!hitR || entL <= entR);
+            if (hitL && hitR)
+                stack[sp++] = leftFirst ? make_uint2(cr, __float_as_uint(entR)) : make_uint2(cl, __float_as_uint(entL));
+            if (hitL || hitR)
+                cur = leftFirst ? cl : cr;
+            else
+                cur = pop();
+        }
+        if (cur == kDone)
+            break;
+        const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+        if (kCount)
+            *ntri += count;
+        for (unsigned i = first; i < first + count; i++) {
+            float t;
+            float4 r5;
+            if (!triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, h.t, t, r5))
+                continue;
+            const unsigned rank = __float_as_uint(r5.z);
+            if (t == h.t && h.prim >= 0 && rank < bestRank)
+                continue; // an equal-t triangle the reference visits later is already held
+            h.t = t;
+            h.prim = int(i);
+            h.gid = __float_as_uint(r5.w);
+            bestRank = rank;
+            if (kAnyHit)
+                return h;
+        }
+        cur = pop();
+    }
+    return h;
 }
 
 #ifndef CGE_PREFETCH
