@@ -83,7 +83,7 @@ struct Scratch {
     size_t gatherPixels = 0;
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
-    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveBounce = 0;
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveBounce = 0, waveSub = 0;
     float* bloomTmp = nullptr; // thresholded copy of the frame (renderBloomFilter's screenThreshold)
     size_t bloomPixels = 0;
     cudaStream_t stream = nullptr;
@@ -496,8 +496,13 @@ constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than thi
 
 struct WaveSizes {
     size_t recFloats, meta, next, dirFloats, vis;
-    size_t bytes() const { return recFloats * 4 + meta * 8 * 2 + next * 4 + dirFloats * 4 + vis; } // meta + bounce queue
+    size_t bytes() const { return recFloats * 4 + meta * 8 * 2 + next * 4 + dirFloats * 4 + vis; } // meta + bounce queue (the
+                                                                                                     // sub-ray colours are small beside these)
 };
+// camera rays per pixel: with extra.enableMultipleRaysPerPixel every one of them is a chain of its own in the queues
+size_t sub_rays(const DevParams& dp) { return dp.aa_side ? size_t(dp.aa_side) * dp.aa_side : 1; }
+
+// cap = queue capacity per level = camera rays of the launch
 WaveSizes wave_sizes(const DevParams& dp, size_t cap)
 {
     WaveSizes w;
@@ -518,14 +523,16 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
     v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
     v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
         && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count && !dp.aa_side;
-    const size_t cap = size_t(dp.tile_count) * 32;
+    const size_t cap = size_t(dp.tile_count) * 32 * sub_rays(dp);
     v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
     // The wavefront pays off when a pixel's cost is wildly non-uniform, i.e. with area lights (16+ shadow rays per evaluation,
     // 2^k evaluations at level k).  Point-light frames (<= 1 shadow ray per light and hit, recursion folded) are bounded per
     // pixel and launch-latency sensitive: there the single per-thread kernel is faster.
     const bool areaLights = dp.draws_per_hit > 0 || (p.flags & CGE_FLAG_WAVEFRONT);
-    // several camera rays per pixel (anti-aliasing) share one running draw counter: per-thread kernel only for now
-    v.wave = v.fast && !v.coop && !v.count && areaLights && !dp.aa_side && (p.features & CGE_FEAT_SHADING)
+    // several camera rays per pixel: the queues address a pixel with 24 bits (wavefront.cuh meta layout), larger frames and
+    // the opt-in per-level chain stage take the per-thread kernel
+    const bool aaFits = !dp.aa_side || (size_t(p.width) * size_t(p.height) <= (size_t(1) << 24) && !(p.flags & CGE_FLAG_CHAIN_PER_LEVEL));
+    v.wave = v.fast && !v.coop && !v.count && areaLights && aaFits && (p.features & CGE_FEAT_SHADING)
         && !(p.flags & (CGE_FLAG_PER_THREAD | CGE_FLAG_DEBUG_CYCLES)) && v.waveBytes <= kWaveScratchLimit && cap > 0;
     return v;
 }
@@ -612,7 +619,7 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         return std::max(1u, std::min(grid, (myTiles + 3) / 4));
     };
     if (v.wave) {
-        const size_t cap = size_t(myTiles) * 32;
+        const size_t cap = size_t(myTiles) * 32 * sub_rays(dp);
         const WaveSizes ws = wave_sizes(dp, cap);
         auto grow = [&](auto*& ptr, size_t& have, size_t need, size_t elem) -> cudaError_t {
             if (have >= need)
@@ -633,6 +640,8 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
             err = grow(s->wave.next, s->waveNext, ws.next, sizeof(unsigned));
         if (err == cudaSuccess)
             err = grow(s->wave.dir, s->waveDirFloats, ws.dirFloats, sizeof(float));
+        if (err == cudaSuccess && dp.aa_side)
+            err = grow(s->wave.sub, s->waveSub, cap * 3, sizeof(float));
         // Shadow-ray granularity.  Default: 16 coupled rays per lane inside wf_shade_kernel<false>.  When the launch has few
         // direct-lighting evaluations per resident warp (small frames, one rank's share of a multi-GPU frame) the tail of
         // that coarse granularity dominates, so the rays are traced in groups of 4 per lane (wf_vis_grouped_kernel) into
@@ -663,10 +672,14 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         int perSm = 0;
         if (err == cudaSuccess)
             err = (p->flags & CGE_FLAG_CHAIN_PER_LEVEL) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_primary_kernel, 128, 0)
-                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel, 128, 0);
+                  : dp.aa_side                          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<true>, 128, 0)
+                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<false>, 128, 0);
         if (err == cudaSuccess && !(p->flags & CGE_FLAG_CHAIN_PER_LEVEL)) {
             cudaEventRecord(stage[0], s->stream);
-            wf_chain_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
+            if (dp.aa_side)
+                wf_chain_kernel<true><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
+            else
+                wf_chain_kernel<false><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
             err = cudaGetLastError();
             cudaEventRecord(stage[1], s->stream);
         } else if (err == cudaSuccess) {
@@ -729,6 +742,11 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         if (err == cudaSuccess) {
             wf_fold_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(wp, s->wave, rgbDev);
             err = cudaGetLastError();
+        }
+        if (err == cudaSuccess && dp.aa_side) {
+            wf_resolve_kernel<<<unsigned((size_t(myTiles) * 32 + 127) / 128), 128, 0, s->stream>>>(wp, s->wave, rgbDev);
+            err = cudaGetLastError();
+            *launches += 1;
         }
         cudaEventRecord(stage[4], s->stream);
         s->staged = true;
@@ -1265,6 +1283,7 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.dir);
         cudaFree(s->wave.vis);
         cudaFree(s->wave.bounce);
+        cudaFree(s->wave.sub);
         cudaFree(s->bloomTmp);
         cudaFree(s->wave.counts);
         if (s->ev0)

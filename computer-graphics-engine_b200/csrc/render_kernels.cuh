@@ -216,7 +216,8 @@ struct PixelTracer {
     }
 };
 
-__device__ __forceinline__ bool next_tile(const DevParams& p, unsigned* tileCounter, unsigned lane, int& x, int& y)
+// kOut: the tile's position in this launch's list (its pixels are [32 kOut, 32 kOut + 32) of every per-launch buffer)
+__device__ __forceinline__ bool next_tile(const DevParams& p, unsigned* tileCounter, unsigned lane, int& x, int& y, unsigned* kOut = nullptr)
 {
     unsigned k = 0;
     if (lane == 0)
@@ -224,6 +225,8 @@ __device__ __forceinline__ bool next_tile(const DevParams& p, unsigned* tileCoun
     k = __shfl_sync(0xffffffffu, k, 0);
     if (k >= p.tile_count)
         return false;
+    if (kOut)
+        *kOut = k;
     // multi-GPU: the tile list is interleaved across ranks, entry k of this rank's list is tile part_index + k * part_count
     const unsigned tile = p.part_index + (p.tile_first + k) * p.part_count;
     x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);

@@ -52,6 +52,12 @@ CGE_SAMPLER_HD uint32_t cge_aa_seed(uint32_t seed, uint32_t pixel) { return cge_
 // largest raysPerPixelSide the reference GUI allows.
 struct CgeMt19937Head {
     uint32_t lo, hi, i; // s[i], s[i + 397]
+    CGE_SAMPLER_HD CgeMt19937Head()
+        : lo(0)
+        , hi(0)
+        , i(0)
+    {
+    }
     CGE_SAMPLER_HD explicit CgeMt19937Head(uint32_t seed)
         : lo(seed)
         , hi(seed)

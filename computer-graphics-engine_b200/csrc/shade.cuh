@@ -171,6 +171,14 @@ __device__ __forceinline__ float rand01(unsigned seed, unsigned pixel, unsigned 
     return fmul(float(int(cge_hash_sample(seed, pixel, ctr))), 4.656612873077392578125e-10f);
 }
 
+// x / float(n) as the reference computes it.  For a power-of-two sample count (the common 2 / 4 / 8 / 16) the quotient equals the
+// product with the exactly representable reciprocal, one FMUL instead of an IEEE division; the branch is uniform.
+__device__ __forceinline__ float div_by_count(float x, int n)
+{
+    const float fn = float(n);
+    return (n & (n - 1)) == 0 && n > 0 ? fmul(x, fdiv(1.0f, fn)) : fdiv(x, fn);
+}
+
 struct LightSample {
     vec3 pos, col;
     bool shadowed; // whether the reference tests visibility for this sample
@@ -188,21 +196,19 @@ __device__ __forceinline__ LightSample sample_light(const float* __restrict__ L,
         out.shadowed = p.features & CGE_FEAT_HARD_SHADOW;
     } else if (type == CGE_LIGHT_SEGMENT) {
         const vec3 e0 = ld3(0), e1 = ld3(3), c0 = ld3(6), c1 = ld3(9);
-        const float n = float(p.segment_samples);
         const float r = rand01(p.seed, pixel, ctr + unsigned(si));
-        const float w = fdiv(fadd(float(si), r), n);
+        const float w = div_by_count(fadd(float(si), r), p.segment_samples);
         out.pos = (e1 - e0) * w + e0;
         out.col = w * c1 + fsub(1.0f, w) * c0;
         out.shadowed = true;
     } else {
         const vec3 v0 = ld3(0), e01 = ld3(3), e02 = ld3(6), c0 = ld3(9), c1 = ld3(12), c2 = ld3(15), c3 = ld3(18);
         const int ns = p.parallelogram_samples;
-        const float n = float(ns);
         const int i = si / ns, k = si % ns; // i (edge01) outer, k (edge02) inner; horizontal draw first
         const float hr = rand01(p.seed, pixel, ctr + 2u * unsigned(si));
         const float vr = rand01(p.seed, pixel, ctr + 2u * unsigned(si) + 1u);
-        const float hw = fdiv(fadd(float(i), hr), n);
-        const float vw = fdiv(fadd(float(k), vr), n);
+        const float hw = div_by_count(fadd(float(i), hr), ns);
+        const float vw = div_by_count(fadd(float(k), vr), ns);
         out.pos = (v0 + hw * e01) + vw * e02;
         const vec3 bottom = hw * c1 + fsub(1.0f, hw) * c0;
         const vec3 top = hw * c3 + fsub(1.0f, hw) * c2;
@@ -254,8 +260,11 @@ struct PixelSampler {
     CgeMt19937Head mt;
     float px, py, bx, by; // pixel corner and the size of one stratum (pixelBox) in NDC
     __device__ PixelSampler(const DevParams& p, int x, int y)
-        : mt(cge_aa_seed(p.seed, unsigned(y) * unsigned(p.width) + unsigned(x)))
     {
+        px = py = bx = by = 0.0f;
+        if (!p.aa_side) // feature off: nothing to set up (the generator's warm-up is 397 integer steps)
+            return;
+        mt = CgeMt19937Head(cge_aa_seed(p.seed, unsigned(y) * unsigned(p.width) + unsigned(x)));
         const float n = float(p.aa_side);
         px = fsub(fmul(fdiv(float(x), float(p.width)), 2.0f), 1.0f);
         py = fsub(fmul(fdiv(float(y), float(p.height)), 2.0f), 1.0f);

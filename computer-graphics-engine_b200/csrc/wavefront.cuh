@@ -30,6 +30,14 @@ namespace cge {
 
 constexpr int kWaveRecFloats = kRecFloats + 3; // hit record + the shadow-ray origin of src/light.cpp:54-58 (hoisted)
 
+// meta word layout.  .x = pixel index (y * W + x, reference coordinates) | sub-ray << 24: with extra.enableMultipleRaysPerPixel
+// a pixel has n x n camera rays, each a chain of its own in the queues (the host takes this path only for frames of at most
+// 2^24 pixels).  .y = hit levels of the chain | missEnd << 8 | units << 9, units = direct-lighting evaluations made by the
+// pixel's EARLIER camera rays: the reference's rand() counter keeps running across them (src/render.cpp:297-299).
+constexpr unsigned kMetaPixelMask = 0x00ffffffu;
+__device__ __forceinline__ unsigned wf_pixel(const uint2& m) { return m.x & kMetaPixelMask; }
+__device__ __forceinline__ unsigned wf_sub_ray(const uint2& m) { return m.x >> 24; }
+
 struct WaveBuffers {
     float* rec;
     uint2* meta;
@@ -39,6 +47,7 @@ struct WaveBuffers {
     unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] ray counter,
                         // [32..47] bounce-queue length per level, [48..63] bounce-queue chunk counter per level
     uint2* bounce;      // [level][cap]: (level-0 slot of the pixel, slot of its hit at level - 1): the rays wf_bounce_kernel traces
+    float* sub;         // multiple rays per pixel: [3][launch pixel][sub-ray] colour of every camera ray, summed by wf_resolve_kernel
     unsigned cap;
 };
 
@@ -66,7 +75,9 @@ __device__ __forceinline__ size_t wf_dir_off(const DevParams& p, unsigned cap, u
 #ifndef CGE_MINB_CHAIN
 #define CGE_MINB_CHAIN 6
 #endif
-__global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_chain_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb, float* __restrict__ rgb,
+// kSubRays: extra.enableMultipleRaysPerPixel (a separate instantiation so that the common case does not carry the sampler's state)
+template <bool kSubRays>
+__global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb, float* __restrict__ rgb,
     int* __restrict__ ids, Counters* __restrict__ gcnt)
 {
     const unsigned lane = threadIdx.x & 31;
@@ -74,73 +85,96 @@ __global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_chain_kernel(DevScene 
     const bool recursive = p.features & CGE_FEAT_RECURSIVE;
     Counters cnt {};
     int x, y;
-    while (next_tile(p, wb.counts + 16, lane, x, y)) {
+    unsigned tileK = 0;
+    const unsigned aa = kSubRays ? p.aa_side : 0u;
+    const unsigned nSub = kSubRays ? aa * aa : 1u;
+    while (next_tile(p, wb.counts + 16, lane, x, y, &tileK)) {
         const bool live = x < p.width && y < p.height;
         const unsigned pixel = unsigned(y) * unsigned(p.width) + unsigned(x);
-        Ray ray {};
-        if (live)
-            ray = generate_ray(cam, x, y, p.width, p.height);
-        bool alive = live;
-        bool missEnd = false;
-        int n = 0;
-        unsigned slots[kMaxLevels];
-        for (int level = 0; __any_sync(0xffffffffu, alive); level++) {
-            bool hit = false;
-            Hit h {};
-            if (alive) {
-                h = trace_fast<false>(s, ray.o, ray.d, ray.t);
-                if (level == 0)
-                    cnt.primary++;
-                else
-                    cnt.bounce++;
-                hit = h.prim >= 0;
-                if (!hit) {
-                    missEnd = true;
-                    alive = false;
+        DevParams sp = p;
+        if (!kSubRays)
+            sp.aa_side = 0;
+        PixelSampler ps(sp, live ? x : 0, live ? y : 0);
+        unsigned unitsBefore = 0; // direct-lighting evaluations of this pixel's earlier camera rays
+        if (kSubRays && live && ids) { // the id map stays that of the un-jittered pixel-corner ray (not a reference ray: not counted)
+            const Ray c = generate_ray(cam, x, y, p.width, p.height);
+            const Hit h = trace_fast<false>(s, c.o, c.d, c.t);
+            ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = h.prim >= 0 ? int(h.gid) : -1;
+        }
+        for (unsigned sub = 0; sub < nSub; sub++) {
+            Ray ray {};
+            if (live)
+                ray = kSubRays ? ps.ray(cam, int(sub / aa), int(sub % aa)) : generate_ray(cam, x, y, p.width, p.height);
+            bool alive = live;
+            bool missEnd = false;
+            int n = 0;
+            unsigned slots[kMaxLevels];
+            for (int level = 0; __any_sync(0xffffffffu, alive); level++) {
+                bool hit = false;
+                Hit h {};
+                if (alive) {
+                    h = trace_fast<false>(s, ray.o, ray.d, ray.t);
+                    if (level == 0)
+                        cnt.primary++;
+                    else
+                        cnt.bounce++;
+                    hit = h.prim >= 0;
+                    if (!hit) {
+                        missEnd = true;
+                        alive = false;
+                    }
+                }
+                // warp-aggregated queue append: one atomic per warp and level
+                const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                unsigned base = 0;
+                if (lane == 0 && ballot)
+                    base = atomicAdd(wb.counts + level, unsigned(__popc(ballot)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) {
+                    const unsigned slot = base + unsigned(__popc(ballot & below));
+                    slots[level] = slot;
+                    ray.t = h.t;
+                    HitRec r;
+                    resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
+                    float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + slot;
+                    const size_t c = wb.cap;
+                    b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
+                    b[3 * c] = r.ray.d.x, b[4 * c] = r.ray.d.y, b[5 * c] = r.ray.d.z;
+                    b[6 * c] = r.ray.t;
+                    b[7 * c] = r.normal.x, b[8 * c] = r.normal.y, b[9 * c] = r.normal.z;
+                    b[10 * c] = r.m.kd.x, b[11 * c] = r.m.kd.y, b[12 * c] = r.m.kd.z;
+                    b[13 * c] = r.m.ks.x, b[14 * c] = r.m.ks.y, b[15 * c] = r.m.ks.z;
+                    b[16 * c] = r.m.shininess;
+                    const vec3 so = shadow_origin(r);
+                    b[17 * c] = so.x, b[18 * c] = so.y, b[19 * c] = so.z;
+                    if (level > 0)
+                        wb.next[size_t(level - 1) * wb.cap + slots[level - 1]] = slot;
+                    else if (ids && !kSubRays)
+                        ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = int(h.gid);
+                    n = level + 1;
+                    Ray nextRay;
+                    if (!recursive || level >= p.ray_depth || !reflection_ray(r, nextRay))
+                        alive = false;
+                    else
+                        ray = nextRay;
                 }
             }
-            // warp-aggregated queue append: one atomic per warp and level
-            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-            unsigned base = 0;
-            if (lane == 0 && ballot)
-                base = atomicAdd(wb.counts + level, unsigned(__popc(ballot)));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hit) {
-                const unsigned slot = base + unsigned(__popc(ballot & below));
-                slots[level] = slot;
-                ray.t = h.t;
-                HitRec r;
-                resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
-                float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + slot;
-                const size_t c = wb.cap;
-                b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
-                b[3 * c] = r.ray.d.x, b[4 * c] = r.ray.d.y, b[5 * c] = r.ray.d.z;
-                b[6 * c] = r.ray.t;
-                b[7 * c] = r.normal.x, b[8 * c] = r.normal.y, b[9 * c] = r.normal.z;
-                b[10 * c] = r.m.kd.x, b[11 * c] = r.m.kd.y, b[12 * c] = r.m.kd.z;
-                b[13 * c] = r.m.ks.x, b[14 * c] = r.m.ks.y, b[15 * c] = r.m.ks.z;
-                b[16 * c] = r.m.shininess;
-                const vec3 so = shadow_origin(r);
-                b[17 * c] = so.x, b[18 * c] = so.y, b[19 * c] = so.z;
-                if (level > 0)
-                    wb.next[size_t(level - 1) * wb.cap + slots[level - 1]] = slot;
-                else if (ids)
-                    ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = int(h.gid);
-                n = level + 1;
-                Ray nextRay;
-                if (!recursive || level >= p.ray_depth || !reflection_ray(r, nextRay))
-                    alive = false;
-                else
-                    ray = nextRay;
+            if (live) {
+                reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
+                const uint2 m = make_uint2(pixel | (sub << 24), unsigned(n) | (missEnd ? 256u : 0u) | (unitsBefore << 9));
+                for (int k = 0; k < n; k++)
+                    wb.meta[size_t(k) * wb.cap + slots[k]] = m;
+                if (kSubRays)
+                    unitsBefore += p.draws_per_hit ? (1u << n) - 1u : 0u;
+                if (n == 0) {
+                    if (!kSubRays) {
+                        store_pixel(p, rgb, ids, x, y, v3(0.0f), -1); // primary miss: black (reference src/render.cpp:148)
+                    } else { // this camera ray adds vec3(0) to the pixel's sum
+                        const size_t at = (size_t(tileK) * 32u + lane) * nSub + sub, plane = size_t(p.tile_count) * 32u * nSub;
+                        wb.sub[at] = 0.0f, wb.sub[plane + at] = 0.0f, wb.sub[2 * plane + at] = 0.0f;
+                    }
+                }
             }
-        }
-        if (live) {
-            reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
-            const unsigned tag = unsigned(n) | (missEnd ? 256u : 0u);
-            for (int k = 0; k < n; k++)
-                wb.meta[size_t(k) * wb.cap + slots[k]] = make_uint2(pixel, tag);
-            if (n == 0)
-                store_pixel(p, rgb, ids, x, y, v3(0.0f), -1); // primary miss: black (reference src/render.cpp:148)
         }
     }
     flush_counters(cnt, gcnt);
@@ -374,6 +408,11 @@ __device__ __forceinline__ unsigned wf_draw_base(const DevParams& p, unsigned k,
     }
     return idx * p.draws_per_hit;
 }
+// ... plus the draws of the pixel's earlier camera rays (meta .y bits 9..31, zero without multiple rays per pixel)
+__device__ __forceinline__ unsigned wf_unit_ctr(const DevParams& p, unsigned k, unsigned path, const uint2& m)
+{
+    return wf_draw_base(p, k, path, m.y & 255u) + (m.y >> 9) * p.draws_per_hit;
+}
 
 // hit-record fields the zero-shading cull needs (shade.cuh shading_is_zero): incoming ray and normal of queue slot e, level k
 __device__ __forceinline__ ShadeFrame wf_load_frame(const WaveBuffers& wb, unsigned k, unsigned e)
@@ -473,8 +512,8 @@ __global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevPa
                         const unsigned inLevel = u - cum[k], cnt = wb.counts[k];
                         const unsigned path = inLevel / cnt, e = inLevel - path * cnt;
                         const uint2 m = wb.meta[size_t(k) * wb.cap + e];
-                        pixel = m.x;
-                        ctrBase = wf_draw_base(p, k, path, m.y & 255u);
+                        pixel = wf_pixel(m);
+                        ctrBase = wf_unit_ctr(p, k, path, m);
                         const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
                         o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
                         if (s.cull_zero_shading)
@@ -619,7 +658,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_grouped_kernel(DevSc
         const unsigned block = inLevel / cnt, e = inLevel - block * cnt;
         const unsigned path = block / groups, g = block - path * groups;
         const uint2 m = wb.meta[size_t(k) * wb.cap + e];
-        const unsigned ctrBase = wf_draw_base(p, k, path, m.y & 255u);
+        const unsigned ctrBase = wf_unit_ctr(p, k, path, m);
         const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
         const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
         ShadeFrame frame {};
@@ -629,7 +668,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_grouped_kernel(DevSc
         const unsigned sEnd = min(S, (g + 1u) * kGroup);
         int occluder = -1; // the triangle that blocked this lane's previous sample: tested first (occluder coherence)
         for (unsigned sg = g * kGroup; sg < sEnd; sg++) {
-            const LightSample ls = wf_sample(s, p, sg, m.x, ctrBase);
+            const LightSample ls = wf_sample(s, p, sg, wf_pixel(m), ctrBase);
             unsigned char v = 1;
             if (ls.shadowed && !shading_is_zero(s, frame, ls.pos)) {
                 nshadow++;
@@ -690,8 +729,7 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
         const unsigned cnt = wb.counts[k];
         const unsigned path = inLevel / cnt, e = inLevel - path * cnt;
         const uint2 m = wb.meta[size_t(k) * wb.cap + e];
-        const unsigned nChain = m.y & 255u;
-        const unsigned ctr = wf_draw_base(p, k, path, nChain);
+        const unsigned ctr = wf_unit_ctr(p, k, path, m);
         const float* b = wb.rec + (size_t(k) * kWaveRecFloats) * wb.cap + e;
         const size_t c = wb.cap;
         HitRec h;
@@ -704,7 +742,7 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
         h.m.shininess = b[16 * c];
         // ray index of this evaluation's sample 0 (see wf_visibility_kernel); consecutive samples are cnt bytes apart
         const unsigned char* vis = kLookup ? wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e) : nullptr;
-        const vec3 d = wf_direct<kLookup>(s, p, h, m.x, ctr, nshadow, vis, cnt);
+        const vec3 d = wf_direct<kLookup>(s, p, h, wf_pixel(m), ctr, nshadow, vis, cnt);
         float* out = wb.dir + wf_dir_off(p, wb.cap, k) + (size_t(path) * 3u) * wb.cap + e;
         out[0] = d.x;
         out[c] = d.y;
@@ -771,8 +809,44 @@ __global__ void __launch_bounds__(128) wf_fold_kernel(DevParams p, WaveBuffers w
             }
         }
     }
-    const unsigned px = m.x % unsigned(p.width), py = m.x / unsigned(p.width);
+    const unsigned pixel = wf_pixel(m);
+    const unsigned px = pixel % unsigned(p.width), py = pixel / unsigned(p.width);
+    if (p.aa_side) { // one of the pixel's n x n camera rays: parked for wf_resolve_kernel, which adds them in the reference's order
+        const unsigned nSub = p.aa_side * p.aa_side;
+        const unsigned tile = (py / kTileH) * p.n_tiles_x + px / kTileW;
+        const unsigned k = (tile - p.part_index) / p.part_count - p.tile_first; // position of the tile in this launch's list
+        const size_t at = (size_t(k) * 32u + (py % kTileH) * kTileW + px % kTileW) * nSub + wf_sub_ray(m);
+        const size_t plane = size_t(p.tile_count) * 32u * nSub;
+        wb.sub[at] = out.x, wb.sub[plane + at] = out.y, wb.sub[2 * plane + at] = out.z;
+        return;
+    }
     const size_t idx = size_t(p.height - 1 - int(py)) * size_t(p.width) + size_t(px);
+    rgb[idx * 3 + 0] = out.x;
+    rgb[idx * 3 + 1] = out.y;
+    rgb[idx * 3 + 2] = out.z;
+}
+
+// extra.enableMultipleRaysPerPixel (src/render.cpp:295-303,322): color = sum of the camera rays' colours in their order,
+// color /= n * n, colorSum = 0 + color, finalColor = colorSum / float(1)
+__global__ void __launch_bounds__(128) wf_resolve_kernel(DevParams p, WaveBuffers wb, float* __restrict__ rgb)
+{
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned k = g / 32u, lane = g % 32u;
+    if (k >= p.tile_count)
+        return;
+    const unsigned tile = p.part_index + (p.tile_first + k) * p.part_count;
+    const int x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW), y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
+    if (x >= p.width || y >= p.height)
+        return;
+    const unsigned nSub = p.aa_side * p.aa_side;
+    const size_t plane = size_t(p.tile_count) * 32u * nSub;
+    const float* q = wb.sub + size_t(g) * nSub;
+    vec3 color = v3(0.0f);
+    for (unsigned sub = 0; sub < nSub; sub++)
+        color = color + v3(q[sub], q[plane + sub], q[2 * plane + sub]);
+    color = color / float(int(nSub));
+    const vec3 out = (v3(0.0f) + color) / 1.0f;
+    const size_t idx = size_t(p.height - 1 - y) * size_t(p.width) + size_t(x);
     rgb[idx * 3 + 0] = out.x;
     rgb[idx * 3 + 1] = out.y;
     rgb[idx * 3 + 2] = out.z;

@@ -99,3 +99,27 @@ def test_extras_argument_errors(cge):
             with pytest.raises(cge.CgeError) as e:
                 sc.render(dict(cfg, features=cfg["features"] | (1 << bit)))
             assert e.value.code == cge.ERR_UNSUPPORTED
+
+
+def test_aa_wavefront_equals_per_thread_kernel(cge, monkeypatch):
+    """With area lights a multi-sample frame goes through the wavefront pipeline (every camera ray a chain of its own in the
+    queues, draw counters offset by the pixel's earlier rays, wf_resolve_kernel adding them in the reference's order): the
+    frame must equal the per-thread kernel's bit for bit, whole, in bands and in partitions."""
+    cfg = cge.configs.get("c3_teapot_soft", 480, 270)
+    cfg["features"] |= extras_cases.AA | cge.configs.FEAT_RECURSIVE
+    cfg.update(rays_per_pixel_side=3, ray_depth=2, seed=9)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_PER_THREAD)
+        rgb_w, ids_w, st_w = sc.render(cfg, traversal=1)
+        assert st_w["stage_ms"][1] > 0  # the wavefront pipeline ran
+        assert rgb_w.tobytes() == rgb_t.tobytes() and np.array_equal(ids_w, ids_t)
+        for k in ("primary_rays", "bounce_rays", "shadow_rays", "reference_rays"):
+            assert st_w[k] == st_t[k], k
+        monkeypatch.setenv("CGE_BANDS", "3")
+        rgb_b, _, _ = sc.render(cfg, traversal=1)
+        monkeypatch.delenv("CGE_BANDS")
+        assert rgb_b.tobytes() == rgb_t.tobytes()
+        rgb_p = np.zeros_like(rgb_t)
+        for k in range(3):
+            sc.render(cfg, traversal=1, rgb_out=rgb_p, want_ids=False, part=(k, 3))
+        assert rgb_p.tobytes() == rgb_t.tobytes()
