@@ -284,6 +284,9 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     d.ray_depth = p.ray_depth;
     d.segment_samples = p.segment_samples;
     d.parallelogram_samples = p.parallelogram_samples;
+    auto exact_recip = [](int n) { return n > 0 && (n & (n - 1)) == 0 ? 1.0f / float(n) : 0.0f; };
+    d.segment_recip = exact_recip(p.segment_samples);
+    d.parallelogram_recip = exact_recip(p.parallelogram_samples);
     d.seed = p.seed;
     host_light_counts(sc->host_lights, p, d.draws_per_hit, d.shadow_rays_per_hit, d.samples_per_hit);
     d.levels = (p.features & CGE_FEAT_RECURSIVE) ? uint32_t(p.ray_depth) + 1u : 1u;

@@ -84,6 +84,7 @@ struct DevParams {
     uint32_t features;
     int32_t ray_depth;
     int32_t segment_samples, parallelogram_samples;
+    float segment_recip, parallelogram_recip; // 1 / samples when that is exact (power of two), else 0 (shade.cuh div_by_count)
     uint32_t seed;
     uint32_t draws_per_hit;       // rand() draws one computeLightContribution call makes (0 -> deterministic fold)
     uint32_t shadow_rays_per_hit; // shadow rays one computeLightContribution call traces

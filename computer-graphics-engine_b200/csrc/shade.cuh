@@ -172,11 +172,11 @@ __device__ __forceinline__ float rand01(unsigned seed, unsigned pixel, unsigned 
 }
 
 // x / float(n) as the reference computes it.  For a power-of-two sample count (the common 2 / 4 / 8 / 16) the quotient equals the
-// product with the exactly representable reciprocal, one FMUL instead of an IEEE division; the branch is uniform.
-__device__ __forceinline__ float div_by_count(float x, int n)
+// product with the exactly representable reciprocal, which the host put into DevParams (0 = not a power of two): one FMUL
+// instead of an IEEE division; the branch is uniform.
+__device__ __forceinline__ float div_by_count(float x, int n, float exactRecip)
 {
-    const float fn = float(n);
-    return (n & (n - 1)) == 0 && n > 0 ? fmul(x, fdiv(1.0f, fn)) : fdiv(x, fn);
+    return exactRecip != 0.0f ? fmul(x, exactRecip) : fdiv(x, float(n));
 }
 
 struct LightSample {
@@ -197,7 +197,7 @@ __device__ __forceinline__ LightSample sample_light(const float* __restrict__ L,
     } else if (type == CGE_LIGHT_SEGMENT) {
         const vec3 e0 = ld3(0), e1 = ld3(3), c0 = ld3(6), c1 = ld3(9);
         const float r = rand01(p.seed, pixel, ctr + unsigned(si));
-        const float w = div_by_count(fadd(float(si), r), p.segment_samples);
+        const float w = div_by_count(fadd(float(si), r), p.segment_samples, p.segment_recip);
         out.pos = (e1 - e0) * w + e0;
         out.col = w * c1 + fsub(1.0f, w) * c0;
         out.shadowed = true;
@@ -207,8 +207,8 @@ __device__ __forceinline__ LightSample sample_light(const float* __restrict__ L,
         const int i = si / ns, k = si % ns; // i (edge01) outer, k (edge02) inner; horizontal draw first
         const float hr = rand01(p.seed, pixel, ctr + 2u * unsigned(si));
         const float vr = rand01(p.seed, pixel, ctr + 2u * unsigned(si) + 1u);
-        const float hw = div_by_count(fadd(float(i), hr), ns);
-        const float vw = div_by_count(fadd(float(k), vr), ns);
+        const float hw = div_by_count(fadd(float(i), hr), ns, p.parallelogram_recip);
+        const float vw = div_by_count(fadd(float(k), vr), ns, p.parallelogram_recip);
         out.pos = (v0 + hw * e01) + vw * e02;
         const vec3 bottom = hw * c1 + fsub(1.0f, hw) * c0;
         const vec3 top = hw * c3 + fsub(1.0f, hw) * c2;
