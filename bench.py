@@ -399,10 +399,13 @@ def main():
             algo_bytes = ref_rays / world * bytes_per_ray + 12.0 * W * H / world
         # the dominant kernel traces the shadow rays (wf_vis_grouped_kernel, or wf_shade_kernel for point-light scenes)
         traffic = None
+        warp_inst = None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get(cfg["name"], {}).get(dom_name)
+                entry = json.loads(tf.read_text()).get(cfg["name"], {})
+                traffic = entry.get(dom_name)
+                warp_inst = entry.get(dom_name + "_warp_instructions")
             except Exception:
                 traffic = None
         if dom_ms > 0:
@@ -411,6 +414,15 @@ def main():
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel": "cge::" + dom_name,
                     "kernel_ms": dom_ms, "share_of_step": dom_ms / single_ms,
+                    # the bound that actually operates: warp instructions issued per second against what the
+                    # schedulers can issue (SMs x 4 schedulers x SM clock); instruction count from the committed ncu capture of
+                    # this kernel on this workload (whole frame on one GPU), duration and clock live
+                    "issue": None if not (warp_inst and world == 1 and clocks and clocks.get("sm_mhz")) else {
+                        "warp_instructions_per_launch": warp_inst,
+                        "achieved_ginst_s": warp_inst / (dom_ms * 1e-3) / 1e9,
+                        "peak_ginst_s": 148 * 4 * float(clocks["sm_mhz"]) * 1e6 / 1e9,
+                        "frac": warp_inst / (dom_ms * 1e-3) / (148 * 4 * float(clocks["sm_mhz"]) * 1e6),
+                        "source": "smsp__inst_executed.sum from profiles/r02_wf_vis_grouped_c5.txt (via profiles/traffic.json)"},
                     "measured_on": f"{args.steps} steps of the same frame as ONE pipeline (CGE_BANDS=1, {single_ms:.3f} ms per step): the "
                                    "timed `value` steps run the frame as concurrent bands whose stage boundaries overlap",
                     "stage_ms": {**dict(zip(stage_names, stage_vals)), "pipeline": pipeline_ms},
