@@ -1490,8 +1490,11 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     if (dp.part_count <= 1 && !(p->features & CGE_FEAT_BLOOM_EFFECT) && !(rgba8 && wantIds))
         nBands = nBandsFor(sc, *p, dp, !devOut);
     std::vector<Scratch*> bands;
-    rc = acquire_bands(sc, s, nBands, bands);
-    if (rc == CGE_OK && nBands > 1)
+    if (acquire_bands(sc, s, nBands, bands) != CGE_OK) { // no room for the helpers' queues: one pipeline is always possible
+        cudaGetLastError();
+        nBands = 1;
+    }
+    if (nBands > 1)
         rc = use_band_stream(s, 0);
     if (rc != CGE_OK) {
         for (Scratch* b : bands)
@@ -2006,10 +2009,13 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     // every rank renders its interleaved tile subset straight into the full-frame layout of its own scratch frame, as
     // concurrent bands of its tile list when the share is large enough (launch_bands: the stage tails do not shrink with the
     // partition, so they weigh more the more GPUs share the frame)
-    const unsigned nBands = nBandsFor(sc, p, dp, false);
+    unsigned nBands = nBandsFor(sc, p, dp, false);
     std::vector<Scratch*> bands;
-    rc = acquire_bands(sc, s, nBands, bands);
-    if (rc == CGE_OK && nBands > 1)
+    if (acquire_bands(sc, s, nBands, bands) != CGE_OK) {
+        cudaGetLastError();
+        nBands = 1;
+    }
+    if (nBands > 1)
         rc = use_band_stream(s, 0);
     if (rc != CGE_OK) {
         for (Scratch* b : bands)

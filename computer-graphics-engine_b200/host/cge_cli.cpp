@@ -264,8 +264,11 @@ std::string joinPath(const std::string& dir, const std::string& name)
 
 int main(int argc, char** argv)
 {
-    if (argc != 2) {
-        std::fprintf(stderr, "usage: %s config.toml\n", argv[0]);
+    // --print-config: read the file, print what was understood (the reference prints its Config the same way before it
+    // renders, src/main.cpp:480 / src/config.cpp:68-123) and stop before any GPU work
+    const bool printOnly = argc == 3 && std::string(argv[2]) == "--print-config";
+    if (argc != 2 && !printOnly) {
+        std::fprintf(stderr, "usage: %s config.toml [--print-config]\n", argv[0]);
         return 2;
     }
     try {
@@ -322,6 +325,25 @@ int main(int argc, char** argv)
         bloomDebugOption = int(getNumber(cfg, { "render", "bloom_debug_option" }, 0));
         samplerSeed = uint32_t(getNumber(cfg, { "render", "seed" }, 0));
         const bool timestamp = getBool(cfg, { "render", "timestamp" }, true);
+
+        if (printOnly) {
+            std::printf("window_size %d %d\nscene %s\ndata_path %s\noutput_dir %s\n", windowSize.x, windowSize.y, sceneName.c_str(),
+                dataPath.c_str(), outputDir.c_str());
+            std::printf("features shading %d recursive %d hard_shadow %d soft_shadow %d normal_interp %d texture_mapping %d accel_structure %d\n",
+                features.enableShading, features.enableRecursive, features.enableHardShadow, features.enableSoftShadow,
+                features.enableNormalInterp, features.enableTextureMapping, features.enableAccelStructure);
+            std::printf("extra bits 0x%x\n", featureBits(features) >> 16);
+            std::printf("render ray_depth %d segment_light_samples %d parallelogram_light_samples %d rays_per_pixel_side %d bloom %g %g %d seed %u\n",
+                rayDepth, segmentLightSamples, parallelogramLightDirectionSamples, raysPerPixelSide, bloomScalar, bloomThreshold,
+                bloomDebugOption, samplerSeed);
+            for (const CameraConfig& c : cameras)
+                std::printf("camera fov %g dist %g look_at %g %g %g rotation %g %g %g\n", c.fieldOfView, c.distanceFromLookAt, c.lookAt.x,
+                    c.lookAt.y, c.lookAt.z, c.rotation.x, c.rotation.y, c.rotation.z);
+            if (const Value* lights = cfg.find("lights"); lights && lights->kind == Value::Array)
+                for (const Value& l : lights->arr)
+                    std::printf("light %s\n", getString(l, { "type" }, "none").c_str());
+            return 0;
+        }
 
         // ---- src/main.cpp:478-535 -----------------------------------------------------------------------------------------
         Scene scene = loadFlatScene(joinPath(dataPath, sceneName));
