@@ -123,3 +123,18 @@ def test_aa_wavefront_equals_per_thread_kernel(cge, monkeypatch):
         for k in range(3):
             sc.render(cfg, traversal=1, rgb_out=rgb_p, want_ids=False, part=(k, 3))
         assert rgb_p.tobytes() == rgb_t.tobytes()
+
+
+def test_aa_ten_by_ten_in_the_wavefront(cge):
+    """The GUI maximum (10 x 10 camera rays per pixel = 200 of the 227 usable MT19937 outputs) through the wavefront pipeline."""
+    cfg = cge.configs.get("c3_teapot_soft", 64, 36)
+    cfg["features"] |= extras_cases.AA
+    cfg.update(rays_per_pixel_side=10, seed=4)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        rgb_t, _, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_PER_THREAD)
+        rgb_w, _, st_w = sc.render(cfg, traversal=1)
+        rgb_r, _, _ = sc.render(cfg, traversal=0)
+    assert st_w["stage_ms"][1] > 0 and st_w["primary_rays"] == 100 * 64 * 36
+    assert rgb_w.tobytes() == rgb_t.tobytes()
+    err, nan_mm = compare_images(rgb_w, rgb_r)
+    assert nan_mm == 0 and err <= RGB_TOL

@@ -378,3 +378,25 @@ def test_concurrent_bands_change_no_bit(cge, name, monkeypatch):
             assert rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1) and rgba.tobytes() == rgba1.tobytes()
             for k in ("primary_rays", "bounce_rays", "shadow_rays", "reference_rays", "reference_shadow_rays"):
                 assert st[k] == st1[k], k
+
+
+def test_degenerate_geometry(cge):
+    """Zero-area triangles and a NaN vertex: such primitives can never be hit; the scene must still build (a NaN coordinate
+    sends the fast tree to the host builder, csrc/bvh_sah_gpu.cu sah_gpu_supported) and FAST must equal the literal traversal."""
+    cfg = cge.configs.get("c1_cornell", 96, 96)
+    flat = cge.load_scene(cfg)
+    tri = cge.scenefile.load(cge.configs.SCENE_DIR / "triangle.cges")
+    tri.vertices["position"][:] = tri.vertices["position"][0]   # all three vertices coincide: zero area
+    flat.append_meshes(tri)
+    bad = cge.scenefile.load(cge.configs.SCENE_DIR / "triangle.cges")
+    bad.vertices["position"][1, 0] = np.nan
+    flat.append_meshes(bad, scale=0.1)
+    with cge.Scene(flat) as sc:
+        rgb_f, ids_f, st_f = sc.render(cfg, traversal=1)
+        rgb_r, ids_r, st_r = sc.render(cfg, traversal=0)
+    with cge.Scene(cge.load_scene(cfg)) as sc:
+        rgb_0, ids_0, _ = sc.render(cfg, traversal=1)
+    assert np.array_equal(ids_f, ids_r) and np.array_equal(ids_f, ids_0)  # the added primitives are never hit
+    assert rgb_f.tobytes() == rgb_0.tobytes()
+    err, nan_mm = compare_images(rgb_f, rgb_r)
+    assert nan_mm == 0 and err <= RGB_TOL
