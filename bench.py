@@ -390,14 +390,14 @@ def main():
         pipeline_ms, chain_ms, vis_ms, shade_ms, fold_ms = [float(x) for x in kms]
         shadow_ref_rays = float(cnt[5])
         algo_bytes = shadow_ref_rays / world * bytes_per_ray
-        stage_names = ["wf_chain_kernel", "wf_vis_grouped_kernel", "wf_shade_kernel", "wf_fold_kernel"]
+        stage_names = ["wf_chain_kernel", "wf_vis_regroup_kernel", "wf_shade_kernel", "wf_fold_kernel"]
         stage_vals = [chain_ms, vis_ms, shade_ms, fold_ms]
         dom = int(np.argmax(stage_vals))
         dom_name, dom_ms = stage_names[dom], stage_vals[dom]
         if dom_ms <= 0:  # point-light frame: the single per-thread kernel traces every ray of the frame
             dom_name, dom_ms = "render_kernel", pipeline_ms
             algo_bytes = ref_rays / world * bytes_per_ray + 12.0 * W * H / world
-        # the dominant kernel traces the shadow rays (wf_vis_grouped_kernel, or wf_shade_kernel for point-light scenes)
+        # the dominant kernel traces the shadow rays (wf_vis_regroup_kernel<8> on this workload)
         traffic = None
         warp_inst = None
         tf = ROOT / "profiles" / "traffic.json"
@@ -422,7 +422,7 @@ def main():
                         "achieved_ginst_s": warp_inst / (dom_ms * 1e-3) / 1e9,
                         "peak_ginst_s": 148 * 4 * float(clocks["sm_mhz"]) * 1e6 / 1e9,
                         "frac": warp_inst / (dom_ms * 1e-3) / (148 * 4 * float(clocks["sm_mhz"]) * 1e6),
-                        "source": "smsp__inst_executed.sum from profiles/r02_wf_vis_grouped_c5.txt (via profiles/traffic.json)"},
+                        "source": "smsp__inst_executed.sum from profiles/r02_wf_vis_regroup_c5.txt (via profiles/traffic.json)"},
                     "measured_on": f"{args.steps} steps of the same frame as ONE pipeline (CGE_BANDS=1, {single_ms:.3f} ms per step): the "
                                    "timed `value` steps run the frame as concurrent bands whose stage boundaries overlap",
                     "stage_ms": {**dict(zip(stage_names, stage_vals)), "pipeline": pipeline_ms},

@@ -719,7 +719,19 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         if (err == cudaSuccess && grouped) {
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_vis_grouped_kernel<CGE_GROUP>, 128, 0);
             if (err == cudaSuccess) {
-                wf_vis_grouped_kernel<CGE_GROUP><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                if (env_int("CGE_REGROUP", 1)) {
+                    // the default: lanes trade hits between the samples (wf_vis_regroup_kernel), 4 or 8 samples per lane decided on
+                    // the device from the queue lengths; CGE_REGROUP=0 runs the plain wf_vis_grouped_kernel (A/B)
+                    int perSm4 = 0, perSm8 = 0;
+                    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm4, wf_vis_regroup_kernel<4>, 128, 0);
+                    if (err == cudaSuccess)
+                        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm8, wf_vis_regroup_kernel<8>, 128, 0);
+                    wf_vis_regroup_kernel<4><<<unsigned(sc->sm_count * std::max(perSm4, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                    wf_vis_regroup_kernel<8><<<unsigned(sc->sm_count * std::max(perSm8, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                    *launches += 1;
+                } else {
+                    wf_vis_grouped_kernel<CGE_GROUP><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                }
                 err = cudaGetLastError();
                 *launches += 1;
             }

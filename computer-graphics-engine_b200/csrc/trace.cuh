@@ -302,7 +302,9 @@ __device__ __forceinline__ void slab_box_q(const SlabRayQ& r, unsigned wx, unsig
 // Shadow rays (src/light.cpp:60-72: closest hit with ray.t = 1 used as a boolean): is ANY triangle accepted with 0 <= t <= 1?
 // Lean specialisation of trace_fast<true>: the bound is the constant 1, so the stack needs no entry distances and no
 // re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris) or -1.
-__device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, const vec3 d)
+// kCountVisits: *visits receives the number of inner nodes the ray visited (wf_vis_regroup_kernel ranks a warp's hits by it)
+template <bool kCountVisits = false>
+__device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
 {
     if (s.n_prims == 0)
         return -1;
@@ -317,6 +319,8 @@ __device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, con
     unsigned cur = s.froot;
     while (cur != kDone) {
         while (cur < kDone) {
+            if (kCountVisits)
+                (*visits)++;
             float entL, extL, entR, extR;
 #if CGE_QNODES
             const uint4* nd = s.qnodes + size_t(cur) * 2;

@@ -695,6 +695,140 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_grouped_kernel(DevSc
     flush_counters(cnt, gcnt);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// wf_vis_regroup_kernel: the same work items as wf_vis_grouped_kernel (32 neighbouring hits x kGroup consecutive samples), but
+// the lanes of a warp trade hits between the samples.  A lane's kGroup rays are all long or all short (they start at the same
+// point and end on the same small light), so in wf_vis_grouped_kernel every one of the kGroup steps of a warp lasts as long
+// as the warp's longest hit.  Here step 0 is the same (every lane traces the first sample of its own hit, counting the nodes
+// visited); then the 32 hits are ranked by that count and the remaining 32 x (kGroup - 1) rays are dealt out rank by rank:
+// the second step gets all remaining samples of the longest third of the hits, the last step those of the shortest third.
+// The hits are still the same 32 neighbouring pixels (the coherence of the node fetches is untouched), a hit's data travel
+// between lanes by shuffle, every ray is traced exactly once with the same arithmetic into the same visibility byte.
+// ---------------------------------------------------------------------------------------------------------------------
+struct RegroupHit {
+    unsigned k, e, path, g, pixel, ctrBase, cnt;
+    vec3 o;
+    ShadeFrame f;
+    int occluder;
+    unsigned valid;
+};
+__device__ __forceinline__ RegroupHit regroup_fetch(const RegroupHit& h, unsigned src)
+{
+    const unsigned full = 0xffffffffu;
+    RegroupHit r;
+    r.k = __shfl_sync(full, h.k, src), r.e = __shfl_sync(full, h.e, src), r.path = __shfl_sync(full, h.path, src);
+    r.g = __shfl_sync(full, h.g, src), r.pixel = __shfl_sync(full, h.pixel, src), r.ctrBase = __shfl_sync(full, h.ctrBase, src);
+    r.cnt = __shfl_sync(full, h.cnt, src);
+    r.o = v3(__shfl_sync(full, h.o.x, src), __shfl_sync(full, h.o.y, src), __shfl_sync(full, h.o.z, src));
+    r.f.n = v3(__shfl_sync(full, h.f.n.x, src), __shfl_sync(full, h.f.n.y, src), __shfl_sync(full, h.f.n.z, src));
+    r.f.p = v3(__shfl_sync(full, h.f.p.x, src), __shfl_sync(full, h.f.p.y, src), __shfl_sync(full, h.f.p.z, src));
+    r.occluder = __shfl_sync(full, h.occluder, src);
+    r.valid = __shfl_sync(full, h.valid, src);
+    return r;
+}
+
+// Samples per lane of the launch: 8 when it has many direct-lighting evaluations (one unranked step in eight instead of one in
+// four: C5 shadow pass 13.11 -> 12.58 ms), 4 when it is small (the coarser items leave a tail: a 1/8 share of C5 1.95 -> 2.47 ms,
+// C3 0.80 -> 0.89 ms with 8).  Both instantiations are launched; the one not selected returns at once (the queue lengths only
+// exist on the device).
+constexpr unsigned kRegroupWideUnits = 1250000u; // 20 M shadow rays with 16 samples per evaluation
+__device__ __forceinline__ unsigned wf_regroup_samples_per_lane(const DevParams& p, const WaveBuffers& wb)
+{
+    unsigned long long units = 0;
+    for (unsigned k = 0; k < p.levels; k++)
+        units += (unsigned long long)wb.counts[k] * (p.draws_per_hit == 0 ? 1u : (1u << k));
+    return units >= kRegroupWideUnits && p.samples_per_hit >= 8 ? 8u : 4u;
+}
+
+template <unsigned kGroup>
+__global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
+{
+    __shared__ unsigned char laneOfRank[4][32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool fold = p.draws_per_hit == 0;
+    const unsigned S = p.samples_per_hit;
+    const unsigned groups = (S + kGroup - 1) / kGroup;
+    unsigned cum[kMaxLevels + 1]; // in units (direct-lighting evaluations)
+    cum[0] = 0;
+    for (unsigned k = 0; k < p.levels; k++)
+        cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
+    const unsigned long long total = (unsigned long long)cum[p.levels] * groups;
+    unsigned long long nshadow = 0;
+    if (!wf_use_visibility_bytes(p, wb) || wf_regroup_samples_per_lane(p, wb) != kGroup)
+        return;
+    // one shadow ray of hit h, sample sg; visits (optional) counts the nodes it walked; updates h.occluder
+    auto trace_sample = [&](RegroupHit& h, unsigned sg, unsigned* visits) {
+        const LightSample ls = wf_sample(s, p, sg, h.pixel, h.ctrBase);
+        unsigned char v = 1;
+        if (ls.shadowed && !shading_is_zero(s, h.f, ls.pos)) {
+            nshadow++;
+            const vec3 d = ls.pos - h.o;
+            float t;
+            float4 r5;
+            if (h.occluder >= 0 && triangle_rows_hit(s.ftris + size_t(h.occluder) * kTriRows, h.o, d, 1.0f, t, r5)) {
+                v = 0;
+            } else {
+                const int blocker = visits ? trace_shadow<true>(s, h.o, d, visits) : trace_shadow(s, h.o, d);
+                if (blocker >= 0) {
+                    v = 0;
+                    h.occluder = blocker;
+                }
+            }
+        }
+        wb.vis[size_t(cum[h.k]) * S + size_t(h.path) * S * h.cnt + h.e + size_t(sg) * h.cnt] = v;
+    };
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0)
+            chunk = atomicAdd(wb.counts + 18, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const unsigned long long first = (unsigned long long)chunk * 32ull;
+        if (first >= total)
+            break;
+        const unsigned long long item = first + lane;
+        RegroupHit own {};
+        own.occluder = -1;
+        own.valid = item < total ? 1u : 0u;
+        unsigned visits = 0;
+        if (own.valid) {
+            unsigned k = 0;
+            while (item >= (unsigned long long)cum[k + 1] * groups)
+                k++;
+            const unsigned inLevel = unsigned(item - (unsigned long long)cum[k] * groups), cnt = wb.counts[k];
+            const unsigned block = inLevel / cnt;
+            own.k = k, own.cnt = cnt, own.e = inLevel - block * cnt;
+            own.path = block / groups, own.g = block - own.path * groups;
+            const uint2 m = wb.meta[size_t(k) * wb.cap + own.e];
+            own.pixel = wf_pixel(m);
+            own.ctrBase = wf_unit_ctr(p, k, own.path, m);
+            const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + own.e;
+            own.o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
+            if (s.cull_zero_shading)
+                own.f = wf_load_frame(wb, k, own.e);
+            trace_sample(own, own.g * kGroup, &visits); // step 0: the hit's first sample of this group (always < S)
+        }
+        // rank the hits by the length of that ray, longest first (ties by lane, so the ranks are a permutation)
+        const unsigned key = visits * 32u + (31u - lane);
+        unsigned rank = 0;
+        for (unsigned l = 0; l < 32; l++)
+            rank += __shfl_sync(0xffffffffu, key, l) > key ? 1u : 0u;
+        __syncwarp();
+        laneOfRank[warp][rank] = (unsigned char)lane;
+        __syncwarp();
+        for (unsigned step = 1; step < kGroup; step++) {
+            const unsigned w = (step - 1u) * 32u + lane; // the w-th remaining ray in rank order
+            const unsigned src = laneOfRank[warp][w / (kGroup - 1u)];
+            RegroupHit h = regroup_fetch(own, src);
+            const unsigned sg = h.g * kGroup + 1u + w % (kGroup - 1u);
+            if (h.valid && sg < S)
+                trace_sample(h, sg, nullptr);
+        }
+    }
+    Counters cnt {};
+    cnt.shadow = nshadow;
+    flush_counters(cnt, gcnt);
+}
+
 template <bool kLookup>
 __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
 {
