@@ -230,6 +230,14 @@ typedef struct cge_stats {
 
 typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene + BVH on ONE GPU */
 
+/* ---- development switches (environment variables read at call time; A/B measurements and tests only, not part of the ABI:
+ *      every setting produces the same frame bit for bit) -----------------------------------------------------------------
+ *   CGE_ZERO_SHADING_CULL=0   trace the shadow ray of light samples whose Phong term is exactly zero as well
+ *   CGE_BANDS=n               number of concurrent bands a frame / rank partition is rendered in (1 = one pipeline)
+ *   CGE_REGROUP=0             shadow pass without the in-warp regrouping (wf_vis_grouped_kernel)
+ *   CGE_SAH_BUILD=host        build the FAST traversal tree with the host builder instead of the GPU builder
+ *   CGE_TIMING=1              print the GPU tree builder's phases on stderr */
+
 /* ---- entry points ------------------------------------------------------------------------------------- */
 
 int cge_abi_version(void);
