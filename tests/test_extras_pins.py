@@ -86,3 +86,27 @@ def test_extras_validation_needs_no_gpu():
         pkg.ray_sample_positions(8, 8, 0, 0, 11, 0)
     with pytest.raises(pkg.CgeError):
         pkg.ray_sample_positions(8, 8, 8, 0, 2, 0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_oracle_restatement_equals_live_reference_on_random_extras(ref, seed):
+    """Random combinations of the two extra features, their globals, depth and frame size: the restatement must equal the
+    unmodified reference bit for bit (same libm, same arithmetic order, same hash-seeded generator)."""
+    if not oracleport.available():
+        pytest.skip("oracle/liboracle.so not built")
+    rng = np.random.default_rng(seed)
+    C = pkg.configs
+    name = ["c1_cornell", "c2_cube_textured", "c3_teapot_soft", "c4_monkey_mirror"][int(rng.integers(4))]
+    w, h = int(rng.integers(17, 49)), int(rng.integers(9, 33))
+    cfg = C.get(name, w, h)
+    extra = [extras_cases.AA, extras_cases.BLOOM, extras_cases.AA | extras_cases.BLOOM][int(rng.integers(3))]
+    cfg["features"] |= extra
+    cfg.update(rays_per_pixel_side=int(rng.integers(1, 5)), bloom_scalar=float(rng.uniform(0.05, 0.9)),
+               bloom_threshold=float(rng.uniform(0.0, 0.8)), bloom_debug_option=int(rng.integers(3)),
+               ray_depth=int(rng.integers(0, 4)), seed=int(rng.integers(1 << 30)))
+    path = C.scene_path(cfg)
+    with ref.RefScene(path, cfg["features"]) as rs:
+        want, _, _ = rs.render(cfg, want_ids=False)
+    with oracleport.OracleScene(path, cfg["features"]) as sc:
+        got, _, _ = sc.render(cfg, want_ids=False)
+    assert got.tobytes() == want.tobytes(), (name, w, h, hex(extra), cfg["rays_per_pixel_side"], cfg["bloom_debug_option"])
