@@ -83,7 +83,7 @@ class CgeStats(C.Structure):
 ABI_SYMBOLS = [
     "cge_abi_version", "cge_last_error", "cge_device_count", "cge_camera_from_trackball", "cge_scene_create",
     "cge_scene_update_lights", "cge_scene_destroy", "cge_scene_bvh_info", "cge_scene_bvh_export", "cge_render",
-    "cge_bvh_build_reference_order", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
+    "cge_bvh_build_reference_order", "cge_bvh_validate", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
     "cge_comm_destroy", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
         l.cge_scene_bvh_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
         l.cge_scene_bvh_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.cge_bvh_build_reference_order.argtypes = [C.POINTER(CgeSceneDesc), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] + [C.POINTER(C.c_uint32)] * 3
+        l.cge_bvh_validate.argtypes = [C.POINTER(CgeSceneDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         l.cge_camera_from_trackball.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                                 C.POINTER(CgeCamera)]
         l.cge_fast_bvh_build.argtypes = [C.POINTER(CgeSceneDesc), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] \
@@ -234,6 +235,18 @@ def build_reference_bvh_host(flat: FlatScene):
     _check(lib().cge_bvh_build_reference_order(C.byref(d), _p(nodes), C.byref(n), _p(order) if n_prims else None, C.byref(root),
                                                C.byref(levels), C.byref(leaves)))
     return nodes[: n.value], order, root.value, levels.value, leaves.value
+
+
+def validate_bvh(flat: FlatScene, nodes: np.ndarray, order: np.ndarray, root: int):
+    """Host-only: the check cge_scene_create applies to a caller-supplied tree.  Returns (levels, leaves); raises CgeError."""
+    d, keep = scene_desc(flat)
+    nodes = np.ascontiguousarray(nodes, scenefile.BVH_NODE_DT)
+    order = np.ascontiguousarray(order, "<u4")
+    d.n_bvh_nodes, d.bvh_root = len(nodes), root
+    d.bvh_nodes, d.bvh_prim_order = nodes.ctypes.data if len(nodes) else None, order.ctypes.data if len(order) else None
+    levels, leaves = C.c_uint32(), C.c_uint32()
+    _check(lib().cge_bvh_validate(C.byref(d), C.byref(levels), C.byref(leaves)))
+    return levels.value, leaves.value
 
 
 FAST_NODE_DT = np.dtype([("left_lower", "<f4", (3,)), ("left_upper", "<f4", (3,)), ("right_lower", "<f4", (3,)),

@@ -150,20 +150,40 @@ bool adopt_bvh(const cge_scene_desc& d, HostBvh& out)
             return false;
         seen[out.prim_order[i]] = 1;
     }
-    uint64_t covered = 0;
-    for (const auto& n : out.nodes) {
+    // Walk the tree from the root (iteratively: the input is untrusted).  Every node may be reached at most once (no cycles, no
+    // shared subtrees, hence at most n_bvh_nodes visits), the children of an inner node must split its primitive range exactly
+    // ([beg, mid) left, [mid, end) right - the reference's createBVH, src/bounding_volume_hierarchy.cpp:138-146), the root must
+    // cover [0, n_prims): the leaves reachable from the root then tile [0, n_prims) without overlap.  The depth that sizes the
+    // device traversal stack is the one measured here, not the (untrusted) depth field.
+    const auto& root = out.nodes[out.root];
+    if (root.beg != 0 || root.end != n_prims)
+        return false;
+    std::vector<uint8_t> visited(out.nodes.size(), 0);
+    std::vector<std::pair<uint32_t, uint32_t>> todo { { out.root, 0u } }; // (node, true depth)
+    while (!todo.empty()) {
+        const auto [ni, depth] = todo.back();
+        todo.pop_back();
+        if (visited[ni])
+            return false;
+        visited[ni] = 1;
+        const auto& n = out.nodes[ni];
         if (n.beg >= n.end || n.end > n_prims)
             return false;
-        out.n_levels = std::max(out.n_levels, n.depth + 1);
+        out.n_levels = std::max(out.n_levels, depth + 1);
         if (n.is_leaf) {
             out.n_leaves++;
             out.max_leaf_prims = std::max(out.max_leaf_prims, n.end - n.beg);
-            covered += n.end - n.beg;
-        } else if (n.left >= d.n_bvh_nodes || n.right >= d.n_bvh_nodes) {
-            return false;
+            continue;
         }
+        if (n.left >= d.n_bvh_nodes || n.right >= d.n_bvh_nodes || n.left == n.right)
+            return false;
+        const auto &l = out.nodes[n.left], &r = out.nodes[n.right];
+        if (l.beg != n.beg || l.end != r.beg || r.end != n.end)
+            return false;
+        todo.push_back({ n.left, depth + 1 });
+        todo.push_back({ n.right, depth + 1 });
     }
-    return covered == n_prims;
+    return true;
 }
 
 } // namespace cge

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@
 #include "nccl_min.h"
 #include "render_kernels.cuh"
 #include "wavefront.cuh"
+#include "shadow_packet.cuh"
 
 #ifndef CGE_GROUP
 #define CGE_GROUP 4 // shadow rays per lane in wf_vis_grouped_kernel (A/B in DESIGN.md 5.3)
@@ -100,6 +102,22 @@ struct Scratch {
 };
 } // namespace
 
+// One immutable version of the scene's light list.  A render takes a reference (shared_ptr) under the scene lock when it starts
+// and keeps it until its stream has drained, so cge_scene_update_lights never overwrites or frees a buffer a frame in flight
+// reads: it fills a version nobody holds (or a new one) and swaps it in.
+struct LightSet {
+    std::vector<cge_light_desc> host;
+    float* dev = nullptr;
+    size_t capFloats = 0;
+    uint32_t n = 0;
+    ~LightSet()
+    {
+        if (dev)
+            cudaFree(dev);
+    }
+};
+using LightsRef = std::shared_ptr<const LightSet>;
+
 struct cge_scene {
     int device = 0;
     int sm_count = 0;
@@ -110,13 +128,15 @@ struct cge_scene {
     bool fast_built_on_gpu = false;
     float fast_build_ms = 0.0f; // device time of the GPU SAH build
     DevBuf<int4> textures;
-    DevBuf<float> texels, lights;
+    DevBuf<float> texels;
+    std::shared_ptr<LightSet> lights;                   // the current version (guarded by mu)
+    std::vector<std::shared_ptr<LightSet>> light_pool; // every version allocated so far; one with use_count() == 1 is free
+    cudaStream_t light_stream = nullptr;
     HostBvh bvh;
     uint32_t n_triangles = 0, n_spheres = 0;
     uint32_t accel_root_ref = 0, accel_root_count = 0;
     bool any_transparent = false;
     bool colours_bounded = true; // every kd / ks / texel is finite and <= kColourBound in magnitude (zero-shading cull)
-    std::vector<cge_light_desc> host_lights;
     std::mutex mu;
     std::vector<Scratch*> pool;
 };
@@ -275,7 +295,42 @@ int validate_params(const cge_scene* sc, const cge_params* p)
     return CGE_OK;
 }
 
-DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
+LightsRef lights_of(cge_scene* sc)
+{
+    std::lock_guard<std::mutex> lk(sc->mu);
+    return sc->lights;
+}
+
+// Install a new light list: reuse a version no render holds, or allocate one; the upload has completed when this returns.
+int set_lights(cge_scene* sc, const cge_light_desc* lights, uint32_t n)
+{
+    const std::vector<float> packed = pack_lights(lights, n);
+    std::lock_guard<std::mutex> lk(sc->mu);
+    std::shared_ptr<LightSet> ls;
+    for (auto& c : sc->light_pool)
+        if (c.use_count() == 1 && c->capFloats >= packed.size()) {
+            ls = c;
+            break;
+        }
+    if (!ls) {
+        ls = std::make_shared<LightSet>();
+        ls->capFloats = std::max<size_t>(packed.size(), 4 * kLightFloats);
+        CGE_CUDA(cudaMalloc(&ls->dev, ls->capFloats * sizeof(float)));
+        sc->light_pool.push_back(ls);
+    }
+    if (!sc->light_stream)
+        CGE_CUDA(cudaStreamCreateWithFlags(&sc->light_stream, cudaStreamNonBlocking));
+    if (!packed.empty()) {
+        CGE_CUDA(cudaMemcpyAsync(ls->dev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, sc->light_stream));
+        CGE_CUDA(cudaStreamSynchronize(sc->light_stream));
+    }
+    ls->host.assign(lights, lights + n);
+    ls->n = n;
+    sc->lights = ls;
+    return CGE_OK;
+}
+
+DevParams make_dev_params(const cge_scene* sc, const cge_params& p, const LightSet& ls)
 {
     DevParams d {};
     d.width = p.width;
@@ -288,7 +343,7 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p)
     d.segment_recip = exact_recip(p.segment_samples);
     d.parallelogram_recip = exact_recip(p.parallelogram_samples);
     d.seed = p.seed;
-    host_light_counts(sc->host_lights, p, d.draws_per_hit, d.shadow_rays_per_hit, d.samples_per_hit);
+    host_light_counts(ls.host, p, d.draws_per_hit, d.shadow_rays_per_hit, d.samples_per_hit);
     d.levels = (p.features & CGE_FEAT_RECURSIVE) ? uint32_t(p.ray_depth) + 1u : 1u;
     d.units_per_lane = d.draws_per_hit == 0 ? d.levels : ((1u << d.levels) - 1u);
     d.debug_cycles = (p.flags & CGE_FLAG_DEBUG_CYCLES) ? 1u : 0u;
@@ -375,10 +430,12 @@ int env_int(const char* name, int fallback)
     return v && *v ? std::atoi(v) : fallback;
 }
 
-DevScene scene_for(const cge_scene* sc, const cge_params& p)
+DevScene scene_for(const cge_scene* sc, const cge_params& p, const LightSet& ls)
 {
     DevScene d = sc->dev;
-    d.cull_zero_shading = sc->colours_bounded && light_colours_bounded(sc->host_lights) && env_int("CGE_ZERO_SHADING_CULL", 1);
+    d.lights = ls.dev;
+    d.n_lights = ls.n;
+    d.cull_zero_shading = sc->colours_bounded && light_colours_bounded(ls.host) && env_int("CGE_ZERO_SHADING_CULL", 1);
     if (p.features & CGE_FEAT_ACCEL_STRUCTURE) {
         d.root_ref = sc->accel_root_ref;
         d.root_count = sc->accel_root_count;
@@ -603,10 +660,10 @@ __global__ void unpack_tiles_kernel(const float* __restrict__ inRgb, const int* 
     }
 }
 
-int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_params* p, const DevParams& dp, float* rgbDev,
-    int* idsDev, uint32_t* launches)
+int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camera* cam, const cge_params* p, const DevParams& dp,
+    float* rgbDev, int* idsDev, uint32_t* launches)
 {
-    const DevScene ds = scene_for(sc, *p);
+    const DevScene ds = scene_for(sc, *p, ls);
     DevCamera dc { cam->origin[0], cam->origin[1], cam->origin[2], cam->quat[0], cam->quat[1], cam->quat[2], cam->quat[3],
         cam->half_width, cam->half_height };
     CGE_CUDA(cudaMemsetAsync(s->tileCounter, 0, 64, s->stream));
@@ -652,6 +709,9 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         // device: both variants are launched and each kernel returns at once unless it is the selected one (no host sync).
         const bool visFits = dp.samples_per_hit >= 1 && ws.vis < (size_t(1) << 32);
         DevParams wp = dp;
+        wp.packet_fat = float(env_int("CGE_PACKET_FAT_PCT", 100)) * 0.01f;
+        wp.packet_budget = uint32_t(env_int("CGE_PACKET_BUDGET", 48));
+        wp.packet_leaf_cost = uint32_t(env_int("CGE_PACKET_LEAF_COST", 4));
         wp.grouped_below_chunks = uint32_t(size_t(sc->sm_count) * 32 * kGroupedThreshold);
         if ((p->flags & CGE_FLAG_DECOUPLED_SHADE) && visFits)
             wp.shade_mode = 3;
@@ -718,7 +778,24 @@ int launch_render(cge_scene* sc, Scratch* s, const cge_camera* cam, const cge_pa
         }
         if (err == cudaSuccess && grouped) {
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_vis_grouped_kernel<CGE_GROUP>, 128, 0);
-            if (err == cudaSuccess) {
+            const int packet = env_int("CGE_PACKET", 0); // opt-in: measured slower than the per-ray pass
+            if (err == cudaSuccess && packet > 0) {
+                // one tree walk per lane for a packet of light samples (shadow_packet.cuh)
+                auto go = [&](auto kern) {
+                    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
+                    if (err == cudaSuccess) {
+                        kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                        err = cudaGetLastError();
+                    }
+                };
+                if (packet >= 16)
+                    go(wf_vis_packet_kernel<16>);
+                else if (packet >= 8)
+                    go(wf_vis_packet_kernel<8>);
+                else
+                    go(wf_vis_packet_kernel<4>);
+                *launches += 1;
+            } else if (err == cudaSuccess) {
                 if (env_int("CGE_REGROUP", 1)) {
                     // the default: lanes trade hits between the samples (wf_vis_regroup_kernel), 4 or 8 samples per lane decided on
                     // the device from the queue lengths; CGE_REGROUP=0 runs the plain wf_vis_grouped_kernel (A/B)
@@ -818,11 +895,11 @@ int apply_bloom(Scratch* s, const cge_params& p, float* frame, uint32_t* launche
 // B200 (tools/sweep_bands.py): the wavefront pipeline gains from ~1 Mpixel up (its stages have long tails), the
 // single per-thread kernel only through the overlapped copy of a host-output frame; small launches are launch-latency bound
 // and stay in one piece.
-unsigned nBandsFor(const cge_scene* sc, const cge_params& p, const DevParams& dp, bool hostCopy)
+unsigned nBandsFor(const cge_scene* sc, const LightSet& ls, const cge_params& p, const DevParams& dp, bool hostCopy)
 {
     const size_t pixels = size_t(dp.tile_count) * 32;
     unsigned n = 1;
-    const bool wave = choose_variant(scene_for(sc, p), p, dp).wave;
+    const bool wave = choose_variant(scene_for(sc, p, ls), p, dp).wave;
     if (wave)
         n = pixels >= (size_t(3) << 20) ? 4 : pixels >= (size_t(3) << 19) ? 2 : 1; // a 1 Mpixel share (C5 on 8 GPUs) is faster in one piece
     else if (hostCopy)
@@ -869,7 +946,7 @@ int acquire_bands(cge_scene* sc, Scratch* primary, unsigned nBands, std::vector<
 // otherwise all bands share the top priority, which hides the tails best.  On return the primary stream has waited for the
 // kernels of every band; ev0 must already be recorded on it.
 template <typename After>
-int launch_bands(cge_scene* sc, const std::vector<Scratch*>& bands, const std::vector<uint2>& ranges, bool staggered, const cge_camera* cam,
+int launch_bands(cge_scene* sc, const LightSet& ls, const std::vector<Scratch*>& bands, const std::vector<uint2>& ranges, bool staggered, const cge_camera* cam,
     const cge_params* p, const DevParams& dp, float* rgbDev, int* idsDev, uint32_t* launches, After&& after)
 {
     Scratch* s = bands[0];
@@ -884,7 +961,7 @@ int launch_bands(cge_scene* sc, const std::vector<Scratch*>& bands, const std::v
         DevParams bp = dp;
         bp.tile_first = ranges[b].x;
         bp.tile_count = ranges[b].y;
-        const int rc = launch_render(sc, sb, cam, p, bp, rgbDev, idsDev, launches);
+        const int rc = launch_render(sc, ls, sb, cam, p, bp, rgbDev, idsDev, launches);
         if (rc != CGE_OK)
             return rc;
         after(b, sb);
@@ -1136,7 +1213,8 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
             q[0] = f4(n.l_lo[0], n.l_lo[1], n.l_lo[2], n.l_hi[0]);
             q[1] = f4(n.l_hi[1], n.l_hi[2], n.r_lo[0], n.r_lo[1]);
             q[2] = f4(n.r_lo[2], n.r_hi[0], n.r_hi[1], n.r_hi[2]);
-            q[3] = f4(bitsf(n.left), bitsf(n.right), 0.0f, 0.0f);
+            auto extent = [](const float* lo, const float* hi) { return std::max({ hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2] }); };
+            q[3] = f4(bitsf(n.left), bitsf(n.right), extent(n.l_lo, n.l_hi), extent(n.r_lo, n.r_hi));
         }
     }
 
@@ -1211,9 +1289,6 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     sc->colours_bounded = bounded(texels.data(), texels.size());
     for (size_t m = 0; m < mats.size(); m += 3) // kd.xyz and ks.xyz (shininess and transparency are not colours)
         sc->colours_bounded = sc->colours_bounded && bounded(&mats[m].x, 3) && bounded(&mats[m + 1].x, 3);
-    sc->host_lights.assign(d->lights, d->lights + d->n_lights);
-    std::vector<float> lights = pack_lights(d->lights, d->n_lights);
-
     cudaError_t e = cudaSuccess;
     auto up = [&](auto& buf, const auto& host) {
         if (e == cudaSuccess)
@@ -1228,7 +1303,6 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     up(sc->materials, mats);
     up(sc->textures, texs);
     up(sc->texels, texels);
-    up(sc->lights, lights);
     if (e != cudaSuccess) {
         std::string msg = std::string("scene upload: ") + cudaGetErrorString(e);
         cge_scene_destroy(sc);
@@ -1248,10 +1322,16 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     sc->dev.materials = sc->materials.p;
     sc->dev.textures = sc->textures.p;
     sc->dev.texels = sc->texels.p;
-    sc->dev.lights = sc->lights.p;
-    sc->dev.n_lights = d->n_lights;
+    sc->dev.lights = nullptr; // per frame: scene_for() fills in the light-list version the frame holds
+    sc->dev.n_lights = 0;
     sc->dev.n_prims = nPrims;
     sc->dev.has_spheres = d->n_spheres ? 1u : 0u;
+    const int lrc = set_lights(sc, d->lights, d->n_lights);
+    if (lrc != CGE_OK) {
+        const std::string msg = g_err;
+        cge_scene_destroy(sc);
+        return fail(lrc, msg);
+    }
     *out = sc;
     return CGE_OK;
 }
@@ -1264,18 +1344,8 @@ int cge_scene_update_lights(cge_scene* sc, const cge_light_desc* lights, uint32_
         if (lights[l].type > CGE_LIGHT_PARALLELOGRAM)
             return fail(CGE_ERR_INVALID_ARG, "bad light type");
     CGE_CUDA(cudaSetDevice(sc->device));
-    std::vector<float> packed = pack_lights(lights, n);
-    std::lock_guard<std::mutex> lk(sc->mu);
-    if (n * size_t(kLightFloats) <= sc->lights.n && n > 0) {
-        CGE_CUDA(cudaMemcpy(sc->lights.p, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
-    } else {
-        CGE_CUDA(cudaDeviceSynchronize());
-        CGE_CUDA(sc->lights.upload(packed));
-        sc->dev.lights = sc->lights.p;
-    }
-    sc->dev.n_lights = n;
-    sc->host_lights.assign(lights, lights + n);
-    return CGE_OK;
+    // never touches a buffer a frame in flight reads: set_lights fills a version no render holds and swaps it in
+    return set_lights(sc, lights, n);
 }
 
 int cge_scene_destroy(cge_scene* sc)
@@ -1330,7 +1400,10 @@ int cge_scene_destroy(cge_scene* sc)
     sc->materials.release();
     sc->textures.release();
     sc->texels.release();
-    sc->lights.release();
+    sc->lights.reset();
+    sc->light_pool.clear();
+    if (sc->light_stream)
+        cudaStreamDestroy(sc->light_stream);
     delete sc;
     return CGE_OK;
 }
@@ -1380,6 +1453,20 @@ int cge_bvh_build_reference_order(const cge_scene_desc* d, cge_bvh_node* nodesOu
 
 // Host evaluation of PixelSampler (shade.cuh): same generator (sampler.h), same fp32 operations in the same order; this TU is
 // compiled with -ffp-contract=off so the host compiler cannot fuse them either.
+int cge_bvh_validate(const cge_scene_desc* d, uint32_t* nLevelsOut, uint32_t* nLeavesOut)
+{
+    if (!d)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    HostBvh bvh;
+    if (!adopt_bvh(*d, bvh))
+        return fail(CGE_ERR_INVALID_ARG, "supplied BVH is inconsistent with the scene");
+    if (nLevelsOut)
+        *nLevelsOut = bvh.n_levels;
+    if (nLeavesOut)
+        *nLeavesOut = bvh.n_leaves;
+    return CGE_OK;
+}
+
 int cge_ray_sample_positions(int32_t W, int32_t H, int32_t x, int32_t y, int32_t n, uint32_t seed, float* ndcOut)
 {
     if (W <= 0 || H <= 0 || x < 0 || y < 0 || x >= W || y >= H || n < 1 || n > kCgeMaxRaysPerPixelSide || !ndcOut)
@@ -1485,13 +1572,19 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     CGE_CUDA(cudaSetDevice(sc->device));
     const size_t pixels = size_t(p->width) * size_t(p->height);
     Scratch* s = nullptr;
+    std::vector<float> partRgb; // a partition rendered to a host frame: its packed tiles (below)
+    std::vector<int> partIds;
+    const bool partToHost = p->part_count > 1 && !devOut;
+    const size_t partPixels = partToHost ? (size_t((p->width + kTileW - 1) / kTileW) * size_t((p->height + kTileH - 1) / kTileH) / p->part_count + 1) * 32 : 0;
     // rgba8: the float frame lives in the first 3/4 of a doubled scratch frame, the packed bytes in the ids buffer
-    rc = acquire_scratch(sc, devOut ? 1 : pixels, wantIds || rgba8, 0, &s);
+    rc = acquire_scratch(sc, devOut ? 1 : pixels, wantIds || rgba8, partPixels, &s);
     if (rc) {
         release_scratch(sc, s);
         return rc;
     }
-    const DevParams dp = make_dev_params(sc, *p);
+    const LightsRef lights = lights_of(sc); // this frame's version of the light list, held until the stream has drained
+    const LightSet& ls = *lights;
+    const DevParams dp = make_dev_params(sc, *p, ls);
     float* rgbDev = devOut ? rgbOut : s->rgb;
     int* idsDev = wantIds ? (devOut ? idsOut : s->ids) : nullptr;
     uint32_t launches = 0;
@@ -1500,7 +1593,7 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     // buffer with the packed pixels, and a partition (part_count > 1) is left to cge_render_distributed.
     unsigned nBands = 1;
     if (dp.part_count <= 1 && !(p->features & CGE_FEAT_BLOOM_EFFECT) && !(rgba8 && wantIds))
-        nBands = nBandsFor(sc, *p, dp, !devOut);
+        nBands = nBandsFor(sc, ls, *p, dp, !devOut);
     std::vector<Scratch*> bands;
     if (acquire_bands(sc, s, nBands, bands) != CGE_OK) { // no room for the helpers' queues: one pipeline is always possible
         cudaGetLastError();
@@ -1527,7 +1620,7 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
             first = size_t(p->height - yEnd) * size_t(p->width);
             count = size_t(yEnd - yBeg) * size_t(p->width);
         };
-        rc = launch_bands(sc, bands, ranges, !devOut, cam, p, dp, rgbDev, idsDev, &launches, [&](unsigned b, Scratch* sb) {
+        rc = launch_bands(sc, ls, bands, ranges, !devOut, cam, p, dp, rgbDev, idsDev, &launches, [&](unsigned b, Scratch* sb) {
             if (rgba8) {
                 size_t first, count;
                 span(b, first, count);
@@ -1557,7 +1650,7 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
         for (unsigned b = 1; b < bands.size(); b++)
             cudaStreamWaitEvent(s->stream, bands[b]->copyDone, 0);
     } else {
-        rc = launch_render(sc, s, cam, p, dp, rgbDev, idsDev, &launches);
+        rc = launch_render(sc, ls, s, cam, p, dp, rgbDev, idsDev, &launches);
         if (rc == CGE_OK && (p->features & CGE_FEAT_BLOOM_EFFECT))
             rc = apply_bloom(s, *p, rgbDev, &launches);
         cudaEventRecord(s->ev1, s->stream);
@@ -1577,18 +1670,17 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
             if (wantIds)
                 cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
         } else {
-            // partial frame: copy back only the rows of tiles this partition touched would need a gather;
-            // callers that partition (cge_render_distributed) use the packed path instead.  Here: full copy of the
-            // scratch frame is wrong for untouched pixels, so copy tile rows individually.
-            for (unsigned k = 0; k < dp.tile_count; k++) {
-                const unsigned tile = dp.part_index + k * dp.part_count;
-                const int x0 = int(tile % dp.n_tiles_x) * kTileW, y0 = int(tile / dp.n_tiles_x) * kTileH;
-                const int w = std::min(kTileW, p->width - x0);
-                for (int y = y0; y < std::min(y0 + kTileH, p->height); y++) {
-                    const size_t idx = size_t(p->height - 1 - y) * size_t(p->width) + size_t(x0);
-                    cudaMemcpyAsync(rgbOut + idx * 3, s->rgb + idx * 3, size_t(w) * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
-                    if (wantIds)
-                        cudaMemcpyAsync(idsOut + idx, s->ids + idx, size_t(w) * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+            // partial frame (one partition's tiles, the rest of rgb_out stays untouched): pack the tiles contiguously with the
+            // gather kernel of the multi-GPU path, ONE copy to the host, scattered into the frame below once the stream drained
+            if (dp.tile_count) {
+                pack_tiles_kernel<<<(dp.tile_count * 32 + 255) / 256, 256, 0, s->stream>>>(s->rgb, wantIds ? s->ids : nullptr, s->gatherRgb,
+                    wantIds ? s->gatherIds : nullptr, dp, dp.tile_count);
+                launches++;
+                partRgb.resize(size_t(dp.tile_count) * 32 * 3);
+                cudaMemcpyAsync(partRgb.data(), s->gatherRgb, partRgb.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+                if (wantIds) {
+                    partIds.resize(size_t(dp.tile_count) * 32);
+                    cudaMemcpyAsync(partIds.data(), s->gatherIds, partIds.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
                 }
             }
         }
@@ -1597,6 +1689,19 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (rc == CGE_OK && e != cudaSuccess)
         rc = fail(CGE_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    if (rc == CGE_OK && !partRgb.empty()) // packed tile k, pixel j (row-major inside the 8x4 tile) -> Screen layout
+        for (unsigned k = 0; k < dp.tile_count; k++) {
+            const unsigned tile = dp.part_index + k * dp.part_count;
+            const int x0 = int(tile % dp.n_tiles_x) * kTileW, y0 = int(tile / dp.n_tiles_x) * kTileH;
+            const int w = std::min(kTileW, p->width - x0);
+            for (int y = y0; y < std::min(y0 + kTileH, p->height); y++) {
+                const size_t idx = size_t(p->height - 1 - y) * size_t(p->width) + size_t(x0);
+                const size_t src = size_t(k) * 32 + size_t(y - y0) * kTileW;
+                std::memcpy(rgbOut + idx * 3, partRgb.data() + src * 3, size_t(w) * 3 * sizeof(float));
+                if (wantIds)
+                    std::memcpy(idsOut + idx, partIds.data() + src, size_t(w) * sizeof(int));
+            }
+        }
     for (unsigned b = 1; b < bands.size(); b++) {
         const cudaError_t eb = cudaStreamSynchronize(bands[b]->stream);
         if (rc == CGE_OK && eb != cudaSuccess)
@@ -1636,8 +1741,9 @@ int cge_trace_rays(cge_scene* sc, const float* rays7, uint32_t n, const cge_para
         e = cudaMemcpyAsync(dRays, rays7, size_t(n) * 7 * sizeof(float), cudaMemcpyHostToDevice, s->stream);
     if (e == cudaSuccess)
         e = cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream);
-    const DevParams dp = make_dev_params(sc, p);
-    const DevScene ds = scene_for(sc, p);
+    const LightsRef lights = lights_of(sc);
+    const DevParams dp = make_dev_params(sc, p, *lights);
+    const DevScene ds = scene_for(sc, p, *lights);
     Variant v = choose_variant(ds, p, dp);
     v.count = false;
     if (e == cudaSuccess) {
@@ -1995,10 +2101,15 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         return fail(CGE_ERR_INVALID_ARG, "scene and communicator live on different devices");
     const NcclApi* api = nccl_api();
     const bool wantIds = (p.flags & CGE_FLAG_WANT_PRIM_IDS) != 0;
+    const bool rgba8 = p.flags & CGE_FLAG_OUTPUT_RGBA8;
     const bool devOut = p.flags & CGE_FLAG_RGB_DEVICE_PTR;
+    if (rgba8 && devOut)
+        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_OUTPUT_RGBA8 writes a whole host frame");
     CGE_CUDA(cudaSetDevice(sc->device));
     const size_t pixels = size_t(p.width) * size_t(p.height);
-    const DevParams dp = make_dev_params(sc, p);
+    const LightsRef lights = lights_of(sc);
+    const LightSet& ls = *lights;
+    const DevParams dp = make_dev_params(sc, p, ls);
     const unsigned R = unsigned(comm->n_ranks);
     const unsigned myTiles = tiles_of(dp, unsigned(comm->rank), R);
     // packed staging: this rank's tiles (send side); on rank 0 additionally room for every other rank's tiles
@@ -2021,7 +2132,7 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     // every rank renders its interleaved tile subset straight into the full-frame layout of its own scratch frame, as
     // concurrent bands of its tile list when the share is large enough (launch_bands: the stage tails do not shrink with the
     // partition, so they weigh more the more GPUs share the frame)
-    unsigned nBands = nBandsFor(sc, p, dp, false);
+    unsigned nBands = nBandsFor(sc, ls, p, dp, false);
     std::vector<Scratch*> bands;
     if (acquire_bands(sc, s, nBands, bands) != CGE_OK) {
         cudaGetLastError();
@@ -2043,10 +2154,10 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
             const unsigned f0 = unsigned(uint64_t(myTiles) * b / nBands), f1 = unsigned(uint64_t(myTiles) * (b + 1) / nBands);
             ranges.push_back(make_uint2(f0, f1 - f0));
         }
-        rc = launch_bands(sc, bands, ranges, false, cam, &p, dp, frame, frameIds, &launches,
+        rc = launch_bands(sc, ls, bands, ranges, false, cam, &p, dp, frame, frameIds, &launches,
             [&](unsigned, Scratch* sb) { cudaEventRecord(sb->bandDone, sb->stream); });
     } else {
-        rc = launch_render(sc, s, cam, &p, dp, frame, frameIds, &launches);
+        rc = launch_render(sc, ls, s, cam, &p, dp, frame, frameIds, &launches);
     }
     cudaEventRecord(s->ev1, s->stream);
     ncclResult_t nr = ncclSuccess;
@@ -2091,7 +2202,15 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     // the bloom filter is the one cross-pixel step of the path: it runs on rank 0 once the gathered frame is complete
     if (rc == CGE_OK && comm->rank == 0 && (p.features & CGE_FEAT_BLOOM_EFFECT))
         rc = apply_bloom(s, p, frame, &launches);
-    if (rc == CGE_OK && comm->rank == 0 && !devOut) {
+    if (rc == CGE_OK && comm->rank == 0 && rgba8) {
+        // the output stage of Screen::writeBitmapToFile on the gathered frame: the ids (if wanted) leave first, then their buffer
+        // holds the packed pixels (4 bytes per pixel either way), as in cge_render
+        if (wantIds && idsOut)
+            cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+        pack_rgba8_kernel<<<unsigned((pixels + 255) / 256), 256, 0, s->stream>>>(s->rgb, reinterpret_cast<uchar4*>(s->ids), pixels);
+        launches++;
+        cudaMemcpyAsync(rgbOut, s->ids, pixels * 4, cudaMemcpyDeviceToHost, s->stream);
+    } else if (rc == CGE_OK && comm->rank == 0 && !devOut) {
         cudaMemcpyAsync(rgbOut, s->rgb, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
         if (wantIds && idsOut)
             cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);

@@ -14,7 +14,8 @@
 //               q2 = R.lower.z, R.upper.xyz     q3 = child references (bit patterns)
 //             reference-order tree: q3 = { left ref, right ref, left count, right count }; count == 0 -> ref is an
 //             inner-node index, count > 0 -> leaf holding primitives [ref, ref+count) of `tris`.
-//             fast tree: q3 = { left, right, 0, 0 } packed as in bvh_sah.h (bit 31 leaf, bits 28..30 count-1).
+//             fast tree: q3 = { left, right, eL, eR }: child references packed as in bvh_sah.h (bit 31 leaf, bits 28..30
+//             count-1) and the largest extent (max over the axes of upper - lower) of the left / right child box.
 //   qnodes    2 x uint4 per inner node of the fast tree (32 B = one sector): { Lx, Ly, Lz, left } { Rx, Ry, Rz, right }, each
 //             box word = lower | upper << 16 of one axis.  A 16-bit value is 0x8000 | q with q on a 15-bit grid over the
 //             (padded) scene bounds, so that ONE byte permute with the constant 0x3F000000 turns it into the float
@@ -102,6 +103,9 @@ struct DevParams {
     uint32_t shade_mode;
     uint32_t grouped_below_chunks; // auto: trace 4 rays per lane when the launch has fewer 32-evaluation chunks than this
     uint32_t aa_side;              // raysPerPixelSide when extra.enableMultipleRaysPerPixel is set, else 0
+    uint32_t packet_budget, packet_leaf_cost; // shadow_packet.cuh: node visits a hull walk may spend, and what a leaf counts for
+    float packet_fat;              // shadow_packet.cuh: a child box is deferred to the per-ray phase when the packet's hull is wider
+                                   // than (the box's largest extent) / packet_fat where it enters the box
 };
 
 } // namespace cge

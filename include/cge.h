@@ -261,6 +261,12 @@ int cge_scene_bvh_info(const cge_scene* scene, uint32_t* n_nodes, uint32_t* n_le
  * n_spheres entries. */
 int cge_bvh_build_reference_order(const cge_scene_desc* desc, cge_bvh_node* nodes_out, uint32_t* n_nodes_inout,
                                   uint32_t* prim_order_out, uint32_t* root_out, uint32_t* n_levels_out, uint32_t* n_leaves_out);
+/* Host-only (no GPU needed): the check cge_scene_create applies to a caller-supplied tree (desc->bvh_nodes, bvh_prim_order,
+ * bvh_root).  The input is untrusted (flat scene files carry stored trees): bvh_prim_order must be a permutation, the nodes
+ * reachable from the root must form a tree (each reached once: no cycles, no shared subtrees), the children of an inner node
+ * must split its primitive range, the root must cover every primitive.  The depth reported - and used to size the device
+ * traversal stack - is the one measured by the walk, not the depth field.  CGE_OK or CGE_ERR_INVALID_ARG. */
+int cge_bvh_validate(const cge_scene_desc* desc, uint32_t* n_levels_out, uint32_t* n_leaves_out);
 /* The tree CGE_TRAVERSAL_FAST walks (binned SAH, <= 4 primitives per leaf; csrc/sah_split.h specifies it), built by the GPU
  * builder (on_gpu != 0, the one cge_scene_create uses) or by the host builder (on_gpu == 0, no GPU needed).  Both must return
  * the same tree bit for bit.  Inner nodes in depth-first pre-order; child reference: bit 31 = leaf (bits 28..30 = count - 1,

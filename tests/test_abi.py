@@ -89,3 +89,44 @@ def test_host_bvh_builder_dragon_standin_against_live_reference(cge, ref, tmp_pa
     nodes, order, root, levels, leaves = cge.build_reference_bvh_host(flat)
     assert np.array_equal(order, want.bvh_prim_order) and nodes.tobytes() == want.bvh_nodes.tobytes() and root == want.bvh_root
     assert levels == 16
+
+
+def test_supplied_bvh_is_validated_as_untrusted_input(cge):
+    """A caller-supplied tree (stored in a flat scene file) is walked from the root before anything trusts it: cycles, shared
+    subtrees, overlapping or missing leaves and ranges that do not split are refused, and the depth that sizes the device
+    traversal stack is the measured one, whatever the depth fields claim."""
+    flat = cge.scenefile.load(cge.configs.SCENE_DIR / "cornell.cges")
+    nodes, order, root, levels, leaves = cge.build_reference_bvh_host(flat)
+    assert cge.validate_bvh(flat, nodes, order, root) == (levels, leaves)
+    lied = nodes.copy()
+    lied["depth"] = 0  # understated depth: the walk measures the real one
+    assert cge.validate_bvh(flat, lied, order, root) == (levels, leaves)
+    inner = [i for i in range(len(nodes)) if not nodes["is_leaf"][i]]
+    leaf = [i for i in range(len(nodes)) if nodes["is_leaf"][i]]
+
+    def refused(bad_nodes, bad_order=order, bad_root=root):
+        with pytest.raises(cge.CgeError) as e:
+            cge.validate_bvh(flat, bad_nodes, bad_order, bad_root)
+        assert e.value.code == cge.ERR_INVALID_ARG
+
+    cyc = nodes.copy()  # a cycle: an inner node below the root points back at the root
+    child = int(nodes["left"][root])
+    assert not nodes["is_leaf"][child]
+    cyc["left"][child] = root
+    refused(cyc)
+    shared = nodes.copy()  # both children are the same subtree
+    shared["right"][root] = shared["left"][root]
+    refused(shared)
+    overlap = nodes.copy()  # a leaf range that overlaps its sibling's
+    overlap["end"][leaf[0]] += 1
+    refused(overlap)
+    gap = nodes.copy()  # the root does not cover every primitive
+    gap["end"][root] -= 1
+    refused(gap)
+    refused(nodes, bad_root=len(nodes))
+    dup = order.copy()
+    dup[0] = dup[1]
+    refused(nodes, bad_order=dup)
+    unreachable_leaf_as_root = leaf[0]  # a leaf as root covers one primitive only
+    refused(nodes, bad_root=unreachable_leaf_as_root)
+    assert inner
