@@ -21,11 +21,10 @@ LIB_PATH = Path(os.environ.get("CGE_LIB", _PKG / "libcge.so"))  # CGE_LIB: devel
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
-FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_COOPERATIVE = 1, 2, 4, 8
-FLAG_DEBUG_CYCLES, FLAG_PER_THREAD, FLAG_DECOUPLED_SHADE = 16, 32, 64
-FLAG_COUPLED_SHADE, FLAG_GROUPED_SHADE, FLAG_AUTO_SHADE, FLAG_WAVEFRONT = 128, 256, 512, 1024
-FLAG_OUTPUT_RGBA8 = 2048
-FLAG_CHAIN_PER_LEVEL = 4096
+FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_OUTPUT_RGBA8 = 1, 2, 4, 8
+FLAG_PARTITION_TILE_ROWS, FLAG_SHARED_HOST_FRAME = 16, 32
+# development switches (include/cge.h CGE_DEV_FLAG_*): force one of the two production pipelines / the per-pixel cost map
+FLAG_PER_THREAD, FLAG_WAVEFRONT, FLAG_DEBUG_CYCLES = 1 << 16, 1 << 17, 1 << 18
 UNIQUE_ID_BYTES = 128
 
 
@@ -86,7 +85,7 @@ ABI_SYMBOLS = [
     "cge_bvh_build_reference_order", "cge_bvh_validate", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
-    "cge_comm_destroy", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
+    "cge_comm_destroy", "cge_comm_host_frame", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
 ]
 
 _lib = None
@@ -126,6 +125,7 @@ def lib() -> C.CDLL:
         l.cge_comm_unique_id.argtypes = [C.c_void_p]
         l.cge_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         l.cge_comm_destroy.argtypes = [C.c_void_p]
+        l.cge_comm_host_frame.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         l.cge_render_distributed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CgeCamera), C.POINTER(CgeParams),
                                              C.c_void_p, C.c_void_p, C.POINTER(CgeStats)]
         l.cge_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
@@ -379,10 +379,19 @@ class Comm:
             lib().cge_comm_destroy(self.handle)
             self.handle = None
 
+    def host_frame(self, shape, dtype=np.float32) -> np.ndarray:
+        """Collective: a frame in host memory every rank maps (cge_comm_host_frame), for ``render(..., shared_frame=...)``."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        _check(lib().cge_comm_host_frame(self.handle, nbytes, C.byref(ptr)))
+        buf = (C.c_char * nbytes).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def render(self, scene: Scene, cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool = False, rgb_out=None,
-               ids_out=None, device_ptrs=None, camera: CgeCamera | None = None):
+               ids_out=None, device_ptrs=None, camera: CgeCamera | None = None, shared_frame=None, shared_ids=None, flags: int = 0):
+        """cge_render_distributed.  shared_frame: a Comm.host_frame array every rank passes (CGE_FLAG_SHARED_HOST_FRAME)."""
         cam = camera or camera_from_cfg(cfg)
-        p = params_from_cfg(cfg, traversal, want_ids)
+        p = params_from_cfg(cfg, traversal, want_ids, (0, 1), flags)
         H, W = cfg["height"], cfg["width"]
         st = CgeStats()
         if device_ptrs is not None:
@@ -391,6 +400,11 @@ class Comm:
             _check(lib().cge_render_distributed(scene.handle, self.handle, C.byref(cam), C.byref(p), C.c_void_p(rgb_ptr),
                                                 C.c_void_p(ids_ptr) if ids_ptr else None, C.byref(st)))
             return None, None, st.as_dict()
+        if shared_frame is not None:
+            p.flags |= FLAG_SHARED_HOST_FRAME
+            _check(lib().cge_render_distributed(scene.handle, self.handle, C.byref(cam), C.byref(p), _p(shared_frame),
+                                                _p(shared_ids) if want_ids else None, C.byref(st)))
+            return shared_frame, shared_ids, st.as_dict()
         rgb = ids = None
         if self.rank == 0:
             rgb = rgb_out if rgb_out is not None else np.zeros((H, W, 3), np.float32)
@@ -449,12 +463,18 @@ def kat_point_in_triangle(v9, n3, p3, device=0):
     return out
 
 
-def partition_tiles(width: int, height: int, part_index: int, part_count: int) -> list:
+def partition_tiles(width: int, height: int, part_index: int, part_count: int, tile_rows: bool = False) -> list:
     """Tile ids (row-major 8x4 tiles) that cge_render renders for part_index / part_count — the host-side statement of
-    the multi-GPU image partition (csrc/render_kernels.cuh next_tile, csrc/cge_api.cu tiles_of)."""
-    n_tiles = ((width + 7) // 8) * ((height + 3) // 4)
-    part_count = max(part_count, 1)
-    return list(range(part_index if part_count > 1 else 0, n_tiles, part_count))
+    the multi-GPU image partition (csrc/dev_scene.h part_tile_of, csrc/cge_api.cu tiles_of): the parts are dealt units of
+    consecutive tiles round robin, a unit being one tile, or with tile_rows (CGE_FLAG_PARTITION_TILE_ROWS, what
+    cge_render_distributed uses) one whole row of tiles."""
+    tiles_x, tiles_y = (width + 7) // 8, (height + 3) // 4
+    n_tiles = tiles_x * tiles_y
+    if part_count <= 1:
+        return list(range(n_tiles))
+    unit = tiles_x if tile_rows else 1
+    n_units = (n_tiles + unit - 1) // unit
+    return [t for u in range(part_index, n_units, part_count) for t in range(u * unit, min((u + 1) * unit, n_tiles))]
 
 
 def load_scene(cfg: dict) -> FlatScene:

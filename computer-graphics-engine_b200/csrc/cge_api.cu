@@ -2,10 +2,14 @@
 // known-answer entry points, and the multi-GPU tile gather.  No CPU fallback exists anywhere in this file: every
 // compute entry point launches CUDA kernels or returns CGE_ERR_CUDA.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -20,11 +24,13 @@
 #include "nccl_min.h"
 #include "render_kernels.cuh"
 #include "wavefront.cuh"
-#include "shadow_packet.cuh"
-
-#ifndef CGE_GROUP
-#define CGE_GROUP 4 // shadow rays per lane in wf_vis_grouped_kernel (A/B in DESIGN.md 5.3)
+#ifndef CGE_EXPERIMENTS
+#define CGE_EXPERIMENTS 0 // 1: compile the measured-and-rejected variants kept for the record (shadow_packet.cuh) behind their switches
 #endif
+#if CGE_EXPERIMENTS
+#include "shadow_packet.cuh"
+#endif
+
 
 using namespace cge;
 
@@ -85,7 +91,7 @@ struct Scratch {
     size_t gatherPixels = 0;
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
-    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveBounce = 0, waveSub = 0;
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveSub = 0;
     float* bloomTmp = nullptr; // thresholded copy of the frame (renderBloomFilter's screenThreshold)
     size_t bloomPixels = 0;
     cudaStream_t stream = nullptr;
@@ -144,6 +150,11 @@ struct cge_scene {
 struct cge_comm {
     int rank = 0, n_ranks = 1, device = 0;
     void* nccl = nullptr; // ncclComm_t
+    struct HostFrame {
+        void* ptr;
+        size_t bytes;
+    };
+    std::vector<HostFrame> host_frames; // cge_comm_host_frame mappings, released with the communicator
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -330,6 +341,19 @@ int set_lights(cge_scene* sc, const cge_light_desc* lights, uint32_t n)
     return CGE_OK;
 }
 
+// tiles part `rank` of `nRanks` renders: its units (dev_scene.h part_tile_of) are rank, rank + nRanks, ...; the frame's last unit
+// may be short
+unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
+{
+    const unsigned nTiles = d.n_tiles_x * d.n_tiles_y, unit = std::max(d.part_unit, 1u);
+    const unsigned nUnits = (nTiles + unit - 1) / unit;
+    if (nUnits <= rank)
+        return 0;
+    const unsigned mine = (nUnits - rank + nRanks - 1) / nRanks;
+    const unsigned shortBy = (nUnits - 1) % nRanks == rank ? nUnits * unit - nTiles : 0;
+    return mine * unit - shortBy;
+}
+
 DevParams make_dev_params(const cge_scene* sc, const cge_params& p, const LightSet& ls)
 {
     DevParams d {};
@@ -346,15 +370,15 @@ DevParams make_dev_params(const cge_scene* sc, const cge_params& p, const LightS
     host_light_counts(ls.host, p, d.draws_per_hit, d.shadow_rays_per_hit, d.samples_per_hit);
     d.levels = (p.features & CGE_FEAT_RECURSIVE) ? uint32_t(p.ray_depth) + 1u : 1u;
     d.units_per_lane = d.draws_per_hit == 0 ? d.levels : ((1u << d.levels) - 1u);
-    d.debug_cycles = (p.flags & CGE_FLAG_DEBUG_CYCLES) ? 1u : 0u;
+    d.debug_cycles = (p.flags & CGE_DEV_FLAG_DEBUG_CYCLES) ? 1u : 0u;
     d.part_index = p.part_count > 1 ? p.part_index : 0;
     d.part_count = p.part_count > 1 ? p.part_count : 1;
     d.n_tiles_x = uint32_t((p.width + kTileW - 1) / kTileW);
     d.n_tiles_y = uint32_t((p.height + kTileH - 1) / kTileH);
     d.aa_side = (p.features & CGE_FEAT_MULTIPLE_RAYS_PER_PIXEL) ? uint32_t(p.rays_per_pixel_side) : 0u;
-    const uint32_t nTiles = d.n_tiles_x * d.n_tiles_y;
+        d.part_unit = (d.part_count > 1 && (p.flags & CGE_FLAG_PARTITION_TILE_ROWS)) ? d.n_tiles_x : 1u;
     d.tile_first = 0;
-    d.tile_count = nTiles > d.part_index ? (nTiles - d.part_index + d.part_count - 1) / d.part_count : 0;
+    d.tile_count = tiles_of(d, d.part_index, d.part_count);
     return d;
 }
 
@@ -531,33 +555,22 @@ __global__ void bloom_apply_kernel(float* __restrict__ rgb, const float* __restr
     px[0] = out.x, px[1] = out.y, px[2] = out.z;
 }
 
-unsigned tiles_of(const DevParams& d, unsigned rank, unsigned nRanks)
-{
-    const unsigned nTiles = d.n_tiles_x * d.n_tiles_y;
-    return nTiles > rank ? (nTiles - rank + nRanks - 1) / nRanks : 0;
-}
-
-// Which kernel variant a call runs.
-//   fast tree       : CGE_TRAVERSAL_FAST, enableAccelStructure on, no spheres (the archive's sphere test assumes a unit
-//                     direction, so with shadow rays its result depends on which boxes the REFERENCE tree lets through;
-//                     sphere scenes are therefore always walked literally).
-//   cooperative     : opt-in (CGE_FLAG_COOPERATIVE): fast tree + shading on + 1..32 shading samples per hit + the
-//                     per-warp staging fits shared memory.
-//   counting        : literal traversal with box/triangle test counters (CGE_FLAG_COUNT_TESTS).
+// Which kernels a call runs.
+//   fast     : CGE_TRAVERSAL_FAST over the SAH tree (enableAccelStructure on, no spheres: the archive's sphere test assumes a
+//              unit direction, so with shadow rays its result depends on which boxes the REFERENCE tree lets through; sphere
+//              scenes are walked literally), else the literal traversal of the reference-order tree.
+//   count    : box / triangle test counters (CGE_FLAG_COUNT_TESTS; per-thread kernel).
+//   wave     : the wavefront pipeline (wavefront.cuh) instead of the per-thread kernel.
 struct Variant {
-    bool fast, spheres, count, coop, wave;
-    size_t smem;
+    bool fast, spheres, count, wave;
     size_t waveBytes;
 };
 
-constexpr size_t kCoopSmemLimit = 96 * 1024; // per 128-thread CTA: keeps >= 2 CTAs per SM
-constexpr size_t kGroupedThreshold = 24; // worst-case 32-unit chunks per resident warp below which shadow rays are traced 4 per lane
 constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than this fall back to the per-thread kernel
 
 struct WaveSizes {
     size_t recFloats, meta, next, dirFloats, vis;
-    size_t bytes() const { return recFloats * 4 + meta * 8 * 2 + next * 4 + dirFloats * 4 + vis; } // meta + bounce queue (the
-                                                                                                     // sub-ray colours are small beside these)
+    size_t bytes() const { return recFloats * 4 + meta * 8 + next * 4 + dirFloats * 4 + vis; } // (the sub-ray colours are small beside these)
 };
 // camera rays per pixel: with extra.enableMultipleRaysPerPixel every one of them is a chain of its own in the queues
 size_t sub_rays(const DevParams& dp) { return dp.aa_side ? size_t(dp.aa_side) * dp.aa_side : 1; }
@@ -580,20 +593,17 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
     v.spheres = ds.has_spheres != 0;
     v.fast = p.traversal == CGE_TRAVERSAL_FAST && (p.features & CGE_FEAT_ACCEL_STRUCTURE) && !v.spheres;
     v.count = (p.flags & CGE_FLAG_COUNT_TESTS) != 0;
-    v.smem = size_t(coop_warp_floats(dp.levels, dp.units_per_lane)) * 4 * sizeof(float);
-    v.coop = v.fast && (p.features & CGE_FEAT_SHADING) && dp.samples_per_hit >= 1 && dp.samples_per_hit <= 32
-        && v.smem <= kCoopSmemLimit && (p.flags & CGE_FLAG_COOPERATIVE) && !v.count && !dp.aa_side;
     const size_t cap = size_t(dp.tile_count) * 32 * sub_rays(dp);
     v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
     // The wavefront pays off when a pixel's cost is wildly non-uniform, i.e. with area lights (16+ shadow rays per evaluation,
     // 2^k evaluations at level k).  Point-light frames (<= 1 shadow ray per light and hit, recursion folded) are bounded per
     // pixel and launch-latency sensitive: there the single per-thread kernel is faster.
-    const bool areaLights = dp.draws_per_hit > 0 || (p.flags & CGE_FLAG_WAVEFRONT);
-    // several camera rays per pixel: the queues address a pixel with 24 bits (wavefront.cuh meta layout), larger frames and
-    // the opt-in per-level chain stage take the per-thread kernel
-    const bool aaFits = !dp.aa_side || (size_t(p.width) * size_t(p.height) <= (size_t(1) << 24) && !(p.flags & CGE_FLAG_CHAIN_PER_LEVEL));
-    v.wave = v.fast && !v.coop && !v.count && areaLights && aaFits && (p.features & CGE_FEAT_SHADING)
-        && !(p.flags & (CGE_FLAG_PER_THREAD | CGE_FLAG_DEBUG_CYCLES)) && v.waveBytes <= kWaveScratchLimit && cap > 0;
+    const bool areaLights = dp.draws_per_hit > 0 || (p.flags & CGE_DEV_FLAG_WAVEFRONT);
+    // several camera rays per pixel: the queues address a pixel with 24 bits (wavefront.cuh meta layout), larger frames take the
+    // per-thread kernel
+    const bool aaFits = !dp.aa_side || size_t(p.width) * size_t(p.height) <= (size_t(1) << 24);
+    v.wave = v.fast && !v.count && areaLights && aaFits && (p.features & CGE_FEAT_SHADING)
+        && !(p.flags & (CGE_DEV_FLAG_PER_THREAD | CGE_DEV_FLAG_DEBUG_CYCLES)) && v.waveBytes <= kWaveScratchLimit && cap > 0;
     return v;
 }
 
@@ -622,7 +632,7 @@ __global__ void pack_tiles_kernel(const float* __restrict__ rgb, const int* __re
     const unsigned k = g / 32, lane = g % 32;
     if (k >= myTiles)
         return;
-    const unsigned tile = p.part_index + k * p.part_count;
+    const unsigned tile = part_tile_of(p.part_unit, p.part_index, p.part_count, k);
     const int x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
     const int y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
     float r = 0.f, gg = 0.f, b = 0.f;
@@ -640,24 +650,32 @@ __global__ void pack_tiles_kernel(const float* __restrict__ rgb, const int* __re
         outIds[g] = id;
 }
 
-__global__ void unpack_tiles_kernel(const float* __restrict__ inRgb, const int* __restrict__ inIds, float* __restrict__ rgb,
-    int* __restrict__ ids, DevParams p, unsigned srcRank, unsigned nRanks, unsigned srcTiles)
+// Rank 0 of cge_render_distributed: the other ranks' compact rows (dev_scene.h compact_units), received back to back in rank
+// order, scattered into the frame in ONE launch.  Rank r's block b holds tile row u = r + (units[r] - 1 - b) * n_ranks.
+struct UnpackRows {
+    unsigned n_ranks;
+    unsigned offset[16], units[16]; // first block and block count of rank r in the staging buffer (cge_comm_create: <= 16 ranks)
+};
+__global__ void unpack_rows_kernel(const float* __restrict__ inRgb, const int* __restrict__ inIds, float* __restrict__ rgb,
+    int* __restrict__ ids, int W, int H, UnpackRows up, size_t total)
 {
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned k = g / 32, lane = g % 32;
-    if (k >= srcTiles)
+    const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= total)
         return;
-    const unsigned tile = srcRank + k * nRanks;
-    const int x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
-    const int y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
-    if (x < p.width && y < p.height) {
-        const size_t idx = size_t(p.height - 1 - y) * size_t(p.width) + size_t(x);
-        rgb[idx * 3] = inRgb[size_t(g) * 3];
-        rgb[idx * 3 + 1] = inRgb[size_t(g) * 3 + 1];
-        rgb[idx * 3 + 2] = inRgb[size_t(g) * 3 + 2];
-        if (ids && inIds)
-            ids[idx] = inIds[g];
-    }
+    const size_t blockPixels = size_t(kTileH) * size_t(W);
+    const unsigned blk = unsigned(g / blockPixels), within = unsigned(g - size_t(blk) * blockPixels);
+    unsigned r = 1;
+    while (r + 1 < up.n_ranks && blk >= up.offset[r + 1])
+        r++;
+    const unsigned b = blk - up.offset[r], u = r + (up.units[r] - 1u - b) * up.n_ranks;
+    const int rows = min(int(u + 1) * kTileH, H) - int(u) * kTileH, top = H - min(int(u + 1) * kTileH, H);
+    const int row = int(within / unsigned(W)), x = int(within % unsigned(W));
+    if (row >= rows)
+        return; // the frame's topmost tile row can be short
+    const size_t idx = size_t(top + row) * size_t(W) + size_t(x);
+    rgb[idx * 3] = inRgb[g * 3], rgb[idx * 3 + 1] = inRgb[g * 3 + 1], rgb[idx * 3 + 2] = inRgb[g * 3 + 2];
+    if (ids && inIds)
+        ids[idx] = inIds[g];
 }
 
 int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camera* cam, const cge_params* p, const DevParams& dp,
@@ -702,30 +720,16 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
             err = grow(s->wave.dir, s->waveDirFloats, ws.dirFloats, sizeof(float));
         if (err == cudaSuccess && dp.aa_side)
             err = grow(s->wave.sub, s->waveSub, cap * 3, sizeof(float));
-        // Shadow-ray granularity.  Default: 16 coupled rays per lane inside wf_shade_kernel<false>.  When the launch has few
-        // direct-lighting evaluations per resident warp (small frames, one rank's share of a multi-GPU frame) the tail of
-        // that coarse granularity dominates, so the rays are traced in groups of 4 per lane (wf_vis_grouped_kernel) into
-        // visibility bytes and shaded by wf_shade_kernel<true>.  The choice needs the queue lengths, which only exist on the
-        // device: both variants are launched and each kernel returns at once unless it is the selected one (no host sync).
-        const bool visFits = dp.samples_per_hit >= 1 && ws.vis < (size_t(1) << 32);
+        // Shadow rays: traced by wf_vis_regroup_kernel into one visibility byte per ray and shaded from the bytes by
+        // wf_shade_kernel<true>; launches with fewer than 8 samples per evaluation (or visibility bytes beyond 4 GB) let
+        // wf_shade_kernel<false> trace them itself.
+        const bool visFits = dp.samples_per_hit >= 8 && ws.vis < (size_t(1) << 32);
         DevParams wp = dp;
         wp.packet_fat = float(env_int("CGE_PACKET_FAT_PCT", 100)) * 0.01f;
         wp.packet_budget = uint32_t(env_int("CGE_PACKET_BUDGET", 48));
         wp.packet_leaf_cost = uint32_t(env_int("CGE_PACKET_LEAF_COST", 4));
-        wp.grouped_below_chunks = uint32_t(size_t(sc->sm_count) * 32 * kGroupedThreshold);
-        if ((p->flags & CGE_FLAG_DECOUPLED_SHADE) && visFits)
-            wp.shade_mode = 3;
-        else if ((p->flags & CGE_FLAG_GROUPED_SHADE) && visFits)
-            wp.shade_mode = 2;
-        else if ((p->flags & CGE_FLAG_COUPLED_SHADE) || !visFits || dp.samples_per_hit < 8)
-            wp.shade_mode = 1;
-        else if (p->flags & CGE_FLAG_AUTO_SHADE)
-            wp.shade_mode = 0;
-        else
-            wp.shade_mode = 2; // measured faster than the coupled kernel at every size tried
-        const bool decoupled = wp.shade_mode == 3;
-        const bool grouped = wp.shade_mode == 0 || wp.shade_mode == 2;
-        if (err == cudaSuccess && wp.shade_mode != 1)
+        wp.shade_mode = visFits ? 2 : 1;
+        if (err == cudaSuccess && visFits)
             err = grow(s->wave.vis, s->waveVis, ws.vis, 1);
         if (err == cudaSuccess && !s->wave.counts)
             err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 64 * sizeof(unsigned));
@@ -734,98 +738,50 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
         s->wave.cap = unsigned(cap);
         int perSm = 0;
         if (err == cudaSuccess)
-            err = (p->flags & CGE_FLAG_CHAIN_PER_LEVEL) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_primary_kernel, 128, 0)
-                  : dp.aa_side                          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<true>, 128, 0)
-                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<false>, 128, 0);
-        if (err == cudaSuccess && !(p->flags & CGE_FLAG_CHAIN_PER_LEVEL)) {
-            cudaEventRecord(stage[0], s->stream);
+            err = dp.aa_side ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<true>, 128, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<false>, 128, 0);
+        cudaEventRecord(stage[0], s->stream);
+        if (err == cudaSuccess) {
             if (dp.aa_side)
                 wf_chain_kernel<true><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
             else
                 wf_chain_kernel<false><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
             err = cudaGetLastError();
-            cudaEventRecord(stage[1], s->stream);
-        } else if (err == cudaSuccess) {
-            // opt-in: one launch per recursion level (wavefront.cuh); a level whose queue is empty returns at once
-            err = grow(s->wave.bounce, s->waveBounce, ws.meta, sizeof(uint2));
-            cudaEventRecord(stage[0], s->stream);
-            if (err == cudaSuccess) {
-                wf_primary_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
-                err = cudaGetLastError();
-            }
-            int perSmB = 0;
-            if (err == cudaSuccess)
-                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmB, wf_bounce_kernel, 128, 0);
-            for (unsigned level = 1; level < wp.levels && err == cudaSuccess; level++) {
-                wf_bounce_kernel<<<grid_for(perSmB), 128, 0, s->stream>>>(ds, wp, s->wave, level, s->counters);
-                err = cudaGetLastError();
-                *launches += 1;
-            }
-            if (err == cudaSuccess && wp.levels > 1) {
-                wf_chain_finalize_kernel<<<unsigned((cap + 127) / 128), 128, 0, s->stream>>>(s->wave);
-                err = cudaGetLastError();
-                *launches += 1;
-            }
-            cudaEventRecord(stage[1], s->stream);
         }
-        if (err == cudaSuccess && decoupled) {
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_visibility_kernel, 128, 0);
-            if (err == cudaSuccess) {
-                wf_visibility_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
-                err = cudaGetLastError();
-                *launches += 1;
-            }
-        }
-        if (err == cudaSuccess && grouped) {
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_vis_grouped_kernel<CGE_GROUP>, 128, 0);
-            const int packet = env_int("CGE_PACKET", 0); // opt-in: measured slower than the per-ray pass
-            if (err == cudaSuccess && packet > 0) {
-                // one tree walk per lane for a packet of light samples (shadow_packet.cuh)
-                auto go = [&](auto kern) {
-                    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
-                    if (err == cudaSuccess) {
-                        kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
-                        err = cudaGetLastError();
-                    }
-                };
-                if (packet >= 16)
-                    go(wf_vis_packet_kernel<16>);
-                else if (packet >= 8)
-                    go(wf_vis_packet_kernel<8>);
-                else
-                    go(wf_vis_packet_kernel<4>);
-                *launches += 1;
-            } else if (err == cudaSuccess) {
-                if (env_int("CGE_REGROUP", 1)) {
-                    // the default: lanes trade hits between the samples (wf_vis_regroup_kernel), 4 or 8 samples per lane decided on
-                    // the device from the queue lengths; CGE_REGROUP=0 runs the plain wf_vis_grouped_kernel (A/B)
-                    int perSm4 = 0, perSm8 = 0;
-                    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm4, wf_vis_regroup_kernel<4>, 128, 0);
-                    if (err == cudaSuccess)
-                        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm8, wf_vis_regroup_kernel<8>, 128, 0);
-                    wf_vis_regroup_kernel<4><<<unsigned(sc->sm_count * std::max(perSm4, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
-                    wf_vis_regroup_kernel<8><<<unsigned(sc->sm_count * std::max(perSm8, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+        cudaEventRecord(stage[1], s->stream);
+        if (err == cudaSuccess && visFits) {
+            auto go = [&](auto kern) {
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
+                if (err == cudaSuccess) {
+                    kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                    err = cudaGetLastError();
                     *launches += 1;
-                } else {
-                    wf_vis_grouped_kernel<CGE_GROUP><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
                 }
-                err = cudaGetLastError();
-                *launches += 1;
+            };
+#if CGE_EXPERIMENTS
+            const int packet = env_int("CGE_PACKET", 0); // the packet (hull) shadow walk: measured slower
+            if (packet >= 16)
+                go(wf_vis_packet_kernel<16>);
+            else if (packet >= 8)
+                go(wf_vis_packet_kernel<8>);
+            else if (packet > 0)
+                go(wf_vis_packet_kernel<4>);
+            else
+#endif
+            {
+                // 4 or 8 samples per lane, decided on the device from the queue lengths (they only exist there): both
+                // instantiations are launched and the one not selected returns at once
+                go(wf_vis_regroup_kernel<4>);
+                if (err == cudaSuccess)
+                    go(wf_vis_regroup_kernel<8>);
             }
         }
         cudaEventRecord(stage[2], s->stream);
-        if (err == cudaSuccess && wp.shade_mode <= 1) {
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel<false>, 128, 0);
+        if (err == cudaSuccess) {
+            auto kern = visFits ? wf_shade_kernel<true> : wf_shade_kernel<false>;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
             if (err == cudaSuccess) {
-                wf_shade_kernel<false><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
-                err = cudaGetLastError();
-                *launches += 1;
-            }
-        }
-        if (err == cudaSuccess && wp.shade_mode != 1) {
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_shade_kernel<true>, 128, 0);
-            if (err == cudaSuccess) {
-                wf_shade_kernel<true><<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
                 err = cudaGetLastError();
                 *launches += 1;
             }
@@ -843,16 +799,6 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
         cudaEventRecord(stage[4], s->stream);
         s->staged = true;
         *launches += 1; // chain + fold (the caller adds one)
-    } else if (v.coop) {
-        auto kern = render_coop_kernel;
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v.smem));
-        int perSm = 0;
-        if (err == cudaSuccess)
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, v.smem);
-        if (err == cudaSuccess) {
-            kern<<<grid_for(perSm), 128, v.smem, s->stream>>>(ds, dc, dp, rgbDev, idsDev, s->tileCounter, s->counters);
-            err = cudaGetLastError();
-        }
     } else {
         dispatch(v, [&](auto kFast, auto kSpheres, auto kCount) {
             auto kern = render_kernel<decltype(kFast)::value, decltype(kSpheres)::value, decltype(kCount)::value>;
@@ -1367,7 +1313,6 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.next);
         cudaFree(s->wave.dir);
         cudaFree(s->wave.vis);
-        cudaFree(s->wave.bounce);
         cudaFree(s->wave.sub);
         cudaFree(s->bloomTmp);
         cudaFree(s->wave.counts);
@@ -1574,17 +1519,17 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
     Scratch* s = nullptr;
     std::vector<float> partRgb; // a partition rendered to a host frame: its packed tiles (below)
     std::vector<int> partIds;
+    const LightsRef lights = lights_of(sc); // this frame's version of the light list, held until the stream has drained
+    const LightSet& ls = *lights;
+    const DevParams dp = make_dev_params(sc, *p, ls);
     const bool partToHost = p->part_count > 1 && !devOut;
-    const size_t partPixels = partToHost ? (size_t((p->width + kTileW - 1) / kTileW) * size_t((p->height + kTileH - 1) / kTileH) / p->part_count + 1) * 32 : 0;
+    const size_t partPixels = partToHost ? size_t(dp.tile_count) * 32 : 0;
     // rgba8: the float frame lives in the first 3/4 of a doubled scratch frame, the packed bytes in the ids buffer
     rc = acquire_scratch(sc, devOut ? 1 : pixels, wantIds || rgba8, partPixels, &s);
     if (rc) {
         release_scratch(sc, s);
         return rc;
     }
-    const LightsRef lights = lights_of(sc); // this frame's version of the light list, held until the stream has drained
-    const LightSet& ls = *lights;
-    const DevParams dp = make_dev_params(sc, *p, ls);
     float* rgbDev = devOut ? rgbOut : s->rgb;
     int* idsDev = wantIds ? (devOut ? idsOut : s->ids) : nullptr;
     uint32_t launches = 0;
@@ -1691,7 +1636,7 @@ int cge_render(cge_scene* sc, const cge_camera* cam, const cge_params* p, float*
         rc = fail(CGE_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
     if (rc == CGE_OK && !partRgb.empty()) // packed tile k, pixel j (row-major inside the 8x4 tile) -> Screen layout
         for (unsigned k = 0; k < dp.tile_count; k++) {
-            const unsigned tile = dp.part_index + k * dp.part_count;
+            const unsigned tile = part_tile_of(dp.part_unit, dp.part_index, dp.part_count, k);
             const int x0 = int(tile % dp.n_tiles_x) * kTileW, y0 = int(tile / dp.n_tiles_x) * kTileH;
             const int w = std::min(kTileW, p->width - x0);
             for (int y = y0; y < std::min(y0 + kTileH, p->height); y++) {
@@ -2052,8 +1997,8 @@ int cge_comm_unique_id(uint8_t idOut[CGE_UNIQUE_ID_BYTES])
 
 int cge_comm_create(const uint8_t idIn[CGE_UNIQUE_ID_BYTES], int rank, int nRanks, int device, cge_comm** out)
 {
-    if (!idIn || !out || rank < 0 || nRanks < 1 || rank >= nRanks)
-        return fail(CGE_ERR_INVALID_ARG, "bad comm arguments");
+    if (!idIn || !out || rank < 0 || nRanks < 1 || nRanks > 16 || rank >= nRanks)
+        return fail(CGE_ERR_INVALID_ARG, "bad comm arguments (1..16 ranks)");
     const NcclApi* api = nccl_api();
     if (!api)
         return fail(CGE_ERR_NCCL, "libnccl.so.2 not found");
@@ -2078,9 +2023,76 @@ int cge_comm_destroy(cge_comm* c)
     if (!c)
         return CGE_OK;
     const NcclApi* api = nccl_api();
+    for (const auto& f : c->host_frames) {
+        cudaHostUnregister(f.ptr);
+        munmap(f.ptr, f.bytes);
+    }
     if (api && c->nccl)
         api->CommDestroy(static_cast<ncclComm_t>(c->nccl));
     delete c;
+    return CGE_OK;
+}
+
+// A frame in host memory that every rank of the communicator maps (POSIX shared memory, page-locked in each process): with
+// CGE_FLAG_SHARED_HOST_FRAME each rank copies the image rows it rendered straight into it over its own PCIe link.  Collective.
+int cge_comm_host_frame(cge_comm* comm, uint64_t bytes, void** out)
+{
+    if (!comm || !out || bytes == 0)
+        return fail(CGE_ERR_INVALID_ARG, "bad host frame arguments");
+    const NcclApi* api = nccl_api();
+    if (!api)
+        return fail(CGE_ERR_NCCL, "libnccl.so.2 not found");
+    CGE_CUDA(cudaSetDevice(comm->device));
+    ncclComm_t nc = static_cast<ncclComm_t>(comm->nccl);
+    char name[64] = {};
+    static std::atomic<unsigned> serial { 0 };
+    if (comm->rank == 0)
+        std::snprintf(name, sizeof name, "/cge_frame_%d_%u", int(getpid()), serial.fetch_add(1));
+    char* dName = nullptr;
+    int* dOk = nullptr;
+    CGE_CUDA(cudaMalloc(&dName, sizeof name));
+    CGE_CUDA(cudaMalloc(&dOk, sizeof(int)));
+    void* ptr = MAP_FAILED;
+    int fd = -1;
+    if (comm->rank == 0) { // the creator sizes the segment before anyone else opens it
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd >= 0 && ftruncate(fd, off_t(bytes)) != 0) {
+            close(fd);
+            fd = -1;
+        }
+    }
+    cudaMemcpy(dName, name, sizeof name, cudaMemcpyHostToDevice);
+    ncclResult_t nr = api->Broadcast(dName, dName, sizeof name, ncclChar, 0, nc, nullptr);
+    cudaError_t ce = cudaMemcpy(name, dName, sizeof name, cudaMemcpyDeviceToHost); // (legacy stream: ordered after the broadcast)
+    if (comm->rank != 0 && nr == ncclSuccess && ce == cudaSuccess && name[0])
+        fd = shm_open(name, O_RDWR, 0600);
+    if (fd >= 0) {
+        ptr = mmap(nullptr, size_t(bytes), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+    }
+    bool registered = false;
+    if (ptr != MAP_FAILED)
+        registered = cudaHostRegister(ptr, size_t(bytes), cudaHostRegisterPortable) == cudaSuccess;
+    // every rank learns whether every rank succeeded; only then is the name removed (the mappings keep the memory alive)
+    int okHere = (ptr != MAP_FAILED && registered) ? 1 : 0, okAll = 0;
+    cudaMemcpy(dOk, &okHere, sizeof(int), cudaMemcpyHostToDevice);
+    if (nr == ncclSuccess)
+        nr = api->AllReduce(dOk, dOk, 1, ncclInt, ncclMin, nc, nullptr);
+    cudaMemcpy(&okAll, dOk, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dName);
+    cudaFree(dOk);
+    if (comm->rank == 0 && name[0])
+        shm_unlink(name);
+    if (nr != ncclSuccess || !okAll) {
+        cudaGetLastError();
+        if (registered)
+            cudaHostUnregister(ptr);
+        if (ptr != MAP_FAILED)
+            munmap(ptr, size_t(bytes));
+        return fail(nr != ncclSuccess ? CGE_ERR_NCCL : CGE_ERR_NOMEM, "could not map the shared host frame on every rank");
+    }
+    comm->host_frames.push_back({ ptr, size_t(bytes) });
+    *out = ptr;
     return CGE_OK;
 }
 
@@ -2092,46 +2104,61 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     cge_params p = *pIn;
     p.part_index = uint32_t(comm->rank);
     p.part_count = uint32_t(comm->n_ranks);
+    p.flags |= CGE_FLAG_PARTITION_TILE_ROWS; // a rank's share = runs of 4 complete image rows, contiguous in the frame
     int rc = validate_params(sc, &p);
     if (rc)
         return rc;
-    if (!cam || (comm->rank == 0 && !rgbOut))
-        return fail(CGE_ERR_INVALID_ARG, "null camera or output");
-    if (sc->device != comm->device)
-        return fail(CGE_ERR_INVALID_ARG, "scene and communicator live on different devices");
-    const NcclApi* api = nccl_api();
     const bool wantIds = (p.flags & CGE_FLAG_WANT_PRIM_IDS) != 0;
     const bool rgba8 = p.flags & CGE_FLAG_OUTPUT_RGBA8;
     const bool devOut = p.flags & CGE_FLAG_RGB_DEVICE_PTR;
-    if (rgba8 && devOut)
-        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_OUTPUT_RGBA8 writes a whole host frame");
+    // every rank writes its rows into the shared host frame itself (not with bloom: it needs the gathered frame on one GPU)
+    const bool shared = (p.flags & CGE_FLAG_SHARED_HOST_FRAME) && comm->n_ranks > 1 && !(p.features & CGE_FEAT_BLOOM_EFFECT);
+    if (!cam || ((comm->rank == 0 || shared) && !rgbOut))
+        return fail(CGE_ERR_INVALID_ARG, "null camera or output");
+    if (sc->device != comm->device)
+        return fail(CGE_ERR_INVALID_ARG, "scene and communicator live on different devices");
+    if ((rgba8 || (p.flags & CGE_FLAG_SHARED_HOST_FRAME)) && devOut)
+        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_OUTPUT_RGBA8 / CGE_FLAG_SHARED_HOST_FRAME write a host frame");
+    if (shared && rgba8)
+        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_SHARED_HOST_FRAME carries the float frame");
+    if (shared) {
+        bool known = false;
+        for (const auto& f : comm->host_frames)
+            known = known || (f.ptr == rgbOut && f.bytes >= size_t(p.width) * size_t(p.height) * 12);
+        if (!known)
+            return fail(CGE_ERR_INVALID_ARG, "CGE_FLAG_SHARED_HOST_FRAME: rgb_out must be a frame cge_comm_host_frame returned");
+    }
+    const NcclApi* api = nccl_api();
     CGE_CUDA(cudaSetDevice(sc->device));
-    const size_t pixels = size_t(p.width) * size_t(p.height);
+    const size_t W = size_t(p.width), pixels = W * size_t(p.height);
     const LightsRef lights = lights_of(sc);
     const LightSet& ls = *lights;
-    const DevParams dp = make_dev_params(sc, p, ls);
-    const unsigned R = unsigned(comm->n_ranks);
-    const unsigned myTiles = tiles_of(dp, unsigned(comm->rank), R);
-    // packed staging: this rank's tiles (send side); on rank 0 additionally room for every other rank's tiles
+    DevParams dp = make_dev_params(sc, p, ls);
+    const unsigned R = unsigned(comm->n_ranks), rank = unsigned(comm->rank);
+    // a rank's share: units = tile rows rank, rank + R, ...; COMPACT layout (dev_scene.h): units(r) blocks of 4 x W pixels
+    auto unitsOf = [&](unsigned r) { return dp.n_tiles_y > r ? (dp.n_tiles_y - r + R - 1) / R : 0u; };
+    const unsigned myUnits = unitsOf(rank);
+    const bool compact = R > 1 && (rank != 0 || shared); // rank 0 renders straight into the frame it gathers
+    dp.compact_units = compact ? std::max(myUnits, 1u) : 0u;
+    const size_t blockPixels = size_t(kTileH) * W;
     size_t othersPixels = 0;
-    std::vector<size_t> offs(R, 0);
-    if (comm->rank == 0)
+    UnpackRows up {};
+    if (rank == 0 && !shared)
         for (unsigned r = 1; r < R; r++) {
-            offs[r] = othersPixels;
-            othersPixels += size_t(tiles_of(dp, r, R)) * 32;
+            up.offset[r] = unsigned(othersPixels / blockPixels);
+            up.units[r] = unitsOf(r);
+            othersPixels += size_t(unitsOf(r)) * blockPixels;
         }
-    const size_t gatherPixels = comm->rank == 0 ? othersPixels : size_t(myTiles) * 32;
     Scratch* s = nullptr;
-    rc = acquire_scratch(sc, pixels, true, std::max<size_t>(gatherPixels, 1), &s);
+    rc = acquire_scratch(sc, compact ? std::max<size_t>(size_t(myUnits) * blockPixels, 1) : pixels, true, std::max<size_t>(othersPixels, 1), &s);
     if (rc) {
         release_scratch(sc, s);
         return rc;
     }
     ncclComm_t nc = static_cast<ncclComm_t>(comm->nccl);
     uint32_t launches = 0;
-    // every rank renders its interleaved tile subset straight into the full-frame layout of its own scratch frame, as
-    // concurrent bands of its tile list when the share is large enough (launch_bands: the stage tails do not shrink with the
-    // partition, so they weigh more the more GPUs share the frame)
+    // every rank renders its share as concurrent bands of its tile list when the share is large enough (launch_bands: the
+    // stage tails do not shrink with the partition, so they weigh more the more GPUs share the frame)
     unsigned nBands = nBandsFor(sc, ls, p, dp, false);
     std::vector<Scratch*> bands;
     if (acquire_bands(sc, s, nBands, bands) != CGE_OK) {
@@ -2146,12 +2173,12 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         return rc;
     }
     cudaEventRecord(s->ev0, s->stream);
-    float* frame = (comm->rank == 0 && devOut) ? rgbOut : s->rgb;
-    int* frameIds = wantIds ? ((comm->rank == 0 && devOut && idsOut) ? idsOut : s->ids) : nullptr;
+    float* frame = (rank == 0 && devOut) ? rgbOut : s->rgb;
+    int* frameIds = wantIds ? ((rank == 0 && devOut && idsOut) ? idsOut : s->ids) : nullptr;
     if (nBands > 1) {
         std::vector<uint2> ranges;
         for (unsigned b = 0; b < nBands; b++) {
-            const unsigned f0 = unsigned(uint64_t(myTiles) * b / nBands), f1 = unsigned(uint64_t(myTiles) * (b + 1) / nBands);
+            const unsigned f0 = unsigned(uint64_t(dp.tile_count) * b / nBands), f1 = unsigned(uint64_t(dp.tile_count) * (b + 1) / nBands);
             ranges.push_back(make_uint2(f0, f1 - f0));
         }
         rc = launch_bands(sc, ls, bands, ranges, false, cam, &p, dp, frame, frameIds, &launches,
@@ -2161,38 +2188,60 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     }
     cudaEventRecord(s->ev1, s->stream);
     ncclResult_t nr = ncclSuccess;
-    if (rc == CGE_OK && R > 1) {
-        if (comm->rank != 0) {
-            if (myTiles) {
-                pack_tiles_kernel<<<(myTiles * 32 + 255) / 256, 256, 0, s->stream>>>(frame, frameIds, s->gatherRgb,
-                    wantIds ? s->gatherIds : nullptr, dp, myTiles);
-                launches++;
+    if (rc == CGE_OK && shared) {
+        // ---- each rank's rows leave for the shared host frame over its own PCIe link: ONE strided copy -----------------------
+        // block b of the compact buffer holds tile row u = rank + (myUnits - 1 - b) * R, frame rows [H - min(4u + 4, H), H - 4u);
+        // only the frame's topmost tile row can be short (H not a multiple of 4): it is block 0 of the rank that owns it
+        auto copyOut = [&](char* dst, const char* src, size_t px) { // px = bytes per pixel
+            unsigned b0 = 0;
+            const unsigned uTop = rank + (myUnits - 1) * R;
+            const int topRows = p.height - int(uTop) * kTileH; // rows of this rank's topmost tile row
+            if (myUnits && topRows < kTileH) {
+                cudaMemcpyAsync(dst + size_t(p.height - int(uTop) * kTileH - topRows) * W * px, src, size_t(topRows) * W * px,
+                    cudaMemcpyDeviceToHost, s->stream);
+                b0 = 1;
+            }
+            if (myUnits > b0) {
+                const unsigned uFirst = rank + (myUnits - 1 - b0) * R; // tile row of block b0
+                const size_t top = size_t(p.height - int(uFirst + 1) * kTileH);
+                cudaMemcpy2DAsync(dst + top * W * px, size_t(R) * blockPixels * px, src + size_t(b0) * blockPixels * px, blockPixels * px,
+                    blockPixels * px, myUnits - b0, cudaMemcpyDeviceToHost, s->stream);
+            }
+        };
+        copyOut(reinterpret_cast<char*>(rgbOut), reinterpret_cast<const char*>(s->rgb), 12);
+        if (wantIds && idsOut)
+            copyOut(reinterpret_cast<char*>(idsOut), reinterpret_cast<const char*>(s->ids), 4);
+        // the frame is complete when every rank's copy has landed: a 4-byte all-reduce behind the copies on every stream
+        nr = api->AllReduce(s->tileCounter, s->tileCounter, 1, ncclInt, ncclSum, nc, s->stream);
+    } else if (rc == CGE_OK && R > 1) {
+        // ---- gather on rank 0: the other ranks send their compact rows as they are, one unpack launch scatters all of them ----
+        const size_t myPixels = size_t(myUnits) * blockPixels;
+        if (rank != 0) {
+            if (myPixels) {
                 nr = api->GroupStart();
                 if (nr == ncclSuccess)
-                    nr = api->Send(s->gatherRgb, size_t(myTiles) * 32 * 3, ncclFloat, 0, nc, s->stream);
+                    nr = api->Send(s->rgb, myPixels * 3, ncclFloat, 0, nc, s->stream);
                 if (nr == ncclSuccess && wantIds)
-                    nr = api->Send(s->gatherIds, size_t(myTiles) * 32, ncclInt, 0, nc, s->stream);
+                    nr = api->Send(s->ids, myPixels, ncclInt, 0, nc, s->stream);
                 if (nr == ncclSuccess)
                     nr = api->GroupEnd();
             }
         } else {
             nr = api->GroupStart();
             for (unsigned r = 1; r < R && nr == ncclSuccess; r++) {
-                const unsigned t = tiles_of(dp, r, R);
-                if (!t)
+                const size_t n = size_t(up.units[r]) * blockPixels, at = size_t(up.offset[r]) * blockPixels;
+                if (!n)
                     continue;
-                nr = api->Recv(s->gatherRgb + offs[r] * 3, size_t(t) * 32 * 3, ncclFloat, int(r), nc, s->stream);
+                nr = api->Recv(s->gatherRgb + at * 3, n * 3, ncclFloat, int(r), nc, s->stream);
                 if (nr == ncclSuccess && wantIds)
-                    nr = api->Recv(s->gatherIds + offs[r], size_t(t) * 32, ncclInt, int(r), nc, s->stream);
+                    nr = api->Recv(s->gatherIds + at, n, ncclInt, int(r), nc, s->stream);
             }
             if (nr == ncclSuccess)
                 nr = api->GroupEnd();
-            for (unsigned r = 1; r < R && nr == ncclSuccess; r++) {
-                const unsigned t = tiles_of(dp, r, R);
-                if (!t)
-                    continue;
-                unpack_tiles_kernel<<<(t * 32 + 255) / 256, 256, 0, s->stream>>>(s->gatherRgb + offs[r] * 3,
-                    wantIds ? s->gatherIds + offs[r] : nullptr, frame, frameIds, dp, r, R, t);
+            if (nr == ncclSuccess && othersPixels) {
+                up.n_ranks = R;
+                unpack_rows_kernel<<<unsigned((othersPixels + 255) / 256), 256, 0, s->stream>>>(s->gatherRgb, wantIds ? s->gatherIds : nullptr,
+                    frame, frameIds, p.width, p.height, up, othersPixels);
                 launches++;
             }
         }
@@ -2200,9 +2249,9 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     if (rc == CGE_OK && nr != ncclSuccess)
         rc = fail(CGE_ERR_NCCL, std::string("nccl gather: ") + api->GetErrorString(nr));
     // the bloom filter is the one cross-pixel step of the path: it runs on rank 0 once the gathered frame is complete
-    if (rc == CGE_OK && comm->rank == 0 && (p.features & CGE_FEAT_BLOOM_EFFECT))
+    if (rc == CGE_OK && rank == 0 && (p.features & CGE_FEAT_BLOOM_EFFECT))
         rc = apply_bloom(s, p, frame, &launches);
-    if (rc == CGE_OK && comm->rank == 0 && rgba8) {
+    if (rc == CGE_OK && rank == 0 && rgba8) {
         // the output stage of Screen::writeBitmapToFile on the gathered frame: the ids (if wanted) leave first, then their buffer
         // holds the packed pixels (4 bytes per pixel either way), as in cge_render
         if (wantIds && idsOut)
@@ -2210,7 +2259,7 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         pack_rgba8_kernel<<<unsigned((pixels + 255) / 256), 256, 0, s->stream>>>(s->rgb, reinterpret_cast<uchar4*>(s->ids), pixels);
         launches++;
         cudaMemcpyAsync(rgbOut, s->ids, pixels * 4, cudaMemcpyDeviceToHost, s->stream);
-    } else if (rc == CGE_OK && comm->rank == 0 && !devOut) {
+    } else if (rc == CGE_OK && rank == 0 && !devOut && !shared) {
         cudaMemcpyAsync(rgbOut, s->rgb, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
         if (wantIds && idsOut)
             cudaMemcpyAsync(idsOut, s->ids, pixels * sizeof(int), cudaMemcpyDeviceToHost, s->stream);

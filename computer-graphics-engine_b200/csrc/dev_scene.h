@@ -80,6 +80,18 @@ struct DevCamera {
     float half_w, half_h;
 };
 
+struct DevParams;
+__host__ __device__ inline uint32_t part_tile_of(uint32_t unit, uint32_t index, uint32_t count, uint32_t k)
+{
+    const uint32_t j = k / unit;
+    return (index + j * count) * unit + (k - j * unit); // entry k of the part's tile list -> tile id
+}
+__host__ __device__ inline uint32_t part_entry_of(uint32_t unit, uint32_t index, uint32_t count, uint32_t tile)
+{
+    const uint32_t u = tile / unit;
+    return (u - index) / count * unit + (tile - u * unit); // inverse of part_tile_of for a tile of this part
+}
+
 struct DevParams {
     int32_t width, height;
     uint32_t features;
@@ -91,17 +103,22 @@ struct DevParams {
     uint32_t shadow_rays_per_hit; // shadow rays one computeLightContribution call traces
     uint32_t samples_per_hit;     // shading evaluations per call (point: 1, segment: N, parallelogram: N*N)
     uint32_t part_index, part_count;
+    // the image partition deals UNITS of part_unit consecutive tiles (row-major tile numbering): unit u belongs to part u % part_count.
+    // 1 = single 8x4 tiles (cge_render's documented partition), n_tiles_x = whole tile rows (cge_render_distributed: a rank's pixels
+    // are then runs of 4 complete image rows, contiguous in the frame)
+    uint32_t part_unit;
+    // output layout.  0: Screen::pixels() order over the whole frame, index (H-1-y)*W + x (src/screen.cpp:45).  n > 0 (a rank of
+    // cge_render_distributed; part_unit = n_tiles_x, n = the part's tile rows): COMPACT - only the part's own image rows, tile row
+    // by tile row in frame order (render_kernels.cuh out_pixel_index), so that the part's share of the frame is one strided copy
+    uint32_t compact_units;
     // this launch renders entries [tile_first, tile_first + tile_count) of the partition's tile list (entry k = tile
     // part_index + k * part_count); the whole list unless the frame is rendered in bands (cge_api.cu cge_render)
     uint32_t tile_first, tile_count;
     uint32_t n_tiles_x, n_tiles_y;
-    // cooperative kernel only
     uint32_t levels;          // ray_depth + 1 when recursive, else 1
     uint32_t units_per_lane;  // direct-lighting evaluations a pixel can need: levels (fold) or 2^levels - 1
-    uint32_t debug_cycles;    // CGE_FLAG_DEBUG_CYCLES
-    // wavefront shadow-ray granularity: 0 auto (decided on the device from the queue lengths), 1 coupled, 2 grouped, 3 decoupled
-    uint32_t shade_mode;
-    uint32_t grouped_below_chunks; // auto: trace 4 rays per lane when the launch has fewer 32-evaluation chunks than this
+    uint32_t debug_cycles;    // CGE_DEV_FLAG_DEBUG_CYCLES
+    uint32_t shade_mode;      // wavefront: 1 = wf_shade_kernel<false> traces the shadow rays itself, 2 = visibility bytes (wavefront.cuh)
     uint32_t aa_side;              // raysPerPixelSide when extra.enableMultipleRaysPerPixel is set, else 0
     uint32_t packet_budget, packet_leaf_cost; // shadow_packet.cuh: node visits a hull walk may spend, and what a leaf counts for
     float packet_fat;              // shadow_packet.cuh: a child box is deferred to the per-ray phase when the packet's hull is wider

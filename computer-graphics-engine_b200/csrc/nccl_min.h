@@ -1,4 +1,4 @@
-// nccl_min.h — the handful of NCCL entry points the framebuffer gather needs, resolved with dlopen at first use.
+// nccl_min.h — the handful of NCCL entry points the framebuffer gather and the shared host frame need, resolved with dlopen at first use.
 // libcge.so therefore loads on machines without NCCL (CPU-only symbol checks) and, inside a torch process, binds to
 // the libnccl.so.2 torch already loaded (2.28.9 here; the system copy is 2.27.3 — the calls below are ABI-stable).
 #pragma once
@@ -13,6 +13,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
     const char* (*GetErrorString)(ncclResult_t);
@@ -36,11 +38,13 @@ inline const NcclApi* nccl_api()
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
-    ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd
-        && api.GetErrorString;
+    ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.Broadcast
+        && api.GroupStart && api.GroupEnd && api.GetErrorString;
     return ok ? &api : nullptr;
 }
 

@@ -1,18 +1,12 @@
-// render_kernels.cuh — the two render kernels.
+// render_kernels.cuh — the one-thread-per-pixel render kernel.
 //
 //   render_kernel       one thread = one pixel, everything sequential per thread: the literal restatement of
 //                       renderRayTracing -> getFinalColor -> recursiveRayTrace (reference src/render.cpp:27-155,
-//                       273-329).  Used for CGE_TRAVERSAL_REFERENCE (validation mode), for scenes with spheres, and
-//                       as the fallback of the cooperative kernel.
-//   render_coop_kernel  the production kernel (CGE_TRAVERSAL_FAST): one warp = one 8x4 pixel tile, three phases:
-//                         A  every lane traces its pixel's mirror chain (closest hits) and parks one hit record per
-//                            level in shared memory;
-//                         B  the warp's direct-lighting work — every (pixel, level, reflection copy, light, sample) —
-//                            is enumerated with a warp prefix sum and dealt out to ALL 32 lanes, consecutive lanes
-//                            taking consecutive samples of the same hit (coherent shadow rays); per-sample terms are
-//                            summed in the reference's order through warp shuffles;
-//                         C  every lane folds its pixel's 2-ary reflection recursion from the parked terms.
-//                       Persistent CTAs pull tiles from a global counter (cost per tile is wildly non-uniform).
+//                       273-329).  Runs CGE_TRAVERSAL_REFERENCE (validation mode) and, over the fast tree, every
+//                       CGE_TRAVERSAL_FAST frame without area lights (bounded cost per pixel, one launch); frames with
+//                       area lights go through the wavefront pipeline (wavefront.cuh).
+//                       Persistent CTAs pull 8x4 tiles from a global counter (cost per tile is wildly non-uniform).
+//   trace_rays_kernel   getFinalColor for caller-supplied rays.
 #pragma once
 #include "shade.cuh"
 
@@ -24,9 +18,6 @@ constexpr int kMaxLevels = kMaxRayDepth + 1;
 // chosen from the A/B runs recorded in profiles/ (see DESIGN.md "Occupancy").
 #ifndef CGE_MINB_THREAD
 #define CGE_MINB_THREAD 8
-#endif
-#ifndef CGE_MINB_COOP
-#define CGE_MINB_COOP 3
 #endif
 
 struct Counters {
@@ -227,17 +218,32 @@ __device__ __forceinline__ bool next_tile(const DevParams& p, unsigned* tileCoun
         return false;
     if (kOut)
         *kOut = k;
-    // multi-GPU: the tile list is interleaved across ranks, entry k of this rank's list is tile part_index + k * part_count
-    const unsigned tile = p.part_index + (p.tile_first + k) * p.part_count;
+    // multi-GPU: the tile list is interleaved across ranks in units of part_unit tiles (dev_scene.h part_tile_of)
+    const unsigned tile = part_tile_of(p.part_unit, p.part_index, p.part_count, p.tile_first + k);
     x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
     y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
     return true;
 }
 
+// Where pixel (x, y) of the reference's coordinates (y up) goes in the output buffers.  Full layout: Screen::setPixel's y flip
+// (src/screen.cpp:45).  Compact layout (dev_scene.h compact_units): tile row u = y / 4 is the part's j-th unit, j = (u - part_index)
+// / part_count; its up to 4 image rows form block (compact_units - 1 - j) of 4 x W pixels, blocks and the rows inside a block in
+// frame order (top first) - a strided copy with a positive pitch puts them into the frame.
+__host__ __device__ inline size_t out_pixel_index(const DevParams& p, int x, int y)
+{
+    size_t row = size_t(p.height - 1 - y);
+    if (p.compact_units) {
+        const unsigned u = unsigned(y) / unsigned(kTileH), j = (u - p.part_index) / p.part_count;
+        const int top = p.height - (int(u + 1) * kTileH < p.height ? int(u + 1) * kTileH : p.height); // frame row of the block's first row
+        row = size_t(p.compact_units - 1u - j) * kTileH + (row - size_t(top));
+    }
+    return row * size_t(p.width) + size_t(x);
+}
+
 __device__ __forceinline__ void store_pixel(const DevParams& p, float* __restrict__ rgb, int* __restrict__ ids, int x, int y, vec3 c,
     int primId)
 {
-    const size_t idx = size_t(p.height - 1 - y) * size_t(p.width) + size_t(x); // Screen::setPixel y flip (src/screen.cpp:45)
+    const size_t idx = out_pixel_index(p, x, y);
     rgb[idx * 3 + 0] = c.x;
     rgb[idx * 3 + 1] = c.y;
     rgb[idx * 3 + 2] = c.z;
@@ -310,244 +316,6 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(DevScene s, DevParams p
             ids[i] = primId;
     }
     pt.finish(gcnt);
-}
-
-// -----------------------------------------------------------------------------------------------------------------
-// cooperative kernel (fast tree, triangles only, shading on, 1 <= samples_per_hit <= 32)
-// -----------------------------------------------------------------------------------------------------------------
-// Shared memory per warp (floats):  rec[levels][kRecFloats][32] | dir[units_per_lane][3][32] | pref[33]
-__host__ __device__ inline unsigned coop_warp_floats(unsigned levels, unsigned units)
-{
-    return levels * kRecFloats * 32u + units * 3u * 32u + 40u;
-}
-
-__device__ __forceinline__ void rec_store(float* rec, unsigned level, unsigned lane, const HitRec& h)
-{
-    float* b = rec + size_t(level) * kRecFloats * 32 + lane;
-    b[0 * 32] = h.ray.o.x, b[1 * 32] = h.ray.o.y, b[2 * 32] = h.ray.o.z;
-    b[3 * 32] = h.ray.d.x, b[4 * 32] = h.ray.d.y, b[5 * 32] = h.ray.d.z;
-    b[6 * 32] = h.ray.t;
-    b[7 * 32] = h.normal.x, b[8 * 32] = h.normal.y, b[9 * 32] = h.normal.z;
-    b[10 * 32] = h.m.kd.x, b[11 * 32] = h.m.kd.y, b[12 * 32] = h.m.kd.z;
-    b[13 * 32] = h.m.ks.x, b[14 * 32] = h.m.ks.y, b[15 * 32] = h.m.ks.z;
-    b[16 * 32] = h.m.shininess;
-}
-__device__ __forceinline__ HitRec rec_load(const float* rec, unsigned level, unsigned lane)
-{
-    const float* b = rec + size_t(level) * kRecFloats * 32 + lane;
-    HitRec h;
-    h.ray.o = v3(b[0 * 32], b[1 * 32], b[2 * 32]);
-    h.ray.d = v3(b[3 * 32], b[4 * 32], b[5 * 32]);
-    h.ray.t = b[6 * 32];
-    h.normal = v3(b[7 * 32], b[8 * 32], b[9 * 32]);
-    h.m.kd = v3(b[10 * 32], b[11 * 32], b[12 * 32]);
-    h.m.ks = v3(b[13 * 32], b[14 * 32], b[15 * 32]);
-    h.m.shininess = b[16 * 32];
-    return h;
-}
-
-__global__ void __launch_bounds__(128, CGE_MINB_COOP) render_coop_kernel(DevScene s, DevCamera cam, DevParams p, float* __restrict__ rgb,
-    int* __restrict__ ids, unsigned* __restrict__ tileCounter, Counters* __restrict__ gcnt)
-{
-    extern __shared__ float smem[];
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* rec = smem + size_t(warp) * coop_warp_floats(p.levels, p.units_per_lane);
-    float* dir = rec + size_t(p.levels) * kRecFloats * 32;
-    unsigned* pref = reinterpret_cast<unsigned*>(dir + size_t(p.units_per_lane) * 3 * 32);
-
-    const bool fold = p.draws_per_hit == 0;
-    const bool recursive = p.features & CGE_FEAT_RECURSIVE;
-    const unsigned S = p.samples_per_hit; // 1..32, warp-uniform
-    const unsigned P = 32u / S;           // hits shaded concurrently by one warp
-    Counters cnt {};
-    int x, y;
-    while (next_tile(p, tileCounter, lane, x, y)) {
-        const bool live = x < p.width && y < p.height;
-        // ---- phase A: the pixel's mirror chain ----------------------------------------------------------------------
-        int n = 0, primId = -1;
-        bool missEnd = false;
-        if (live) {
-            Ray ray = generate_ray(cam, x, y, p.width, p.height);
-            for (int level = 0;; level++) {
-                const Hit h = trace_fast<false>(s, ray.o, ray.d, ray.t);
-                if (level == 0)
-                    cnt.primary++;
-                else
-                    cnt.bounce++;
-                if (h.prim < 0) {
-                    missEnd = true;
-                    break;
-                }
-                ray.t = h.t;
-                HitRec r;
-                resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
-                rec_store(rec, unsigned(level), lane, r);
-                if (level == 0)
-                    primId = int(h.gid);
-                n = level + 1;
-                if (!recursive || level >= p.ray_depth)
-                    break;
-                Ray next;
-                if (!reflection_ray(r, next))
-                    break;
-                ray = next;
-            }
-            reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
-        }
-        // ---- phase B: direct lighting of every (pixel, level, copy), dealt out to all lanes --------------------------
-        const unsigned myUnits = fold ? unsigned(n) : ((1u << n) - 1u);
-        unsigned incl = myUnits;
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= unsigned(off))
-                incl += v;
-        }
-        pref[lane + 1] = incl;
-        if (lane == 0)
-            pref[0] = 0;
-        __syncwarp();
-        const unsigned U = __shfl_sync(0xffffffffu, incl, 31);
-        const unsigned g = lane / S, j = lane % S;
-        for (unsigned base = 0; base < U; base += P) {
-            const unsigned u = base + g;
-            const bool active = g < P && u < U;
-            vec3 term = v3(0.0f);
-            unsigned src = 0, ul = 0;
-            if (active) {
-                // owner lane of unit u: pref[src] <= u < pref[src+1]
-                unsigned lo = 0, hi = 32;
-                while (hi - lo > 1) {
-                    const unsigned mid = (lo + hi) >> 1;
-                    if (pref[mid] <= u)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                src = lo;
-                ul = u - pref[src];
-                // (level k, copy path) of the unit and its first draw index in the reference's depth-first order:
-                // index = sum_{i=1..k} (1 + b_i * (2^(nSrc-i) - 1)),  b_i = i-th copy choice on the way down
-                unsigned k = ul, path = 0, ctr = 0;
-                if (!fold) {
-                    k = 31u - unsigned(__clz(int(ul + 1u)));
-                    path = ul + 1u - (1u << k);
-                    const unsigned nSrc = 32u - unsigned(__clz(int(pref[src + 1] - pref[src]))); // units = 2^n - 1
-                    unsigned idx = 0;
-                    for (unsigned i = 1; i <= k; i++) {
-                        const unsigned b = (path >> (k - i)) & 1u;
-                        idx += 1u + b * ((1u << (nSrc - i)) - 1u);
-                    }
-                    ctr = idx * p.draws_per_hit;
-                }
-                const HitRec h = rec_load(rec, k, src);
-                // task j -> (light, sample)
-                unsigned li = 0, si = j, samples = 0, draws = 0, type = 0;
-                const float* L = s.lights;
-                for (;; li++) {
-                    L = s.lights + size_t(li) * kLightFloats;
-                    type = __float_as_uint(__ldg(L));
-                    light_counts(type, p, samples, draws);
-                    if (si < samples)
-                        break;
-                    si -= samples;
-                    ctr += draws;
-                }
-                // pixel id of the owner lane = this tile's pixel of lane `src`
-                const int sx = x - int(lane % kTileW) + int(src % kTileW), sy = y - int(lane / kTileW) + int(src / kTileW);
-                const unsigned spx = unsigned(sy) * unsigned(p.width) + unsigned(sx);
-                const LightSample ls = sample_light(L, type, int(si), p, spx, ctr);
-                float vis = 1.0f;
-                if (ls.shadowed && !shading_is_zero(s, shade_frame(h), ls.pos)) {
-                    const vec3 so = shadow_origin(h);
-                    cnt.shadow++;
-                    vis = trace_shadow(s, so, ls.pos - so) >= 0 ? 0.0f : 1.0f;
-                }
-                term = compute_shading(ls.pos, ls.col, h) * vis;
-            }
-            // ordered reduction: the group leader adds the terms exactly as computeLightContribution does
-            vec3 result = v3(0.0f);
-            unsigned idx = 0;
-            const unsigned gbase = (g < P ? g : 0u) * S;
-            for (unsigned li = 0; li < s.n_lights; li++) {
-                const unsigned type = __float_as_uint(__ldg(s.lights + size_t(li) * kLightFloats));
-                unsigned samples, draws;
-                light_counts(type, p, samples, draws);
-                if (samples == 0)
-                    continue;
-                if (type == CGE_LIGHT_POINT) {
-                    const unsigned from = gbase + idx;
-                    result = result + v3(__shfl_sync(0xffffffffu, term.x, from), __shfl_sync(0xffffffffu, term.y, from),
-                                          __shfl_sync(0xffffffffu, term.z, from));
-                } else {
-                    vec3 color = v3(0.0f);
-                    for (unsigned q = 0; q < samples; q++) {
-                        const unsigned from = gbase + idx + q;
-                        color = color + v3(__shfl_sync(0xffffffffu, term.x, from), __shfl_sync(0xffffffffu, term.y, from),
-                                            __shfl_sync(0xffffffffu, term.z, from));
-                    }
-                    const float denom = type == CGE_LIGHT_SEGMENT ? float(p.segment_samples)
-                                                                  : fmul(float(p.parallelogram_samples), float(p.parallelogram_samples));
-                    result = result + color / denom;
-                }
-                idx += samples;
-            }
-            if (active && j == 0) {
-                float* d = dir + size_t(ul) * 3 * 32 + src;
-                d[0] = result.x, d[32] = result.y, d[64] = result.z;
-            }
-        }
-        __syncwarp();
-        // ---- phase C: fold the 2-ary recursion of this lane's pixel -------------------------------------------------
-        if (live) {
-            vec3 out = v3(0.0f);
-            auto dirAt = [&](unsigned unit) {
-                const float* d = dir + size_t(unit) * 3 * 32 + lane;
-                return v3(d[0], d[32], d[64]);
-            };
-            if (n > 0) {
-                if (fold) {
-                    vec3 val = dirAt(unsigned(n - 1));
-                    if (missEnd)
-                        val = (val + v3(0.0f)) + v3(0.0f);
-                    for (int k = n - 2; k >= 0; k--)
-                        val = (dirAt(unsigned(k)) + val) + val;
-                    out = val;
-                } else {
-                    vec3 acc[kMaxLevels];
-                    unsigned char state[kMaxLevels];
-                    int level = 0;
-                    unsigned path = 0;
-                    acc[0] = dirAt(0);
-                    state[0] = 0;
-                    for (;;) {
-                        const bool spawned = (level < n - 1) || missEnd;
-                        if (!spawned || state[level] == 2) {
-                            const vec3 v = acc[level];
-                            if (level == 0) {
-                                out = v;
-                                break;
-                            }
-                            level--;
-                            path >>= 1;
-                            acc[level] = acc[level] + v;
-                            state[level]++;
-                        } else if (level + 1 < n) {
-                            path = path * 2u + state[level];
-                            level++;
-                            acc[level] = dirAt((1u << level) - 1u + path);
-                            state[level] = 0;
-                        } else {
-                            acc[level] = acc[level] + v3(0.0f);
-                            state[level]++;
-                        }
-                    }
-                }
-            }
-            store_pixel(p, rgb, ids, x, y, out, primId);
-        }
-        __syncwarp();
-    }
-    flush_counters(cnt, gcnt);
 }
 
 } // namespace cge

@@ -44,27 +44,15 @@ struct WaveBuffers {
     unsigned* next;
     float* dir;
     unsigned char* vis; // one byte per (level, copy, sample, slot): 1 = light sample visible
-    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] ray counter,
-                        // [32..47] bounce-queue length per level, [48..63] bounce-queue chunk counter per level
-    uint2* bounce;      // [level][cap]: (level-0 slot of the pixel, slot of its hit at level - 1): the rays wf_bounce_kernel traces
+    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] shadow-ray chunk counter
     float* sub;         // multiple rays per pixel: [3][launch pixel][sub-ray] colour of every camera ray, summed by wf_resolve_kernel
     unsigned cap;
 };
 
-// Shadow-ray granularity of this launch (see cge_api.cu launch_render): true = rays are traced 4 per lane into the visibility
-// bytes (wf_vis_grouped_kernel) and wf_shade_kernel<true> shades; false = wf_shade_kernel<false> traces 16 per lane itself.
-// Decided from the queue lengths the chain kernel produced, identically by every kernel of the pipeline, without a host sync.
-__device__ __forceinline__ bool wf_use_visibility_bytes(const DevParams& p, const WaveBuffers& wb)
-{
-    if (p.shade_mode == 1)
-        return false;
-    if (p.shade_mode >= 2)
-        return true;
-    unsigned long long units = 0;
-    for (unsigned k = 0; k < p.levels; k++)
-        units += (unsigned long long)wb.counts[k] * (p.draws_per_hit == 0 ? 1u : (1u << k));
-    return units / 32ull < p.grouped_below_chunks;
-}
+// Shadow rays of this launch (see cge_api.cu launch_render): true = traced by wf_vis_regroup_kernel into one visibility byte per
+// ray, wf_shade_kernel<true> shades from the bytes; false = wf_shade_kernel<false> traces them itself (frames with fewer than 8
+// samples per evaluation, e.g. point lights forced through the wavefront, or visibility bytes beyond 4 GB).
+__device__ __forceinline__ bool wf_use_visibility_bytes(const DevParams& p, const WaveBuffers&) { return p.shade_mode != 1; }
 
 __device__ __forceinline__ size_t wf_dir_off(const DevParams& p, unsigned cap, unsigned k)
 {
@@ -99,7 +87,7 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
         if (kSubRays && live && ids) { // the id map stays that of the un-jittered pixel-corner ray (not a reference ray: not counted)
             const Ray c = generate_ray(cam, x, y, p.width, p.height);
             const Hit h = trace_fast<false>(s, c.o, c.d, c.t);
-            ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = h.prim >= 0 ? int(h.gid) : -1;
+            ids[out_pixel_index(p, x, y)] = h.prim >= 0 ? int(h.gid) : -1;
         }
         for (unsigned sub = 0; sub < nSub; sub++) {
             Ray ray {};
@@ -150,7 +138,7 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
                     if (level > 0)
                         wb.next[size_t(level - 1) * wb.cap + slots[level - 1]] = slot;
                     else if (ids && !kSubRays)
-                        ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = int(h.gid);
+                        ids[out_pixel_index(p, x, y)] = int(h.gid);
                     n = level + 1;
                     Ray nextRay;
                     if (!recursive || level >= p.ray_depth || !reflection_ray(r, nextRay))
@@ -180,171 +168,8 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
     flush_counters(cnt, gcnt);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// The chain stage as one launch per recursion level - opt-in (CGE_FLAG_CHAIN_PER_LEVEL), measured slower than wf_chain_kernel.
-// The idea: in wf_chain_kernel a lane owns a pixel's whole mirror chain, so the unit of work is up to `levels` closest-hit
-// rays in sequence, only the lanes whose hit reflects stay busy at the deeper levels, and the kernel's tail is the slowest
-// tile whatever the size of the launch (0.59 ms of a 3.1 ms frame on a 1/8 share of C5).  Here a lane traces ONE ray:
-// wf_primary_kernel the camera rays (tiles from the atomic counter), wf_bounce_kernel the reflected rays of level k, 32 per
-// warp from the bounce queue level k - 1 appended to (ballot + one atomic per warp).  A reflected ray is recomputed from the
-// stored hit record, so a queue entry is two indices.  The chain length of a pixel is only known where its chain ends: that
-// lane writes the tag into the pixel's level-0 meta entry and wf_chain_finalize_kernel copies it to the deeper levels'
-// entries, which restores exactly the arrays wf_chain_kernel produces (same records, same links; slot ORDER differs, which
-// nothing depends on).  Measured on B200, C5 (profiles/): primary 0.70 + bounce levels 0.74 + 0.39 + 0.25 ms =
-// 2.1 ms against 1.33 ms for wf_chain_kernel (one rank's 1/8 share: 0.91 vs 0.49 ms): every level pays its own tail, and
-// the incoherent reflected rays no longer overlap with other tiles' cheap camera rays.
-// ---------------------------------------------------------------------------------------------------------------------
-struct ChainHitOut {
-    unsigned slot;
-    bool reflects;
-};
-
-// Append the hits of a warp to the level's queue and write their records; lanes without a hit pass hit = false.
-__device__ __forceinline__ ChainHitOut wf_store_hit(const DevScene& s, const DevParams& p, const WaveBuffers& wb, unsigned level, bool hit,
-    const Hit& h, Ray ray, unsigned pixel, unsigned lane)
-{
-    const unsigned below = (1u << lane) - 1u;
-    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-    unsigned base = 0;
-    if (lane == 0 && ballot)
-        base = atomicAdd(wb.counts + level, unsigned(__popc(ballot)));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    ChainHitOut out { 0u, false };
-    if (!hit)
-        return out;
-    out.slot = base + unsigned(__popc(ballot & below));
-    ray.t = h.t;
-    HitRec r;
-    resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
-    float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + out.slot;
-    const size_t c = wb.cap;
-    b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
-    b[3 * c] = r.ray.d.x, b[4 * c] = r.ray.d.y, b[5 * c] = r.ray.d.z;
-    b[6 * c] = r.ray.t;
-    b[7 * c] = r.normal.x, b[8 * c] = r.normal.y, b[9 * c] = r.normal.z;
-    b[10 * c] = r.m.kd.x, b[11 * c] = r.m.kd.y, b[12 * c] = r.m.kd.z;
-    b[13 * c] = r.m.ks.x, b[14 * c] = r.m.ks.y, b[15 * c] = r.m.ks.z;
-    b[16 * c] = r.m.shininess;
-    const vec3 so = shadow_origin(r);
-    b[17 * c] = so.x, b[18 * c] = so.y, b[19 * c] = so.z;
-    wb.meta[size_t(level) * wb.cap + out.slot] = make_uint2(pixel, 0u); // .y: wf_chain_finalize_kernel (level 0: the chain's end)
-    const bool recursive = p.features & CGE_FEAT_RECURSIVE;
-    out.reflects = recursive && int(level) < p.ray_depth && !(r.m.ks.x == 0.0f && r.m.ks.y == 0.0f && r.m.ks.z == 0.0f);
-    return out;
-}
-
-// Lanes whose hit reflects enqueue the next level's ray; lanes whose chain ends here record (n, missEnd) for their pixel.
-__device__ __forceinline__ void wf_continue_or_end(const DevParams& p, const WaveBuffers& wb, unsigned level, bool live, bool hit,
-    const ChainHitOut& ho, unsigned e0, unsigned lane, Counters& cnt)
-{
-    const unsigned below = (1u << lane) - 1u;
-    const bool goesOn = live && hit && ho.reflects;
-    const unsigned ballot = __ballot_sync(0xffffffffu, goesOn);
-    unsigned base = 0;
-    if (lane == 0 && ballot)
-        base = atomicAdd(wb.counts + 32 + level + 1, unsigned(__popc(ballot)));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (goesOn) {
-        wb.bounce[size_t(level + 1) * wb.cap + base + unsigned(__popc(ballot & below))] = make_uint2(e0, ho.slot);
-    } else if (live) {
-        const int n = hit ? int(level) + 1 : int(level); // hit levels of this pixel's chain
-        const bool missEnd = !hit;
-        reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
-        if (n > 0)
-            wb.meta[e0].y = unsigned(n) | (missEnd ? 256u : 0u);
-    }
-}
-
-__global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_primary_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb,
-    float* __restrict__ rgb, int* __restrict__ ids, Counters* __restrict__ gcnt)
-{
-    const unsigned lane = threadIdx.x & 31;
-    Counters cnt {};
-    int x, y;
-    while (next_tile(p, wb.counts + 16, lane, x, y)) {
-        const bool live = x < p.width && y < p.height;
-        const unsigned pixel = unsigned(y) * unsigned(p.width) + unsigned(x);
-        Ray ray {};
-        Hit h {};
-        bool hit = false;
-        if (live) {
-            ray = generate_ray(cam, x, y, p.width, p.height);
-            h = trace_fast<false>(s, ray.o, ray.d, ray.t);
-            cnt.primary++;
-            hit = h.prim >= 0;
-        }
-        const ChainHitOut ho = wf_store_hit(s, p, wb, 0, hit, h, ray, pixel, lane);
-        if (live && hit && ids)
-            ids[size_t(p.height - 1 - y) * size_t(p.width) + size_t(x)] = int(h.gid);
-        if (live && !hit)
-            store_pixel(p, rgb, ids, x, y, v3(0.0f), -1); // primary miss: black (reference src/render.cpp:148)
-        wf_continue_or_end(p, wb, 0, live, hit, ho, ho.slot, lane, cnt);
-    }
-    flush_counters(cnt, gcnt);
-}
-
-__global__ void __launch_bounds__(128, CGE_MINB_CHAIN) wf_bounce_kernel(DevScene s, DevParams p, WaveBuffers wb, unsigned level,
-    Counters* __restrict__ gcnt)
-{
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned total = wb.counts[32 + level];
-    Counters cnt {};
-    for (;;) {
-        unsigned chunk = 0;
-        if (lane == 0)
-            chunk = atomicAdd(wb.counts + 48 + level, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if ((unsigned long long)chunk * 32ull >= total)
-            break;
-        const unsigned i = chunk * 32u + lane;
-        const bool live = i < total;
-        uint2 item = make_uint2(0u, 0u);
-        unsigned pixel = 0;
-        Ray ray {};
-        Hit h {};
-        bool hit = false;
-        if (live) {
-            item = wb.bounce[size_t(level) * wb.cap + i];
-            // the reflected ray of the hit at level - 1, from its record (computeReflectionRay, src/shading.cpp:40-62)
-            const float* b = wb.rec + (size_t(level - 1) * kWaveRecFloats) * wb.cap + item.y;
-            const size_t c = wb.cap;
-            HitRec prev;
-            prev.ray.o = v3(b[0 * c], b[1 * c], b[2 * c]);
-            prev.ray.d = v3(b[3 * c], b[4 * c], b[5 * c]);
-            prev.ray.t = b[6 * c];
-            prev.normal = v3(b[7 * c], b[8 * c], b[9 * c]);
-            prev.m.ks = v3(b[13 * c], b[14 * c], b[15 * c]);
-            reflection_ray(prev, ray); // ks != 0 was checked when the entry was queued
-            pixel = wb.meta[size_t(level - 1) * wb.cap + item.y].x;
-            h = trace_fast<false>(s, ray.o, ray.d, ray.t);
-            cnt.bounce++;
-            hit = h.prim >= 0;
-        }
-        const ChainHitOut ho = wf_store_hit(s, p, wb, level, hit, h, ray, pixel, lane);
-        if (live && hit)
-            wb.next[size_t(level - 1) * wb.cap + item.y] = ho.slot;
-        wf_continue_or_end(p, wb, level, live, hit, ho, item.x, lane, cnt);
-    }
-    flush_counters(cnt, gcnt);
-}
-
-// the tag (chain length | missEnd << 8) of every pixel, copied from its level-0 entry to the entries of its deeper levels
-__global__ void __launch_bounds__(128) wf_chain_finalize_kernel(WaveBuffers wb)
-{
-    const unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e0 >= wb.counts[0])
-        return;
-    const unsigned tag = wb.meta[e0].y;
-    const int n = int(tag & 255u);
-    unsigned slot = e0;
-    for (int k = 1; k < n; k++) {
-        slot = wb.next[size_t(k - 1) * wb.cap + slot];
-        wb.meta[size_t(k) * wb.cap + slot].y = tag;
-    }
-}
-
 // computeLightContribution for one (pixel, level, copy): same arithmetic and order as PixelTracer::direct.
-// kLookup: visibilities were traced by wf_visibility_kernel; vis points at this evaluation's sample 0, stride = queue length.
+// kLookup: visibilities were traced by wf_vis_regroup_kernel; vis points at this evaluation's sample 0, stride = queue length.
 template <bool kLookup>
 __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p, const HitRec& h, unsigned pixel, unsigned ctr,
     unsigned long long& nshadow, const unsigned char* __restrict__ vis, size_t visStride)
@@ -444,262 +269,15 @@ __device__ __forceinline__ LightSample wf_sample(const DevScene& s, const DevPar
     return sample_light(L, type, int(si), p, pixel, ctr);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// wf_visibility_kernel: every shadow ray of the frame, one ray per lane, lanes DECOUPLED.
-// In wf_shade_kernel<false> a lane owns 16 consecutive shadow rays and the warp waits for its slowest lane on every one of
-// them; ncu (profiles/r01_wf_shade_c5.txt) shows the traversal loop running at 11 of 32 threads because occluded rays end
-// after a few nodes while their unoccluded neighbours walk ~40.  Here a lane that finishes its ray simply takes the next
-// one: lanes that are out of work are counted with __ballot_sync and, once kRefill of them wait (or nothing is in flight),
-// ONE atomicAdd hands each a new ray index (consecutive indices = neighbouring pixels, same sample).  The result is one
-// byte per ray; the arithmetic-order-sensitive part (shading and the ordered sums) runs afterwards in
-// wf_shade_kernel<true>, fully convergent.
-// ---------------------------------------------------------------------------------------------------------------------
-#ifndef CGE_REFILL
-#define CGE_REFILL 10
-#endif
-#ifndef CGE_INNER_MIN
-#define CGE_INNER_MIN 12
-#endif
-constexpr unsigned kRefill = CGE_REFILL;      // refill when this many lanes have no ray in flight
-constexpr unsigned kInnerMin = CGE_INNER_MIN; // keep stepping inner nodes while this many lanes are on one
-
-__global__ void __launch_bounds__(128, 8) wf_visibility_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
-{
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned below = (1u << lane) - 1u;
-    const bool fold = p.draws_per_hit == 0;
-    const unsigned S = p.samples_per_hit;
-    // direct-lighting evaluations ("units") are numbered like wf_shade_kernel's work items
-    unsigned cum[kMaxLevels + 1];
-    cum[0] = 0;
-    for (unsigned k = 0; k < p.levels; k++)
-        cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
-    const unsigned totalUnits = cum[p.levels];
-    unsigned long long nshadow = 0;
-    constexpr unsigned kDone = 0x7fffffffu;
-
-    // per-lane state: the unit being evaluated, the sample whose ray is in flight, and that ray's traversal state
-    bool haveUnit = false, busy = false, drained = false;
-    unsigned pixel = 0, ctrBase = 0, sg = 0;       // sg = sample index within the unit (over all lights)
-    unsigned char* visOut = nullptr;                // this unit's sample 0
-    size_t visStride = 0;
-    vec3 o = v3(0.0f), d = v3(0.0f), inv = v3(0.0f);
-    ShadeFrame frame {};
-    unsigned stack[kFastStackSize];
-    int sp = 0;
-    unsigned cur = kDone;
-
-    for (;;) {
-        // ---- A. lanes without a ray in flight take their unit's next sample, or a new unit ----------------------------
-        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-        if (idle == 0xffffffffu || unsigned(__popc(idle)) >= kRefill || drained) {
-            bool needUnit = !busy && (!haveUnit || sg >= S);
-            const unsigned want = __ballot_sync(0xffffffffu, needUnit && !drained);
-            if (want) {
-                unsigned base = 0;
-                if (lane == 0)
-                    base = atomicAdd(wb.counts + 18, unsigned(__popc(want)));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + unsigned(__popc(want)) >= totalUnits)
-                    drained = true; // warp-uniform: every unit of the frame has been handed out
-                const unsigned u = base + unsigned(__popc(want & below));
-                if (needUnit) {
-                    haveUnit = u < totalUnits;
-                    if (haveUnit) {
-                        unsigned k = 0;
-                        while (u >= cum[k + 1])
-                            k++;
-                        const unsigned inLevel = u - cum[k], cnt = wb.counts[k];
-                        const unsigned path = inLevel / cnt, e = inLevel - path * cnt;
-                        const uint2 m = wb.meta[size_t(k) * wb.cap + e];
-                        pixel = wf_pixel(m);
-                        ctrBase = wf_unit_ctr(p, k, path, m);
-                        const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
-                        o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
-                        if (s.cull_zero_shading)
-                            frame = wf_load_frame(wb, k, e);
-                        visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
-                        visStride = cnt;
-                        sg = 0;
-                    }
-                }
-            } else if (needUnit) {
-                haveUnit = false;
-            }
-            if (!busy && haveUnit && sg < S) {
-                const LightSample ls = wf_sample(s, p, sg, pixel, ctrBase);
-                if (!ls.shadowed || shading_is_zero(s, frame, ls.pos)) {
-                    visOut[size_t(sg) * visStride] = 1; // the reference does not test this sample, or its term is exactly zero
-                    sg++;
-                } else {
-                    d = ls.pos - o;
-                    inv = v3(d.x != 0.0f ? fdiv(1.0f, d.x) : 3.0e38f, d.y != 0.0f ? fdiv(1.0f, d.y) : 3.0e38f,
-                        d.z != 0.0f ? fdiv(1.0f, d.z) : 3.0e38f);
-                    cur = s.n_prims ? s.froot : kDone;
-                    sp = 0;
-                    busy = true;
-                    nshadow++;
-                    if (cur == kDone) { // empty scene: nothing can block
-                        visOut[size_t(sg) * visStride] = 1;
-                        sg++;
-                        busy = false;
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, busy) == 0) {
-            if (drained && __ballot_sync(0xffffffffu, haveUnit && sg < S) == 0)
-                break;
-            continue;
-        }
-        // ---- B. inner nodes: step every lane that is on one, while enough of them are -----------------------------------
-        for (;;) {
-            const bool onInner = busy && cur < kDone;
-            const unsigned nInner = unsigned(__popc(__ballot_sync(0xffffffffu, onInner)));
-            const unsigned nBusy = unsigned(__popc(__ballot_sync(0xffffffffu, busy)));
-            if (nInner == 0 || (nInner < kInnerMin && nBusy > nInner) || (!drained && 32u - nBusy >= kRefill))
-                break;
-            if (onInner) { // same slab test as trace_fast with the constant bound t <= 1
-                const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
-                const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-                const float bound = 1.0001f;
-                const float lx0 = (q0.x - o.x) * inv.x, lx1 = (q0.w - o.x) * inv.x;
-                const float ly0 = (q0.y - o.y) * inv.y, ly1 = (q1.x - o.y) * inv.y;
-                const float lz0 = (q0.z - o.z) * inv.z, lz1 = (q1.y - o.z) * inv.z;
-                const float entL = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
-                const float extL = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
-                const bool hitL = entL <= extL * 1.000002f && entL <= bound;
-                const float rx0 = (q1.z - o.x) * inv.x, rx1 = (q2.y - o.x) * inv.x;
-                const float ry0 = (q1.w - o.y) * inv.y, ry1 = (q2.z - o.y) * inv.y;
-                const float rz0 = (q2.x - o.z) * inv.z, rz1 = (q2.w - o.z) * inv.z;
-                const float entR = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-                const float extR = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
-                const bool hitR = entR <= extR * 1.000002f && entR <= bound;
-                const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
-                const bool leftFirst = hitL && (!hitR || entL <= entR);
-                if (hitL && hitR)
-                    stack[sp++] = leftFirst ? cr : cl;
-                if (hitL || hitR) {
-                    cur = leftFirst ? cl : cr;
-                } else if (sp > 0) {
-                    cur = stack[--sp];
-                } else { // walked everything along the ray: the sample is visible
-                    visOut[size_t(sg) * visStride] = 1;
-                    sg++;
-                    busy = false;
-                    cur = kDone;
-                }
-            }
-        }
-        // ---- C. leaves: every lane that reached one tests its triangles (the archive's test against t <= 1) --------------
-        if (busy && cur > kDone) {
-            const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
-            bool occluded = false;
-            for (unsigned i = first; i < first + count && !occluded; i++) {
-                float t;
-                float4 r5;
-                occluded = triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, 1.0f, t, r5);
-            }
-            if (occluded || sp == 0) {
-                visOut[size_t(sg) * visStride] = occluded ? 0 : 1;
-                sg++;
-                busy = false;
-                cur = kDone;
-            } else {
-                cur = stack[--sp];
-            }
-        }
-    }
-    Counters cnt {};
-    cnt.shadow = nshadow;
-    flush_counters(cnt, gcnt);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// wf_vis_grouped_kernel: shadow rays in groups of kGroup consecutive samples per lane (lanes coupled, like wf_shade_kernel<false>,
-// but 16/kGroup times finer work items).  Used when a launch has too few direct-lighting evaluations per resident warp for the
-// 16-rays-per-lane granularity: on a 1/8 tile partition of C5 the coupled shade kernel left the SMs idle a third of its run
-// time (profiles/, smsp__cycles_active 5.3 M of 8.0 M).  Results go to the visibility bytes; wf_shade_kernel<true> shades.
-// ---------------------------------------------------------------------------------------------------------------------
 #ifndef CGE_MINB_VIS
 #define CGE_MINB_VIS 12 // resident 128-thread CTAs per SM the shadow-ray kernel is compiled for (A/B in DESIGN.md 5.5)
 #endif
-template <unsigned kGroup>
-__global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_grouped_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
-{
-    const unsigned lane = threadIdx.x & 31;
-    const bool fold = p.draws_per_hit == 0;
-    const unsigned S = p.samples_per_hit;
-    const unsigned groups = (S + kGroup - 1) / kGroup;
-    unsigned cum[kMaxLevels + 1]; // in units (direct-lighting evaluations)
-    cum[0] = 0;
-    for (unsigned k = 0; k < p.levels; k++)
-        cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
-    const unsigned long long total = (unsigned long long)cum[p.levels] * groups;
-    unsigned long long nshadow = 0;
-    if (!wf_use_visibility_bytes(p, wb))
-        return;
-    for (;;) {
-        unsigned chunk = 0;
-        if (lane == 0)
-            chunk = atomicAdd(wb.counts + 18, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const unsigned long long first = (unsigned long long)chunk * 32ull;
-        if (first >= total)
-            break;
-        const unsigned long long item = first + lane;
-        if (item >= total)
-            continue;
-        // item -> (level k, copy, sample group, slot): level-major, then copy, then group, then queue order
-        unsigned k = 0;
-        while (item >= (unsigned long long)cum[k + 1] * groups)
-            k++;
-        const unsigned inLevel = unsigned(item - (unsigned long long)cum[k] * groups), cnt = wb.counts[k];
-        const unsigned block = inLevel / cnt, e = inLevel - block * cnt;
-        const unsigned path = block / groups, g = block - path * groups;
-        const uint2 m = wb.meta[size_t(k) * wb.cap + e];
-        const unsigned ctrBase = wf_unit_ctr(p, k, path, m);
-        const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
-        const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
-        ShadeFrame frame {};
-        if (s.cull_zero_shading)
-            frame = wf_load_frame(wb, k, e);
-        unsigned char* visOut = wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e);
-        const unsigned sEnd = min(S, (g + 1u) * kGroup);
-        int occluder = -1; // the triangle that blocked this lane's previous sample: tested first (occluder coherence)
-        for (unsigned sg = g * kGroup; sg < sEnd; sg++) {
-            const LightSample ls = wf_sample(s, p, sg, wf_pixel(m), ctrBase);
-            unsigned char v = 1;
-            if (ls.shadowed && !shading_is_zero(s, frame, ls.pos)) {
-                nshadow++;
-                const vec3 d = ls.pos - o;
-                float t;
-                float4 r5;
-                // Any accepted triangle proves occlusion, whichever one the traversal would have met first; an accepted
-                // hit point lies inside its triangle and hence inside every (conservatively tested) ancestor box.
-                if (occluder >= 0 && triangle_rows_hit(s.ftris + size_t(occluder) * kTriRows, o, d, 1.0f, t, r5)) {
-                    v = 0;
-                } else {
-                    const int blocker = trace_shadow(s, o, d);
-                    if (blocker >= 0) {
-                        v = 0;
-                        occluder = blocker;
-                    }
-                }
-            }
-            visOut[size_t(sg) * cnt] = v;
-        }
-    }
-    Counters cnt {};
-    cnt.shadow = nshadow;
-    flush_counters(cnt, gcnt);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// wf_vis_regroup_kernel: the same work items as wf_vis_grouped_kernel (32 neighbouring hits x kGroup consecutive samples), but
-// the lanes of a warp trade hits between the samples.  A lane's kGroup rays are all long or all short (they start at the same
-// point and end on the same small light), so in wf_vis_grouped_kernel every one of the kGroup steps of a warp lasts as long
-// as the warp's longest hit.  Here step 0 is the same (every lane traces the first sample of its own hit, counting the nodes
+// wf_vis_regroup_kernel: every shadow ray of the frame, any-hit, one visibility byte per ray.  A work item is 32 neighbouring
+// hits (one per lane) x kGroup consecutive light samples, numbered level -> copy -> sample group -> queue slot, so a warp traces
+// the same samples for 32 neighbouring pixels.  The lanes of a warp trade hits between the samples: a lane's kGroup rays are all
+// long or all short (they start at the same point and end on the same small light), so with one hit per lane for all kGroup
+// steps (the form this kernel replaced) every step of a warp lasts as long as the warp's longest hit.  Here step 0 is the same (every lane traces the first sample of its own hit, counting the nodes
 // visited); then the 32 hits are ranked by that count and the remaining 32 x (kGroup - 1) rays are dealt out rank by rank:
 // the second step gets all remaining samples of the longest third of the hits, the last step those of the shortest third.
 // The hits are still the same 32 neighbouring pixels (the coherence of the node fetches is untouched), a hit's data travel
@@ -874,7 +452,7 @@ __global__ void __launch_bounds__(128, 8) wf_shade_kernel(DevScene s, DevParams 
         h.m.kd = v3(b[10 * c], b[11 * c], b[12 * c]);
         h.m.ks = v3(b[13 * c], b[14 * c], b[15 * c]);
         h.m.shininess = b[16 * c];
-        // ray index of this evaluation's sample 0 (see wf_visibility_kernel); consecutive samples are cnt bytes apart
+        // ray index of this evaluation's sample 0 (see wf_vis_regroup_kernel); consecutive samples are cnt bytes apart
         const unsigned char* vis = kLookup ? wb.vis + (size_t(cum[k]) * S + size_t(path) * S * cnt + e) : nullptr;
         const vec3 d = wf_direct<kLookup>(s, p, h, wf_pixel(m), ctr, nshadow, vis, cnt);
         float* out = wb.dir + wf_dir_off(p, wb.cap, k) + (size_t(path) * 3u) * wb.cap + e;
@@ -948,13 +526,13 @@ __global__ void __launch_bounds__(128) wf_fold_kernel(DevParams p, WaveBuffers w
     if (p.aa_side) { // one of the pixel's n x n camera rays: parked for wf_resolve_kernel, which adds them in the reference's order
         const unsigned nSub = p.aa_side * p.aa_side;
         const unsigned tile = (py / kTileH) * p.n_tiles_x + px / kTileW;
-        const unsigned k = (tile - p.part_index) / p.part_count - p.tile_first; // position of the tile in this launch's list
+        const unsigned k = part_entry_of(p.part_unit, p.part_index, p.part_count, tile) - p.tile_first; // position of the tile in this launch's list
         const size_t at = (size_t(k) * 32u + (py % kTileH) * kTileW + px % kTileW) * nSub + wf_sub_ray(m);
         const size_t plane = size_t(p.tile_count) * 32u * nSub;
         wb.sub[at] = out.x, wb.sub[plane + at] = out.y, wb.sub[2 * plane + at] = out.z;
         return;
     }
-    const size_t idx = size_t(p.height - 1 - int(py)) * size_t(p.width) + size_t(px);
+    const size_t idx = out_pixel_index(p, int(px), int(py));
     rgb[idx * 3 + 0] = out.x;
     rgb[idx * 3 + 1] = out.y;
     rgb[idx * 3 + 2] = out.z;
@@ -968,7 +546,7 @@ __global__ void __launch_bounds__(128) wf_resolve_kernel(DevParams p, WaveBuffer
     const unsigned k = g / 32u, lane = g % 32u;
     if (k >= p.tile_count)
         return;
-    const unsigned tile = p.part_index + (p.tile_first + k) * p.part_count;
+    const unsigned tile = part_tile_of(p.part_unit, p.part_index, p.part_count, p.tile_first + k);
     const int x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW), y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
     if (x >= p.width || y >= p.height)
         return;
@@ -980,7 +558,7 @@ __global__ void __launch_bounds__(128) wf_resolve_kernel(DevParams p, WaveBuffer
         color = color + v3(q[sub], q[plane + sub], q[2 * plane + sub]);
     color = color / float(int(nSub));
     const vec3 out = (v3(0.0f) + color) / 1.0f;
-    const size_t idx = size_t(p.height - 1 - y) * size_t(p.width) + size_t(x);
+    const size_t idx = out_pixel_index(p, x, y);
     rgb[idx * 3 + 0] = out.x;
     rgb[idx * 3 + 1] = out.y;
     rgb[idx * 3 + 2] = out.z;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CGE_ABI_VERSION 2
+#define CGE_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------------------ */
 enum {
@@ -160,37 +160,32 @@ enum {
     CGE_TRAVERSAL_FAST = 1       /* binned-SAH tree (<= 4 primitives per leaf), near child first, conservative t culling,
                                     shadow rays stop at the first blocker; equal-t winner chosen by the reference's
                                     visit rank; with area lights a wavefront pipeline over warp-compacted hit queues, otherwise
-                                    one thread per pixel.  Scenes with spheres and
-                                    !enableAccelStructure fall back to the literal traversal. */
+                                    one thread per pixel. */
 };
 enum {
     CGE_SAMPLER_HASH = 0 /* rand() replaced by hash(seed, pixel, draw index) — see DESIGN.md "sampler" */
 };
 enum {
-    CGE_FLAG_WANT_PRIM_IDS = 1u << 0,
-    CGE_FLAG_RGB_DEVICE_PTR = 1u << 1, /* rgb_out / prim_id_out are device pointers on the calling GPU:
-                                          no D2H copy (kernel-only timing, or a caller that keeps the frame in HBM) */
-    CGE_FLAG_COUNT_TESTS = 1u << 2,    /* fill cge_stats::box_tests / tri_tests (with CGE_TRAVERSAL_REFERENCE they equal
-                                          the reference's own intersectRayWithShape/Triangle call counts) */
-    CGE_FLAG_DEBUG_CYCLES = 1u << 4,   /* (implies the per-thread kernel) */
-    CGE_FLAG_PER_THREAD = 1u << 5,
-    CGE_FLAG_COUPLED_SHADE = 1u << 7,   /* wavefront: always 16 coupled shadow rays per lane (disable the small-launch heuristic) */
-    CGE_FLAG_GROUPED_SHADE = 1u << 8,   /* wavefront: trace shadow rays 4 per lane into visibility bytes (the default for area lights) */
-    CGE_FLAG_AUTO_SHADE = 1u << 9,
-    CGE_FLAG_WAVEFRONT = 1u << 10,
-    CGE_FLAG_CHAIN_PER_LEVEL = 1u << 12, /* wavefront: one launch per recursion level over compacted bounce queues (wf_primary_kernel +
-                                            wf_bounce_kernel) instead of one lane per pixel chain (wf_chain_kernel, the default):
-                                            measured slower, kept for A/B */
-    CGE_FLAG_OUTPUT_RGBA8 = 1u << 11,   /* rgb_out is a uint8_t[W*H*4] RGBA buffer: the frame goes through the output stage of
-                                           Screen::writeBitmapToFile (src/screen.cpp:49-60: clamp to [0,1], *255, truncate, alpha
-                                           255; NaN -> 0) on the GPU, so the D2H copy is 4 instead of 12 bytes per pixel */      /* use the wavefront pipeline even for point-light frames (default there: per-thread kernel) */      /* wavefront: pick coupled / grouped on the device from the queue lengths */
-    CGE_FLAG_DECOUPLED_SHADE = 1u << 6, /* wavefront: trace the shadow rays in the lane-decoupled wf_visibility_kernel (one ray
-                                          per lane, idle lanes refilled through ballot + one atomic) and shade from its
-                                          visibility bytes, instead of 16 coupled rays per lane inside wf_shade_kernel.
-                                          Wins on small / sparse frames, loses ~15 % at the judged sizes */     /* CGE_TRAVERSAL_FAST: one-thread-per-pixel kernel instead of the wavefront pipeline */
-    CGE_FLAG_DEBUG_CYCLES_ = 0,   /* development aid: prim_id_out receives each pixel's cost (SM cycles >> 4) */
-    CGE_FLAG_COOPERATIVE = 1u << 3     /* CGE_TRAVERSAL_FAST: use the single-kernel warp-cooperative shadow-queue variant
-                                          instead of the wavefront pipeline (A/B measurements; DESIGN.md "Kernels") */
+    CGE_FLAG_WANT_PRIM_IDS = 1u << 0,  /* fill prim_id_out */
+    CGE_FLAG_RGB_DEVICE_PTR = 1u << 1, /* rgb_out / prim_id_out are device pointers on the calling GPU: no D2H copy (a caller that
+                                          keeps the frame in HBM, or kernel-only timing) */
+    CGE_FLAG_COUNT_TESTS = 1u << 2,    /* fill cge_stats::box_tests / tri_tests (with CGE_TRAVERSAL_REFERENCE they equal the
+                                          reference's own intersectRayWithShape / intersectRayWithTriangle call counts) */
+    CGE_FLAG_OUTPUT_RGBA8 = 1u << 3,   /* rgb_out is a uint8_t[W*H*4] RGBA host buffer: the frame goes through the output stage of
+                                          Screen::writeBitmapToFile (src/screen.cpp:49-60: clamp to [0,1], *255, truncate, alpha 255;
+                                          NaN -> 0) on the GPU, so the D2H copy is 4 instead of 12 bytes per pixel */
+    CGE_FLAG_PARTITION_TILE_ROWS = 1u << 4, /* part_index / part_count deal whole tile rows (runs of 4 complete image rows) instead
+                                          of single 8x4 tiles; cge_render_distributed always partitions this way */
+    CGE_FLAG_SHARED_HOST_FRAME = 1u << 5    /* cge_render_distributed: rgb_out is the frame cge_comm_host_frame returned (the same
+                                          on every rank); each rank copies the rows it rendered straight into it over its own
+                                          PCIe link instead of rank 0 gathering the frame and copying all of it */
+};
+/* Development switches (A/B measurements and the tests that prove both production pipelines bit-identical); not needed by a
+ * caller, every setting renders the same frame. */
+enum {
+    CGE_DEV_FLAG_PER_THREAD = 1u << 16,  /* CGE_TRAVERSAL_FAST: one thread per pixel even for area-light frames (default there: wavefront) */
+    CGE_DEV_FLAG_WAVEFRONT = 1u << 17,   /* CGE_TRAVERSAL_FAST: wavefront pipeline even for point-light frames (default there: per thread) */
+    CGE_DEV_FLAG_DEBUG_CYCLES = 1u << 18 /* prim_id_out receives each pixel's cost in SM cycles >> 4 (implies the per-thread kernel) */
 };
 
 typedef struct cge_params {
@@ -325,11 +320,20 @@ typedef struct cge_comm cge_comm; /* opaque NCCL communicator wrapper */
 int cge_comm_unique_id(uint8_t id_out[CGE_UNIQUE_ID_BYTES]); /* rank 0 calls, broadcasts by any host means */
 int cge_comm_create(const uint8_t id[CGE_UNIQUE_ID_BYTES], int rank, int n_ranks, int device, cge_comm** out);
 int cge_comm_destroy(cge_comm* comm);
-/* Render this rank's interleaved tile subset (part_index/part_count are overwritten with rank/n_ranks), pack
- * the rendered tiles contiguously, ncclSend them to rank 0, which unpacks all ranks' tiles into the full frame
- * and (unless CGE_FLAG_RGB_DEVICE_PTR) copies it to rgb_out.  rgb_out / prim_id_out are only written on rank 0. */
+/* Render this rank's share of the frame - tile rows rank, rank + n_ranks, ... (part_index / part_count are overwritten with
+ * rank / n_ranks, CGE_FLAG_PARTITION_TILE_ROWS is implied) - and deliver the frame on rank 0:
+ *   default                      the other ranks render into a compact buffer that holds just their rows and ncclSend it as it is;
+ *                                rank 0 renders into the frame, receives, scatters every rank's rows in one launch and (unless
+ *                                CGE_FLAG_RGB_DEVICE_PTR) copies the frame to rgb_out.  rgb_out / prim_id_out are only used on rank 0.
+ *   CGE_FLAG_SHARED_HOST_FRAME   rgb_out (and prim_id_out) are frames from cge_comm_host_frame, the same memory on every rank: each
+ *                                rank copies the rows it rendered straight into it over its own PCIe link (one strided copy), and a
+ *                                4-byte all-reduce tells every rank when the frame is complete.  No device-side gather at all.
+ * The image does not depend on the number of ranks (bit-identical to cge_render). */
 int cge_render_distributed(cge_scene* scene, cge_comm* comm, const cge_camera* camera, const cge_params* params,
                            float* rgb_out, int32_t* prim_id_out, cge_stats* stats_out);
+/* Collective over the communicator: `bytes` of host memory mapped by every rank (POSIX shared memory, page-locked in each
+ * process), for CGE_FLAG_SHARED_HOST_FRAME.  *out is this process's address of it.  Released by cge_comm_destroy. */
+int cge_comm_host_frame(cge_comm* comm, uint64_t bytes, void** out);
 
 /* pinned host memory for rgb_out / prim_id_out so the D2H copy runs at full PCIe speed (optional) */
 int cge_host_alloc(void** out, uint64_t bytes);

@@ -42,8 +42,9 @@ def assert_parity(name, rgb, ids, ref_rgb, ref_ids, id_budget=ID_MISMATCH_BUDGET
     assert err <= RGB_TOL * scale, f"{name}: max abs err {err} (scale {scale})"
 
 
-# (traversal, flags): literal traversal with test counters / fast tree per-thread kernel / fast tree cooperative kernel
-MODES = {"reference": (0, 4), "fast-default": (1, 0), "fast-wave": (1, 1024), "fast-wave-decoupled": (1, 1024 | 64), "fast-wave-grouped": (1, 1024 | 256), "fast-wave-coupled": (1, 1024 | 128), "fast-wave-auto": (1, 1024 | 512), "fast-wave-chain-per-level": (1, 1024 | 4096), "fast-thread": (1, 32), "fast-coop": (1, 8)}
+# (traversal, flags): literal traversal with test counters / fast tree with the default pipeline of the frame / fast tree with
+# the wavefront pipeline forced / fast tree with the per-thread kernel forced (include/cge.h CGE_FLAG_COUNT_TESTS, CGE_DEV_FLAG_*)
+MODES = {"reference": (0, 4), "fast-default": (1, 0), "fast-wave": (1, 1 << 17), "fast-thread": (1, 1 << 16)}
 
 
 @pytest.mark.parametrize("name", list(SMALL))
@@ -165,9 +166,8 @@ def test_full_size_properties(cge, name):
         rgb_r, ids_r, st_r = sc.render(cfg, traversal=0)
         assert (ids_f != ids_r).mean() <= ID_MISMATCH_BUDGET
         assert st_f["reference_rays"] == st_r["reference_rays"]
-        # wavefront, per-thread and cooperative kernels walk the same tree with the same arithmetic: identical bits
-        W = cge.FLAG_WAVEFRONT
-        for fl in (cge.FLAG_PER_THREAD, cge.FLAG_COOPERATIVE, W, W | cge.FLAG_DECOUPLED_SHADE, W | cge.FLAG_GROUPED_SHADE, W | cge.FLAG_COUPLED_SHADE, W | cge.FLAG_AUTO_SHADE, W | cge.FLAG_CHAIN_PER_LEVEL):
+        # the two production pipelines (one thread per pixel, wavefront) walk the same tree with the same arithmetic: identical bits
+        for fl in (cge.FLAG_PER_THREAD, cge.FLAG_WAVEFRONT):
             rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=fl)
             assert st_t["reference_rays"] == st_f["reference_rays"] and st_t["gpu_rays"] == st_f["gpu_rays"]
             assert np.array_equal(ids_t, ids_f) and rgb_t.tobytes() == rgb_f.tobytes()
@@ -243,14 +243,14 @@ def test_partition_matches_host_tile_list(cge):
     W, H = cfg["width"], cfg["height"]
     ntx = (W + 7) // 8
     with cge.Scene(cge.load_scene(cfg)) as sc:
-        for parts in (2, 3, 8):
+        for parts, rows in ((2, False), (3, False), (8, False), (2, True), (3, True), (8, True)):
             for k in range(parts):
                 ids = np.full((H, W), -7, np.int32)
                 rgb = np.full((H, W, 3), -7.0, np.float32)
-                sc.render(cfg, rgb_out=rgb, ids_out=ids, part=(k, parts))
+                sc.render(cfg, rgb_out=rgb, ids_out=ids, part=(k, parts), flags=cge.FLAG_PARTITION_TILE_ROWS if rows else 0)
                 touched = ids != -7
                 expect = np.zeros((H, W), bool)
-                for t in cge.partition_tiles(W, H, k, parts):
+                for t in cge.partition_tiles(W, H, k, parts, tile_rows=rows):
                     tx, ty = t % ntx, t // ntx
                     y0, y1 = ty * 4, min(ty * 4 + 4, H)
                     expect[H - y1:H - y0, tx * 8:min(tx * 8 + 8, W)] = True
@@ -334,7 +334,7 @@ def test_zero_shading_cull_changes_no_bit(cge, name, monkeypatch):
     w, h = SMALL[name]
     cfg = cge.configs.get(name, w * 2, h * 2)
     with cge.Scene(cge.load_scene(cfg)) as sc:
-        for flags in (0, cge.FLAG_PER_THREAD, cge.FLAG_WAVEFRONT | cge.FLAG_GROUPED_SHADE, cge.FLAG_WAVEFRONT | cge.FLAG_COUPLED_SHADE):
+        for flags in (0, cge.FLAG_PER_THREAD, cge.FLAG_WAVEFRONT):
             monkeypatch.setenv("CGE_ZERO_SHADING_CULL", "0")
             rgb0, ids0, st0 = sc.render(cfg, traversal=1, flags=flags)
             monkeypatch.setenv("CGE_ZERO_SHADING_CULL", "1")

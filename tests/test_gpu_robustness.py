@@ -96,3 +96,20 @@ def test_partition_to_host_memory_is_few_large_copies(cge):
         dt = time.time() - t0
         assert rgb.tobytes() == full.tobytes() and np.array_equal(ids, full_ids)
         assert dt < 1.0, dt
+
+
+def test_compact_row_layout_of_the_distributed_ranks(cge):
+    """What a rank of cge_render_distributed does, on one GPU: the tile-row partition (CGE_FLAG_PARTITION_TILE_ROWS) of every
+    part reassembles to the full frame bit for bit, ragged sizes included (cge_render scatters a part's packed tiles on the
+    host; the ranks' compact device layout is exercised by tools/multi_gpu_check.py and bench.py under torchrun)."""
+    for name, size in (("c3_teapot_soft", (203, 117)), ("c4_monkey_mirror", (256, 144)), ("c1_cornell", (64, 61))):
+        cfg = cge.configs.get(name, *size)
+        H, W = cfg["height"], cfg["width"]
+        with cge.Scene(cge.load_scene(cfg)) as sc:
+            full, full_ids, _ = sc.render(cfg)
+            for parts in (2, 3, 8):
+                rgb = np.full((H, W, 3), -7.0, np.float32)
+                ids = np.full((H, W), -9, np.int32)
+                for k in range(parts):
+                    sc.render(cfg, rgb_out=rgb, ids_out=ids, part=(k, parts), flags=cge.FLAG_PARTITION_TILE_ROWS)
+                assert rgb.tobytes() == full.tobytes() and np.array_equal(ids, full_ids), (name, parts)

@@ -1,9 +1,10 @@
 """CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path.
 
-The frame is partitioned by interleaved 8x4 tiles (rank r renders tiles r, r+N, r+2N, ...; cge_render's part_index /
-part_count).  Each rank derives its tile list independently; here two gloo ranks exchange them and check that the lists
-are disjoint, cover every tile exactly once, are balanced to within one tile, and that bench.py's reference arm obeys the
-'rank 0 prints, the others exit 0 without work' rule under torch.distributed.run."""
+The frame is partitioned into units of 8x4 tiles dealt round robin (cge_render's part_index / part_count): single tiles
+(rank r renders tiles r, r+N, ...) or, as cge_render_distributed does, whole tile rows (rank r renders tile rows r, r+N, ...).
+Each rank derives its tile list independently; here two gloo ranks exchange them and check that the lists are disjoint, cover
+every tile exactly once, are balanced to within one unit, and that bench.py's reference arm obeys the 'rank 0 prints, the
+others exit 0 without work' rule under torch.distributed.run."""
 import json
 import os
 import subprocess
@@ -24,14 +25,17 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
 for (w, h) in [(3840, 2160), (1024, 1024), (33, 17), (8, 4), (7, 3)]:
-    mine = pkg.partition_tiles(w, h, rank, world)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, mine)
-    allt = sorted(t for g in gathered for t in g)
-    n_tiles = ((w + 7) // 8) * ((h + 3) // 4)
-    ok &= allt == list(range(n_tiles))
-    ok &= max(len(g) for g in gathered) - min(len(g) for g in gathered) <= 1
-    ok &= all(t % world == r for r, g in enumerate(gathered) for t in g)
+    for rows in (False, True):
+        mine = pkg.partition_tiles(w, h, rank, world, tile_rows=rows)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        allt = sorted(t for g in gathered for t in g)
+        tiles_x = (w + 7) // 8
+        n_tiles = tiles_x * ((h + 3) // 4)
+        unit = tiles_x if rows else 1
+        ok &= allt == list(range(n_tiles))
+        ok &= max(len(g) for g in gathered) - min(len(g) for g in gathered) <= unit
+        ok &= all((t // unit) % world == r for r, g in enumerate(gathered) for t in g)
 flag = torch.tensor([1 if ok else 0])
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -1,4 +1,4 @@
-"""Per-pixel cost map of a config (CGE_FLAG_DEBUG_CYCLES): where does the frame time go?"""
+"""Per-pixel cost map of a config (CGE_DEV_FLAG_DEBUG_CYCLES): where does the frame time go?"""
 import importlib, sys
 from pathlib import Path
 import numpy as np
@@ -11,8 +11,8 @@ if len(sys.argv) > 2:
     cfg["features"] = int(sys.argv[2], 0)
 with pkg.Scene(pkg.load_scene(cfg)) as sc:
     sc.render(cfg)
-    rgb, cost, st = sc.render(cfg, flags=16 | 32)
-    _, nb, stc = sc.render(cfg, flags=16 | 4 | 32)
+    rgb, cost, st = sc.render(cfg, flags=pkg.FLAG_DEBUG_CYCLES | pkg.FLAG_PER_THREAD)
+    _, nb, stc = sc.render(cfg, flags=pkg.FLAG_DEBUG_CYCLES | pkg.FLAG_COUNT_TESTS | pkg.FLAG_PER_THREAD)
     _, ids, _ = sc.render(cfg)
 print("fast-tree box tests / ray", stc["box_tests"] / stc["gpu_rays"], "tri tests / ray", stc["tri_tests"] / stc["gpu_rays"])
 nbt = nb[: nb.shape[0] // 4 * 4, : nb.shape[1] // 8 * 8].reshape(nb.shape[0] // 4, 4, nb.shape[1] // 8, 8)

@@ -17,24 +17,44 @@ dist.broadcast(idt, 0)
 comm = pkg.Comm(bytes(idt.cpu().numpy().tobytes()), rank, world, local)
 ok = True
 # "+bloom" / "+aa" after a config name switch the implemented ExtraFeatures on (bloom runs on rank 0 after the gather)
-for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_soft:0.5", "c5_dragon:0.25", "c1_cornell+bloom+aa:0.5"]):
+for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_soft:0.5", "c5_dragon:0.25", "c1_cornell+bloom+aa:0.5",
+                              "c4_monkey_mirror+ragged:0.37"]):
     name, scale = (spec.split(":") + ["1.0"])[:2]
     name, *extras = name.split("+")
     full = pkg.configs.get(name)
-    cfg = pkg.configs.get(name, int(full["width"] * float(scale)), int(full["height"] * float(scale)))
+    cfg = pkg.configs.get(name, int(full["width"] * float(scale)) + (3 if "ragged" in extras else 0),
+                          int(full["height"] * float(scale)) + (1 if "ragged" in extras else 0))
     if "bloom" in extras:
         cfg["features"] |= pkg.configs.FEAT_BLOOM_EFFECT
     if "aa" in extras:
         cfg["features"] |= pkg.configs.FEAT_MULTIPLE_RAYS_PER_PIXEL
         cfg["rays_per_pixel_side"] = 2
+    H, W = cfg["height"], cfg["width"]
+    shared_rgb, shared_ids = comm.host_frame((H, W, 3), np.float32), comm.host_frame((H, W), np.int32)
     with pkg.Scene(pkg.load_scene(cfg), device=local) as sc:
         rgb, ids, st = comm.render(sc, cfg, want_ids=True)
         dist.barrier()
+        # the same frame with every rank writing its own rows into the shared host frame (no gather)
+        shared_rgb[:] = -7.0
+        shared_ids[:] = -7
+        dist.barrier()
+        _, _, sts = comm.render(sc, cfg, want_ids=True, shared_frame=shared_rgb, shared_ids=shared_ids)
+        rgba = np.zeros((H, W, 4), np.uint8)
+        import ctypes as C
+        p8 = pkg.params_from_cfg(cfg, pkg.TRAVERSAL_FAST, False, (0, 1), pkg.FLAG_OUTPUT_RGBA8)
+        cam8, st8 = pkg.camera_from_cfg(cfg), pkg.CgeStats()
+        rc8 = pkg.lib().cge_render_distributed(sc.handle, comm.handle, C.byref(cam8), C.byref(p8), rgba.ctypes.data if rank == 0 else None,
+                                               None, C.byref(st8))
         if rank == 0:
             rgb1, ids1, st1 = sc.render(cfg, want_ids=True)
+            rgba1, _ = sc.render_rgba8(cfg)
             same = rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1)
-            ok &= same
+            same_shared = shared_rgb.tobytes() == rgb1.tobytes() and np.array_equal(shared_ids, ids1)
+            same8 = rc8 == 0 and np.array_equal(rgba, rgba1)
+            ok &= same and same_shared and same8
             print(json.dumps({"cfg": spec, "w": cfg["width"], "h": cfg["height"], "ranks": world, "bit_identical_to_1gpu": bool(same),
+                              "shared_host_frame_identical": bool(same_shared), "rgba8_identical": bool(same8),
+                              "shared_total_ms": round(sts["total_ms"], 3),
                               "dist_total_ms": round(st["total_ms"], 3), "dist_kernel_ms_rank0": round(st["kernel_ms"], 3),
                               "single_kernel_ms": round(st1["kernel_ms"], 3), "launches_rank0": st["kernel_launches"]}), flush=True)
         dist.barrier()

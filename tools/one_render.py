@@ -1,4 +1,4 @@
-"""Render one config a few times in one mode (profiling target).  usage: one_render.py cfg mode[fast-thread|fast-coop|reference] [n] [scale]"""
+"""Render one config a few times in one mode (profiling target).  usage: one_render.py cfg mode[fast-default|fast-wave|fast-thread|reference] [n] [scale]"""
 import importlib, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -9,7 +9,7 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 scale = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 full = pkg.configs.get(name)
 cfg = pkg.configs.get(name, int(full["width"] * scale), int(full["height"] * scale))
-trav, flags = {"fast-default": (1, 0), "fast-wave": (1, pkg.FLAG_WAVEFRONT), "fast-wave-decoupled": (1, pkg.FLAG_WAVEFRONT | pkg.FLAG_DECOUPLED_SHADE), "fast-thread": (1, pkg.FLAG_PER_THREAD), "fast-coop": (1, pkg.FLAG_COOPERATIVE), "reference": (0, 0)}[mode]
+trav, flags = {"fast-default": (1, 0), "fast-wave": (1, pkg.FLAG_WAVEFRONT), "fast-thread": (1, pkg.FLAG_PER_THREAD), "reference": (0, 0)}[mode]
 with pkg.Scene(pkg.load_scene(cfg)) as sc:
     for _ in range(n):
         _, _, st = sc.render(cfg, traversal=trav, want_ids=False, flags=flags)

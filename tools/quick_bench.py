@@ -15,9 +15,9 @@ for name in names:
     t0 = time.time(); flat = pkg.load_scene(cfg); t1 = time.time()
     with pkg.Scene(flat) as sc:
         t2 = time.time()
-        modes = [(1, 0, "fast-default"), (1, pkg.FLAG_WAVEFRONT, "fast-wave"), (1, pkg.FLAG_WAVEFRONT | pkg.FLAG_COUPLED_SHADE, "fast-wave-coupled"), (1, pkg.FLAG_WAVEFRONT | pkg.FLAG_DECOUPLED_SHADE, "fast-wave-decoupled"), (1, pkg.FLAG_PER_THREAD, "fast-thread"), (1, pkg.FLAG_COOPERATIVE, "fast-coop"), (0, 0, "reference")]
+        modes = [(1, 0, "fast-default"), (1, pkg.FLAG_WAVEFRONT, "fast-wave"), (1, pkg.FLAG_PER_THREAD, "fast-thread"), (0, 0, "reference")]
         if name == "c5_dragon" and scale > 0.3:
-            modes = modes[:6]
+            modes = modes[:3]
         for trav, flags, label in modes:
             best = None
             for it in range(3):

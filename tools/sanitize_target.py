@@ -9,10 +9,10 @@ W = pkg.FLAG_WAVEFRONT
 for name, (w, h) in {"c1_cornell": (64, 64), "c2_cube_textured": (64, 36), "c3_teapot_soft": (48, 28), "c4_monkey_mirror": (48, 28)}.items():
     cfg = pkg.configs.get(name, w, h)
     with pkg.Scene(pkg.load_scene(cfg)) as sc:
-        for trav, fl in [(0, 4), (1, 0), (1, W), (1, W | pkg.FLAG_COUPLED_SHADE), (1, W | pkg.FLAG_DECOUPLED_SHADE), (1, W | pkg.FLAG_AUTO_SHADE),
-                         (1, pkg.FLAG_PER_THREAD), (1, pkg.FLAG_COOPERATIVE), (1, W | pkg.FLAG_CHAIN_PER_LEVEL)]:
+        for trav, fl in [(0, 4), (1, 0), (1, W), (1, pkg.FLAG_PER_THREAD)]:
             sc.render(cfg, traversal=trav, flags=fl)
             sc.render(cfg, traversal=trav, flags=fl, part=(1, 3))
+            sc.render(cfg, traversal=trav, flags=fl | pkg.FLAG_PARTITION_TILE_ROWS, part=(1, 3))
         C = pkg.configs
         for extra, kw in ((C.FEAT_MULTIPLE_RAYS_PER_PIXEL, {"rays_per_pixel_side": 2}), (C.FEAT_BLOOM_EFFECT, {}),
                           (C.FEAT_BLOOM_EFFECT | C.FEAT_MULTIPLE_RAYS_PER_PIXEL, {"rays_per_pixel_side": 3})):
@@ -28,6 +28,6 @@ for name, (w, h) in {"c1_cornell": (64, 64), "c2_cube_textured": (64, 36), "c3_t
 flat = pkg.standin.make("dragon", n=24)
 cfg = pkg.configs.get("c5_dragon", 48, 28)
 with pkg.Scene(flat) as sc:
-    for fl in (0, W | pkg.FLAG_DECOUPLED_SHADE, pkg.FLAG_PER_THREAD, pkg.FLAG_COOPERATIVE):
+    for fl in (0, pkg.FLAG_PER_THREAD):
         sc.render(cfg, flags=fl)
 print("dragon ok")
