@@ -128,7 +128,8 @@ struct cge_scene {
     int device = 0;
     int sm_count = 0;
     DevScene dev {};
-    DevBuf<float4> nodes, tris, fnodes, ftris, shade, materials;
+    DevBuf<float4> nodes, tris, fnodes, ftris, shade, materials, sph_rows, sph_boxes;
+    DevBuf<uint32_t> sph_box_off, fpos;
     DevBuf<uint4> qnodes;
     FastBvh fast;
     bool fast_built_on_gpu = false;
@@ -460,6 +461,7 @@ DevScene scene_for(const cge_scene* sc, const cge_params& p, const LightSet& ls)
     d.lights = ls.dev;
     d.n_lights = ls.n;
     d.cull_zero_shading = sc->colours_bounded && light_colours_bounded(ls.host) && env_int("CGE_ZERO_SHADING_CULL", 1);
+    d.noaccel = (p.features & CGE_FEAT_ACCEL_STRUCTURE) ? 0u : 1u;
     if (p.features & CGE_FEAT_ACCEL_STRUCTURE) {
         d.root_ref = sc->accel_root_ref;
         d.root_count = sc->accel_root_count;
@@ -556,9 +558,10 @@ __global__ void bloom_apply_kernel(float* __restrict__ rgb, const float* __restr
 }
 
 // Which kernels a call runs.
-//   fast     : CGE_TRAVERSAL_FAST over the SAH tree (enableAccelStructure on, no spheres: the archive's sphere test assumes a
-//              unit direction, so with shadow rays its result depends on which boxes the REFERENCE tree lets through; sphere
-//              scenes are walked literally), else the literal traversal of the reference-order tree.
+//   fast     : CGE_TRAVERSAL_FAST over the SAH tree of the triangles, with the scene's spheres tested beside it (the archive's
+//              sphere test assumes a unit direction, so with shadow rays its result depends on which boxes the REFERENCE tree
+//              lets through: each sphere carries that box chain, trace.cuh sphere_reached); else the literal traversal of the
+//              reference-order tree.
 //   count    : box / triangle test counters (CGE_FLAG_COUNT_TESTS; per-thread kernel).
 //   wave     : the wavefront pipeline (wavefront.cuh) instead of the per-thread kernel.
 struct Variant {
@@ -566,6 +569,7 @@ struct Variant {
     size_t waveBytes;
 };
 
+constexpr unsigned kMaxFastSpheres = 64;
 constexpr size_t kWaveScratchLimit = size_t(24) << 30; // queues larger than this fall back to the per-thread kernel
 
 struct WaveSizes {
@@ -591,7 +595,10 @@ Variant choose_variant(const DevScene& ds, const cge_params& p, const DevParams&
 {
     Variant v {};
     v.spheres = ds.has_spheres != 0;
-    v.fast = p.traversal == CGE_TRAVERSAL_FAST && (p.features & CGE_FEAT_ACCEL_STRUCTURE) && !v.spheres;
+    // The fast tree serves every CGE_TRAVERSAL_FAST frame: spheres are tested beside it behind the reference tree's box chain,
+    // and a frame without enableAccelStructure is the same minimum-t answer with the tie rank of the reference's primitive
+    // vector (trace.cuh).  More spheres than a linear pass should carry fall back to the literal traversal.
+    v.fast = p.traversal == CGE_TRAVERSAL_FAST && ds.n_sph <= kMaxFastSpheres;
     v.count = (p.flags & CGE_FLAG_COUNT_TESTS) != 0;
     const size_t cap = size_t(dp.tile_count) * 32 * sub_rays(dp);
     v.waveBytes = wave_sizes(dp, std::max<size_t>(cap, 1)).bytes();
@@ -1130,28 +1137,43 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
         }
     }
     auto in_order = [&](const std::vector<uint32_t>& order) {
-        std::vector<float4> out(size_t(nPrims) * kTriRows);
-        for (uint32_t i = 0; i < nPrims; i++)
-            std::memcpy(&out[size_t(i) * kTriRows], &recs[size_t(order[i]) * kTriRows], sizeof(float4) * kTriRows);
+        std::vector<float4> out(order.size() * kTriRows);
+        for (size_t i = 0; i < order.size(); i++)
+            std::memcpy(&out[i * kTriRows], &recs[size_t(order[i]) * kTriRows], sizeof(float4) * kTriRows);
         return out;
     };
     std::vector<float4> tris = haveBvh ? in_order(sc->bvh.prim_order) : std::vector<float4>();
 
-    // ---- fast tree (binned SAH, <= 4 primitives per leaf) for CGE_TRAVERSAL_FAST; triangles-only scenes ---------------
+    // ---- fast tree (binned SAH, <= 4 primitives per leaf) for CGE_TRAVERSAL_FAST: over the TRIANGLES; spheres are kept beside
+    //      it (below) -------------------------------------------------------------------------------------------------------
     std::vector<float4> ftris, fnodes;
-    if (haveBvh && d->n_spheres == 0) {
+    std::vector<uint32_t> fpos;
+    cge_scene_desc triDesc = *d;
+    triDesc.n_spheres = 0;
+    triDesc.spheres = nullptr;
+    triDesc.bvh_nodes = nullptr;
+    triDesc.bvh_prim_order = nullptr;
+    triDesc.n_bvh_nodes = 0;
+    if (haveBvh && d->n_triangles > 0) {
         // built on the GPU (bvh_sah_gpu.cu); the host builder produces the identical tree and serves scenes with non-finite
         // coordinates.  CGE_SAH_BUILD=host forces it (A/B timing, tests).
         const char* forced = std::getenv("CGE_SAH_BUILD");
-        const bool onGpu = sah_gpu_supported(*d) && !(forced && std::string(forced) == "host");
+        const bool onGpu = sah_gpu_supported(triDesc) && !(forced && std::string(forced) == "host");
         std::string buildErr;
-        const bool ok = onGpu ? build_sah_bvh_gpu(*d, sc->fast, &sc->fast_build_ms, &buildErr) : build_sah_bvh(*d, sc->fast);
+        const bool ok = onGpu ? build_sah_bvh_gpu(triDesc, sc->fast, &sc->fast_build_ms, &buildErr) : build_sah_bvh(triDesc, sc->fast);
         sc->fast_built_on_gpu = onGpu;
         if (!ok || sc->fast.depth > uint32_t(kFastStackSize - 2)) {
             delete sc;
             return fail(ok ? CGE_ERR_UNSUPPORTED : CGE_ERR_CUDA, buildErr.empty() ? "fast BVH build failed" : buildErr);
         }
         ftris = in_order(sc->fast.prim_order);
+        // position of every fast-tree primitive in the reference's primitive vector: the tie rank without enableAccelStructure
+        std::vector<uint32_t> posOf(nPrims, 0);
+        for (uint32_t i = 0; i < nPrims; i++)
+            posOf[sc->bvh.prim_order[i]] = i;
+        fpos.resize(sc->fast.prim_order.size());
+        for (size_t i = 0; i < fpos.size(); i++)
+            fpos[i] = posOf[sc->fast.prim_order[i]];
         fnodes.resize(sc->fast.nodes.size() * kNodeRows);
         for (size_t i = 0; i < sc->fast.nodes.size(); i++) {
             const FastNode& n = sc->fast.nodes[i];
@@ -1171,6 +1193,31 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     if (!sc->fast.nodes.empty())
         quantise_fast_nodes(sc->fast, qnodes, qlo, qext);
 #endif
+
+    // ---- spheres beside the fast tree: their rows and, per sphere, the boxes the reference's traversal tests on its way to the
+    //      sphere's leaf - the nodes below the root on the path to it (the root's own box is never tested, :312-361) --------------
+    std::vector<float4> sphRows, sphBoxes;
+    std::vector<uint32_t> sphBoxOff { 0 };
+    if (haveBvh && d->n_spheres) {
+        std::vector<uint32_t> posOf(nPrims, 0);
+        for (uint32_t i = 0; i < nPrims; i++)
+            posOf[sc->bvh.prim_order[i]] = i;
+        for (uint32_t k = 0; k < d->n_spheres; k++) {
+            const uint32_t gid = d->n_triangles + k, pos = posOf[gid];
+            const float4* rec = &recs[size_t(gid) * kTriRows];
+            sphRows.insert(sphRows.end(), rec, rec + kTriRows);
+            sphRows[sphRows.size() - kTriRows + 2].x = bitsf(pos);
+            uint32_t ni = sc->bvh.root;
+            while (!sc->bvh.nodes[ni].is_leaf) {
+                const auto& n = sc->bvh.nodes[ni];
+                ni = pos < sc->bvh.nodes[n.left].end ? n.left : n.right; // children split [beg, mid) | [mid, end)
+                const auto& c = sc->bvh.nodes[ni];
+                sphBoxes.push_back(f4(c.lower[0], c.lower[1], c.lower[2], 0.0f));
+                sphBoxes.push_back(f4(c.upper[0], c.upper[1], c.upper[2], 0.0f));
+            }
+            sphBoxOff.push_back(uint32_t(sphBoxes.size() / 2));
+        }
+    }
 
     // ---- inner nodes: each carries both child boxes ----------------------------------------------------------
     std::vector<float4> nodes;
@@ -1245,6 +1292,10 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     up(sc->fnodes, fnodes);
     up(sc->qnodes, qnodes);
     up(sc->ftris, ftris);
+    up(sc->sph_rows, sphRows);
+    up(sc->sph_boxes, sphBoxes);
+    up(sc->sph_box_off, sphBoxOff);
+    up(sc->fpos, fpos);
     up(sc->shade, shade);
     up(sc->materials, mats);
     up(sc->textures, texs);
@@ -1263,6 +1314,12 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
         sc->dev.qext[k] = qext[k];
     }
     sc->dev.ftris = sc->ftris.p;
+    sc->dev.n_ftris = uint32_t(ftris.size() / kTriRows);
+    sc->dev.sph_rows = sc->sph_rows.p;
+    sc->dev.sph_boxes = sc->sph_boxes.p;
+    sc->dev.sph_box_off = sc->sph_box_off.p;
+    sc->dev.fpos = sc->fpos.p;
+    sc->dev.n_sph = uint32_t(sphRows.size() / kTriRows);
     sc->dev.froot = sc->fast.root;
     sc->dev.shade = sc->shade.p;
     sc->dev.materials = sc->materials.p;
@@ -1341,6 +1398,10 @@ int cge_scene_destroy(cge_scene* sc)
     sc->fnodes.release();
     sc->qnodes.release();
     sc->ftris.release();
+    sc->sph_rows.release();
+    sc->sph_boxes.release();
+    sc->sph_box_off.release();
+    sc->fpos.release();
     sc->shade.release();
     sc->materials.release();
     sc->textures.release();

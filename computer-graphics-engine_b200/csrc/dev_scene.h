@@ -70,6 +70,18 @@ struct DevScene {
     uint32_t root_ref, root_count; // reference-order tree root, same encoding as a child slot
     uint32_t froot;                // fast tree root (packed)
     uint32_t has_spheres;
+    // FAST traversal of scenes with spheres / without enableAccelStructure (trace.cuh sphere_pass_*): the fast tree holds the
+    // triangles only; the (few) spheres are tested one by one, each behind the chain of REFERENCE-tree boxes the reference's
+    // traversal tests before it reaches the sphere's leaf (the archive's sphere test assumes a unit direction, so for shadow rays
+    // WHETHER it is called decides the result)
+    const float4* sph_rows;      // kTriRows rows per sphere, as in `tris` (r1 = centre, radius; r2.x = bits{position in the reference's
+                                 // primitive vector}; r5.z = bits{visit rank}; r5.w = bits{global id | sphere bit})
+    const float4* sph_boxes;     // 2 rows per box: lower.xyz, upper.xyz
+    const uint32_t* sph_box_off; // n_sph + 1 offsets into sph_boxes (in boxes)
+    const uint32_t* fpos;        // fast-tree primitive index -> position in the reference's primitive vector (the tie rank when
+                                 // enableAccelStructure is off: the reference then loops over that vector, :303-305)
+    uint32_t n_sph, n_ftris;
+    uint32_t noaccel;            // this frame has enableAccelStructure off
     float qlo[3], qext[3]; // quantisation grid of qnodes: coordinate = qlo + m * qext, m in [1, 2)
     uint32_t cull_zero_shading; // FAST traversal: skip the shadow ray of a light sample with n.l <= 0 (shade.cuh shading_is_zero)
 };

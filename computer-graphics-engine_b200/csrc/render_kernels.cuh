@@ -75,10 +75,10 @@ struct PixelTracer {
     {
         cnt.shadow++;
         if (kFast)
-            return kCount ? trace_fast<true, kCount>(s, o, d, 1.0f, &nbox, &ntri).prim >= 0 : trace_shadow(s, o, d) >= 0;
+            return kCount ? trace_fast<true, kCount>(s, o, d, 1.0f, &nbox, &ntri).prim >= 0 : trace_shadow(s, o, d) != -1;
         return trace_reference<kSpheres, kCount>(s, o, d, 1.0f, nbox, ntri).prim >= 0;
     }
-    __device__ const float4* rows(const Hit& h) const { return (kFast ? s.ftris : s.tris) + size_t(h.prim) * kTriRows; }
+    __device__ const float4* rows(const Hit& h) const { return kFast ? fast_hit_rows(s, h) : s.tris + size_t(h.prim) * kTriRows; }
 
     // computeLightContribution (src/light.cpp:108-164)
     __device__ vec3 direct(const HitRec& h, unsigned pixel, unsigned ctr)

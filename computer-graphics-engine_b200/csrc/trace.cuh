@@ -175,13 +175,82 @@ __device__ __forceinline__ void slab_box(const SlabRay& r, float lox, float loy,
     ext = min3(tfx, tfy, tfz);
 }
 
-// Fast tree.  Triangles only (scenes with spheres are always walked by trace_reference, see cge_api.cu).
+// ---- spheres beside the fast tree (dev_scene.h) ------------------------------------------------------------------------------------
+// Would the reference's traversal reach sphere i's leaf?  It tests the box of every node on the way from the root's child down
+// to the leaf with ray.t = FLT_MAX (src/bounding_volume_hierarchy.cpp:334-352); without enableAccelStructure it tests no box.
+__device__ __forceinline__ bool sphere_reached(const DevScene& s, unsigned i, const vec3 o, const vec3 d)
+{
+    if (s.noaccel)
+        return true;
+    for (unsigned b = __ldg(s.sph_box_off + i); b < __ldg(s.sph_box_off + i + 1); b++) {
+        const float4 lo = ldg4(s.sph_boxes + 2 * size_t(b)), hi = ldg4(s.sph_boxes + 2 * size_t(b) + 1);
+        Ray ray { o, d, FLT_MAX };
+        if (!intersect_aabb(v3(lo.x, lo.y, lo.z), v3(hi.x, hi.y, hi.z), ray))
+            return false;
+    }
+    return true;
+}
+// Closest hit: merge the spheres into the triangle result h.  A sphere is accepted only with t STRICTLY below the ray's current
+// t (I6), a triangle with t <= (I4): whatever the visit order, a sphere wins exactly when its t is strictly below every triangle's,
+// and among spheres of equal t the first visited one (lowest rank) stays.
+__device__ __forceinline__ void sphere_pass_closest(const DevScene& s, const vec3 o, const vec3 d, Hit& h)
+{
+    float bestT = h.t;
+    unsigned bestKey = 0xffffffffu;
+    int best = -1;
+    for (unsigned i = 0; i < s.n_sph; i++) {
+        const float4* tr = s.sph_rows + size_t(i) * kTriRows;
+        const float4 r1 = ldg4(tr + 1);
+        Ray ray { o, d, h.t };
+        if (!intersect_sphere(v3(r1.x, r1.y, r1.z), r1.w, ray, nullptr)) // rejects t >= h.t: the triangle (or tmax) keeps ties
+            continue;
+        if (!sphere_reached(s, i, o, d)) // (the cheap test first: most rays miss the sphere and never need the box chain)
+            continue;
+        const unsigned key = s.noaccel ? __float_as_uint(ldg4(tr + 2).x) : __float_as_uint(ldg4(tr + 5).z);
+        if (ray.t < bestT || (ray.t == bestT && best >= 0 && key < bestKey)) {
+            bestT = ray.t;
+            bestKey = key;
+            best = int(i);
+        }
+    }
+    if (best >= 0) {
+        h.t = bestT;
+        h.prim = best;
+        h.gid = __float_as_uint(ldg4(s.sph_rows + size_t(best) * kTriRows + 5).w);
+    }
+}
+// Any hit with 0 <= t < tmax on a sphere the reference would test?
+__device__ __forceinline__ bool sphere_pass_shadow(const DevScene& s, const vec3 o, const vec3 d, float tmax)
+{
+    for (unsigned i = 0; i < s.n_sph; i++) {
+        const float4 r1 = ldg4(s.sph_rows + size_t(i) * kTriRows + 1);
+        Ray ray { o, d, tmax };
+        if (intersect_sphere(v3(r1.x, r1.y, r1.z), r1.w, ray, nullptr) && sphere_reached(s, i, o, d))
+            return true;
+    }
+    return false;
+}
+// rows of a hit primitive: the fast tree's triangle rows, or the sphere rows
+__device__ __forceinline__ const float4* fast_hit_rows(const DevScene& s, const Hit& h)
+{
+    return ((h.gid & kSphereBit) ? s.sph_rows : s.ftris) + size_t(h.prim) * kTriRows;
+}
+constexpr int kSphereBlocker = -2; // trace_shadow: blocked by a sphere (no triangle to remember)
+
+// Fast tree (triangles) + the sphere pass.
 template <bool kAnyHit, bool kCount = false>
 __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax, unsigned* nbox = nullptr, unsigned* ntri = nullptr)
 {
     Hit h { tmax, -1, 0u };
-    if (s.n_prims == 0)
+    if (s.n_ftris == 0) {
+        if (s.n_sph) {
+            if (!kAnyHit)
+                sphere_pass_closest(s, o, d, h);
+            else if (sphere_pass_shadow(s, o, d, tmax))
+                h.prim = 0, h.gid = kSphereBit;
+        }
         return h;
+    }
     unsigned bestRank = 0;
     // Reciprocal direction for the slab test.  For an axis with d == 0 the archive's box function substitutes the
     // constants [FLT_MIN, FLT_MAX] whatever the origin, i.e. it never rejects on that axis.
@@ -239,7 +308,7 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
             float4 r5;
             if (!triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, h.t, t, r5))
                 continue;
-            const unsigned rank = __float_as_uint(r5.z);
+            const unsigned rank = s.noaccel ? __ldg(s.fpos + i) : __float_as_uint(r5.z);
             if (t == h.t && h.prim >= 0 && rank < bestRank)
                 continue; // an equal-t triangle the reference visits later is already held
             h.t = t;
@@ -250,6 +319,12 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
                 return h;
         }
         cur = pop();
+    }
+    if (s.n_sph) {
+        if (!kAnyHit)
+            sphere_pass_closest(s, o, d, h);
+        else if (h.prim < 0 && sphere_pass_shadow(s, o, d, tmax))
+            h.prim = 0, h.gid = kSphereBit;
     }
     return h;
 }
@@ -313,22 +388,70 @@ __device__ __forceinline__ void slab_box_q(const SlabRayQ& r, unsigned wx, unsig
     ext = min3(tfx, tfy, tfz);
 }
 
+// ---- traversal stacks ------------------------------------------------------------------------------------------------------
+// LocalStack: a per-thread array (local memory: L1-resident, but every push / pop is an L1 transaction of its own).
+// SharedStack: the first kShort entries of every lane live in shared memory, lane-interleaved (entry e of thread t at
+// [e][t]: a warp's push or pop is one conflict-free access), deeper entries spill to a small local array.  The near-first
+// (or far-first) walk of a binary tree holds at most one entry per level; the any-hit walks of the shadow pass rarely hold
+// more than a handful, so with kShort = 12 the local part is practically never touched (ncu: local sectors ~ 0).
+struct LocalStack {
+    unsigned v[kFastStackSize];
+    int sp = 0;
+    __device__ __forceinline__ void reset() { sp = 0; }
+    __device__ __forceinline__ void push(unsigned x) { v[sp++] = x; }
+    __device__ __forceinline__ bool pop(unsigned& x)
+    {
+        if (sp == 0)
+            return false;
+        x = v[--sp];
+        return true;
+    }
+};
+template <int kShort>
+struct SharedStack {
+    unsigned (*s)[128]; // [kShort][128] in shared memory, one column per thread of the 128-thread CTA
+    unsigned tid;
+    unsigned ovf[kFastStackSize - kShort];
+    int sp = 0;
+    __device__ __forceinline__ SharedStack(unsigned (*base)[128], unsigned t)
+        : s(base)
+        , tid(t)
+    {
+    }
+    __device__ __forceinline__ void reset() { sp = 0; }
+    __device__ __forceinline__ void push(unsigned x)
+    {
+        if (sp < kShort)
+            s[sp][tid] = x;
+        else
+            ovf[sp - kShort] = x;
+        sp++;
+    }
+    __device__ __forceinline__ bool pop(unsigned& x)
+    {
+        if (sp == 0)
+            return false;
+        sp--;
+        x = sp < kShort ? s[sp][tid] : ovf[sp - kShort];
+        return true;
+    }
+};
+
 // Shadow rays (src/light.cpp:60-72: closest hit with ray.t = 1 used as a boolean): is ANY triangle accepted with 0 <= t <= 1?
 // Lean specialisation of trace_fast<true>: the bound is the constant 1, so the stack needs no entry distances and no
-// re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris) or -1.
+// re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris), kSphereBlocker, or -1 (visible).
 // kCountVisits: *visits receives the number of inner nodes the ray visited (wf_vis_regroup_kernel ranks a warp's hits by it)
-template <bool kCountVisits = false>
-__device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
+template <bool kCountVisits, typename Stack>
+__device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
 {
-    if (s.n_prims == 0)
-        return -1;
+    if (s.n_ftris == 0)
+        return s.n_sph && sphere_pass_shadow(s, o, d, 1.0f) ? kSphereBlocker : -1;
 #if CGE_QNODES
     const SlabRayQ sr = slab_ray_q(s, o, d);
 #else
     const SlabRay sr = slab_ray(o, d);
 #endif
-    unsigned stack[kFastStackSize];
-    int sp = 0;
+    stk.reset();
     constexpr unsigned kDone = 0x7fffffffu;
     unsigned cur = s.froot;
     while (cur != kDone) {
@@ -363,15 +486,15 @@ __device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, con
 #endif
             if (hitL && hitR) {
                 const unsigned far = leftFirst ? cr : cl;
-                stack[sp++] = far;
+                stk.push(far);
 #if CGE_PREFETCH == 1
                 prefetch_child(s, far);
 #endif
             }
             if (hitL || hitR)
                 cur = leftFirst ? cl : cr;
-            else
-                cur = sp > 0 ? stack[--sp] : kDone;
+            else if (!stk.pop(cur))
+                cur = kDone;
         }
         if (cur == kDone)
             break;
@@ -382,9 +505,17 @@ __device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, con
             if (triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, 1.0f, t, r5))
                 return int(i);
         }
-        cur = sp > 0 ? stack[--sp] : kDone;
+        if (!stk.pop(cur))
+            cur = kDone;
     }
-    return -1;
+    return s.n_sph && sphere_pass_shadow(s, o, d, 1.0f) ? kSphereBlocker : -1;
+}
+
+template <bool kCountVisits = false>
+__device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
+{
+    LocalStack stk;
+    return trace_shadow_on<kCountVisits>(stk, s, o, d, visits);
 }
 
 } // namespace cge

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
         if (kSubRays && live && ids) { // the id map stays that of the un-jittered pixel-corner ray (not a reference ray: not counted)
             const Ray c = generate_ray(cam, x, y, p.width, p.height);
             const Hit h = trace_fast<false>(s, c.o, c.d, c.t);
-            ids[out_pixel_index(p, x, y)] = h.prim >= 0 ? int(h.gid) : -1;
+            ids[out_pixel_index(p, x, y)] = h.prim >= 0 ? int(h.gid & ~kSphereBit) : -1;
         }
         for (unsigned sub = 0; sub < nSub; sub++) {
             Ray ray {};
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
                     slots[level] = slot;
                     ray.t = h.t;
                     HitRec r;
-                    resolve_hit(s, p.features, s.ftris + size_t(h.prim) * kTriRows, h.gid, ray, r);
+                    resolve_hit(s, p.features, fast_hit_rows(s, h), h.gid, ray, r);
                     float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + slot;
                     const size_t c = wb.cap;
                     b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
                     if (level > 0)
                         wb.next[size_t(level - 1) * wb.cap + slots[level - 1]] = slot;
                     else if (ids && !kSubRays)
-                        ids[out_pixel_index(p, x, y)] = int(h.gid);
+                        ids[out_pixel_index(p, x, y)] = int(h.gid & ~kSphereBit);
                     n = level + 1;
                     Ray nextRay;
                     if (!recursive || level >= p.ray_depth || !reflection_ray(r, nextRay))
@@ -191,7 +191,7 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
                 v = vis[size_t(sg) * visStride] ? 1.0f : 0.0f;
             } else if (ls.shadowed && !shading_is_zero(s, frame, ls.pos)) {
                 nshadow++;
-                v = trace_shadow(s, sp, ls.pos - sp) >= 0 ? 0.0f : 1.0f;
+                v = trace_shadow(s, sp, ls.pos - sp) != -1 ? 0.0f : 1.0f;
             }
             result = result + c * v;
         } else if (samples) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ vec3 wf_direct(const DevScene& s, const DevParams& p,
                     v = 1.0f;
                 } else {
                     nshadow++;
-                    v = trace_shadow(s, sp, ls.pos - sp) >= 0 ? 0.0f : 1.0f;
+                    v = trace_shadow(s, sp, ls.pos - sp) != -1 ? 0.0f : 1.0f;
                 }
                 color = color + compute_shading(ls.pos, ls.col, h) * v;
             }
@@ -269,6 +269,14 @@ __device__ __forceinline__ LightSample wf_sample(const DevScene& s, const DevPar
     return sample_light(L, type, int(si), p, pixel, ctr);
 }
 
+#ifndef CGE_VIS_SHORT_STACK
+#define CGE_VIS_SHORT_STACK 0 // > 0: the shadow-ray kernel keeps that many stack entries per lane in shared memory (trace.cuh
+                              // SharedStack) instead of the per-thread local array.  Measured on B200, shadow pass of
+                              // C5 / a 1/8 share / C3: local array 12.07 / 1.75 / 0.86 ms; 12 shared entries 14.99 / 2.14 / 0.96 ms
+                              // (10 CTAs per SM, 48 registers: 13.39 / 1.98 / 0.88; 16 entries: 13.41 / 1.93 / 0.88): the index
+                              // arithmetic and the overflow test cost more than the L1 transactions they save.  Off.
+#endif
+constexpr int kVisShortStack = CGE_VIS_SHORT_STACK > 0 ? CGE_VIS_SHORT_STACK : 1;
 #ifndef CGE_MINB_VIS
 #define CGE_MINB_VIS 12 // resident 128-thread CTAs per SM the shadow-ray kernel is compiled for (A/B in DESIGN.md 5.5)
 #endif
@@ -322,6 +330,12 @@ template <unsigned kGroup>
 __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
 {
     __shared__ unsigned char laneOfRank[4][32];
+#if CGE_VIS_SHORT_STACK > 0
+    __shared__ unsigned stackMem[kVisShortStack][128]; // the traversal stacks (trace.cuh SharedStack)
+    SharedStack<kVisShortStack> stk(stackMem, threadIdx.x);
+#else
+    LocalStack stk;
+#endif
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool fold = p.draws_per_hit == 0;
     const unsigned S = p.samples_per_hit;
@@ -346,10 +360,11 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevSc
             if (h.occluder >= 0 && triangle_rows_hit(s.ftris + size_t(h.occluder) * kTriRows, h.o, d, 1.0f, t, r5)) {
                 v = 0;
             } else {
-                const int blocker = visits ? trace_shadow<true>(s, h.o, d, visits) : trace_shadow(s, h.o, d);
-                if (blocker >= 0) {
+                const int blocker = visits ? trace_shadow_on<true>(stk, s, h.o, d, visits) : trace_shadow_on<false>(stk, s, h.o, d);
+                if (blocker != -1) {
                     v = 0;
-                    h.occluder = blocker;
+                    if (blocker >= 0)
+                        h.occluder = blocker;
                 }
             }
         }

@@ -160,7 +160,10 @@ enum {
     CGE_TRAVERSAL_FAST = 1       /* binned-SAH tree (<= 4 primitives per leaf), near child first, conservative t culling,
                                     shadow rays stop at the first blocker; equal-t winner chosen by the reference's
                                     visit rank; with area lights a wavefront pipeline over warp-compacted hit queues, otherwise
-                                    one thread per pixel. */
+                                    one thread per pixel.  Spheres (up to 64) are tested beside the tree, each behind the chain
+                                    of reference-tree boxes that decides whether the reference calls its sphere test; frames
+                                    without enableAccelStructure walk the same tree with the tie rank of the reference's
+                                    primitive vector.  Scenes with more spheres take the literal traversal. */
 };
 enum {
     CGE_SAMPLER_HASH = 0 /* rand() replaced by hash(seed, pixel, draw index) — see DESIGN.md "sampler" */
