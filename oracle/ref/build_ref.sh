@@ -64,4 +64,20 @@ g++ -shared -fopenmp -o "$OUT/libcge_ref.so" $OBJ/ref_api.o $COMMON "$R/prebuilt
     $WRAPS -Wl,--wrap=rand -Wl,--wrap=_ZNSt13random_device9_M_getvalEv -Wl,-Bsymbolic -ldl
 g++ -shared -fopenmp -o "$OUT/libcge_ref_plain.so" $OBJ/ref_api_plain.o $COMMON "$R/prebuilt/libIntersect_linux_x64.a" \
     -Wl,--wrap=rand -Wl,--wrap=_ZNSt13random_device9_M_getvalEv -Wl,-Bsymbolic -ldl
+# ---- libcge_ref_gpu.so: the reference engine with the GPU path behind its own seam ---------------------------------------
+# computer-graphics-engine_b200/host/render_gpu.cpp (the file a maintainer adds: renderRayTracing -> libcge.so) compiled against
+# the reference's unmodified headers.  The reference's own renderRayTracing stays in the link as renderRayTracingCPU, the shim's
+# fallback: the rename is done on a COPY of the object file (objcopy --redefine-sym), no reference source is touched.
+PKG=$REPO/computer-graphics-engine_b200
+if [ -f "$PKG/libcge.so" ] && command -v objcopy > /dev/null; then
+    RRT=_Z16renderRayTracingRK5SceneRK9TrackballRK12BvhInterfaceR6ScreenRK8Features
+    RRT_CPU=_Z19renderRayTracingCPURK5SceneRK9TrackballRK12BvhInterfaceR6ScreenRK8Features
+    objcopy --redefine-sym $RRT=$RRT_CPU "$OBJ/render.o" "$OBJ/render_cpu.o"
+    g++ $CXXFLAGS $INC -c "$PKG/host/render_gpu.cpp" -o "$OBJ/render_gpu.o"
+    g++ $CXXFLAGS $INC -DCGE_REF_NO_COUNTERS -DCGE_REF_GPU_SHIM -c "$HERE/ref_api.cpp" -o "$OBJ/ref_api_gpu.o"
+    g++ -shared -fopenmp -o "$OUT/libcge_ref_gpu.so" $OBJ/ref_api_gpu.o ${COMMON/$OBJ\/render.o/$OBJ/render_cpu.o} $OBJ/render_gpu.o \
+        "$R/prebuilt/libIntersect_linux_x64.a" -Wl,--wrap=rand -Wl,--wrap=_ZNSt13random_device9_M_getvalEv -Wl,-Bsymbolic \
+        -L"$PKG" -lcge -Wl,-rpath,'$ORIGIN/../../computer-graphics-engine_b200' -ldl
+    echo "built $OUT/libcge_ref_gpu.so"
+fi
 echo "built $OUT/libcge_ref.so $OUT/libcge_ref_plain.so"

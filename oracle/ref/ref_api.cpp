@@ -669,6 +669,10 @@ void ref_bvh_info(void* b, int32_t* nNodes, int32_t* nLevels, int32_t* nLeaves)
     *nLeaves = rb->bvh->numLeaves();
 }
 
+#ifdef CGE_REF_GPU_SHIM
+extern "C" void cgeSetSamplerSeed(uint32_t seed); // computer-graphics-engine_b200/host/render_gpu.cpp
+#endif
+
 struct ref_render_params {
     int32_t width, height;
     uint32_t features;
@@ -707,6 +711,9 @@ int ref_render(void* scene, void* bvhHandle, const ref_render_params* p, float* 
     parallelogramLightDirectionSamples = p->parallelogram_samples;
     g_samplerMode = int(p->sampler);
     g_seed = p->seed;
+#ifdef CGE_REF_GPU_SHIM
+    cgeSetSamplerSeed(p->seed); // libcge_ref_gpu.so: renderRayTracing is the GPU shim; its stateless sampler gets the same seed
+#endif
     if (p->rays_per_pixel_side > 0)
         raysPerPixelSide = p->rays_per_pixel_side;
     if (features.extra.enableBloomEffect) {

@@ -38,17 +38,23 @@ class CgeCamera(C.Structure):
                 ("half_height", C.c_float)]
 
 
-def available(plain: bool = False) -> bool:
-    return (REF_DIR / ("libcge_ref_plain.so" if plain else "libcge_ref.so")).exists()
+def _lib_name(plain) -> str:
+    # plain = "gpu": the reference engine linked with computer-graphics-engine_b200/host/render_gpu.cpp, i.e. its own
+    # renderRayTracing(scene, camera, bvh, screen, features) answered by libcge.so (oracle/ref/build_ref.sh)
+    return "libcge_ref_gpu.so" if plain == "gpu" else "libcge_ref_plain.so" if plain else "libcge_ref.so"
+
+
+def available(plain=False) -> bool:
+    return (REF_DIR / _lib_name(plain)).exists()
 
 
 _libs = {}
 
 
-def lib(plain: bool = False):
-    key = bool(plain)
+def lib(plain=False):
+    key = plain if plain == "gpu" else bool(plain)
     if key not in _libs:
-        path = REF_DIR / ("libcge_ref_plain.so" if plain else "libcge_ref.so")
+        path = REF_DIR / _lib_name(plain)
         l = C.CDLL(str(path))
         l.ref_scene_load_flat.restype = C.c_void_p
         l.ref_scene_load_flat.argtypes = [C.c_char_p]
@@ -92,7 +98,7 @@ def _f32(a):
 class RefScene:
     """Reference ``Scene`` + ``BvhInterface`` built from a flat scene file."""
 
-    def __init__(self, path, features: int, plain: bool = False):
+    def __init__(self, path, features: int, plain=False):
         self.l = lib(plain)
         self.scene = self.l.ref_scene_load_flat(str(path).encode())
         if not self.scene:
