@@ -91,7 +91,11 @@ struct Scratch {
     size_t gatherPixels = 0;
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
-    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveSub = 0;
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveSub = 0, waveCont = 0;
+    // split chain stage (wavefront.cuh wf_primary_kernel / wf_continue_kernel): the level-0 shadow pass runs on auxStream beside
+    // the continuation kernel
+    cudaStream_t auxStream = nullptr;
+    cudaEvent_t evPrimary = nullptr, evVis0 = nullptr;
     float* bloomTmp = nullptr; // thresholded copy of the frame (renderBloomFilter's screenThreshold)
     size_t bloomPixels = 0;
     cudaStream_t stream = nullptr;
@@ -744,43 +748,96 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
             err = cudaMemsetAsync(s->wave.counts, 0, 64 * sizeof(unsigned), s->stream);
         s->wave.cap = unsigned(cap);
         int perSm = 0;
-        if (err == cudaSuccess)
-            err = dp.aa_side ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<true>, 128, 0)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<false>, 128, 0);
-        cudaEventRecord(stage[0], s->stream);
-        if (err == cudaSuccess) {
-            if (dp.aa_side)
-                wf_chain_kernel<true><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
-            else
-                wf_chain_kernel<false><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
-            err = cudaGetLastError();
-        }
-        cudaEventRecord(stage[1], s->stream);
-        if (err == cudaSuccess && visFits) {
+        // The chain stage in two kernels (wavefront.cuh): camera rays, then the rest of the chains BESIDE the level-0 shadow pass,
+        // which hides the chain tail.  Frames with recursion and one camera ray per pixel; CGE_CHAIN_SPLIT=0 keeps the one kernel.
+        // Measured on B200: a 1/8 share of C5 (one rank of eight) 2.59 -> 2.52 ms; the whole frame as one pipeline
+        // 15.57 -> 15.67 ms and as four concurrent bands 15.33 -> 15.91 ms (bands already fill the tails, and the two shadow
+        // launches each end in a tail of their own): on for launches below the band threshold only.
+        const bool smallLaunch = size_t(myTiles) * 32 < (size_t(3) << 19);
+        const bool split = visFits && !dp.aa_side && wp.levels > 1 && env_int("CGE_CHAIN_SPLIT", smallLaunch ? 1 : 0);
+        auto launchVis = [&](cudaStream_t st, unsigned levelBegin, unsigned levelEnd, unsigned counterIdx) {
             auto go = [&](auto kern) {
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
                 if (err == cudaSuccess) {
-                    kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                    kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, st>>>(ds, wp, s->wave, s->counters, levelBegin, levelEnd, counterIdx);
                     err = cudaGetLastError();
                     *launches += 1;
                 }
             };
-#if CGE_EXPERIMENTS
-            const int packet = env_int("CGE_PACKET", 0); // the packet (hull) shadow walk: measured slower
-            if (packet >= 16)
-                go(wf_vis_packet_kernel<16>);
-            else if (packet >= 8)
-                go(wf_vis_packet_kernel<8>);
-            else if (packet > 0)
-                go(wf_vis_packet_kernel<4>);
-            else
-#endif
-            {
-                // 4 or 8 samples per lane, decided on the device from the queue lengths (they only exist there): both
-                // instantiations are launched and the one not selected returns at once
-                go(wf_vis_regroup_kernel<4>);
+            // 4 or 8 samples per lane, decided on the device from the queue lengths (they only exist there): both
+            // instantiations are launched and the one not selected returns at once
+            go(wf_vis_regroup_kernel<4>);
+            if (err == cudaSuccess)
+                go(wf_vis_regroup_kernel<8>);
+        };
+        cudaEventRecord(stage[0], s->stream);
+        if (err == cudaSuccess && split) {
+            if (!s->auxStream) {
+                int least = 0, greatest = 0;
+                cudaDeviceGetStreamPriorityRange(&least, &greatest);
+                err = cudaStreamCreateWithPriority(&s->auxStream, cudaStreamNonBlocking, greatest);
                 if (err == cudaSuccess)
-                    go(wf_vis_regroup_kernel<8>);
+                    err = cudaEventCreateWithFlags(&s->evPrimary, cudaEventDisableTiming);
+                if (err == cudaSuccess)
+                    err = cudaEventCreateWithFlags(&s->evVis0, cudaEventDisableTiming);
+            }
+            if (err == cudaSuccess)
+                err = grow(s->wave.cont, s->waveCont, cap, sizeof(unsigned));
+            if (err == cudaSuccess)
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_primary_kernel, 128, 0);
+            if (err == cudaSuccess) {
+                wf_primary_kernel<<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
+                err = cudaGetLastError();
+                cudaEventRecord(s->evPrimary, s->stream);
+            }
+            if (err == cudaSuccess) { // level 0 is final: its shadow rays start on the second stream
+                cudaStreamWaitEvent(s->auxStream, s->evPrimary, 0);
+                launchVis(s->auxStream, 0, 1, 18);
+                cudaEventRecord(s->evVis0, s->auxStream);
+            }
+            if (err == cudaSuccess)
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_continue_kernel, 128, 0);
+            if (err == cudaSuccess) {
+                wf_continue_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                err = cudaGetLastError();
+                *launches += 1;
+            }
+            cudaEventRecord(stage[1], s->stream);
+            if (err == cudaSuccess)
+                launchVis(s->stream, 1, wp.levels, 19);
+            cudaStreamWaitEvent(s->stream, s->evVis0, 0);
+        } else {
+            if (err == cudaSuccess)
+                err = dp.aa_side ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<true>, 128, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_chain_kernel<false>, 128, 0);
+            if (err == cudaSuccess) {
+                if (dp.aa_side)
+                    wf_chain_kernel<true><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
+                else
+                    wf_chain_kernel<false><<<grid_for(perSm), 128, 0, s->stream>>>(ds, dc, wp, s->wave, rgbDev, idsDev, s->counters);
+                err = cudaGetLastError();
+            }
+            cudaEventRecord(stage[1], s->stream);
+            if (err == cudaSuccess && visFits) {
+#if CGE_EXPERIMENTS
+                const int packet = env_int("CGE_PACKET", 0); // the packet (hull) shadow walk: measured slower
+                auto goPacket = [&](auto kern) {
+                    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
+                    if (err == cudaSuccess) {
+                        kern<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, s->stream>>>(ds, wp, s->wave, s->counters);
+                        err = cudaGetLastError();
+                        *launches += 1;
+                    }
+                };
+                if (packet >= 16)
+                    goPacket(wf_vis_packet_kernel<16>);
+                else if (packet >= 8)
+                    goPacket(wf_vis_packet_kernel<8>);
+                else if (packet > 0)
+                    goPacket(wf_vis_packet_kernel<4>);
+                else
+#endif
+                    launchVis(s->stream, 0, wp.levels, 18);
             }
         }
         cudaEventRecord(stage[2], s->stream);
@@ -1371,6 +1428,13 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.dir);
         cudaFree(s->wave.vis);
         cudaFree(s->wave.sub);
+        cudaFree(s->wave.cont);
+        if (s->auxStream)
+            cudaStreamDestroy(s->auxStream);
+        if (s->evPrimary)
+            cudaEventDestroy(s->evPrimary);
+        if (s->evVis0)
+            cudaEventDestroy(s->evVis0);
         cudaFree(s->bloomTmp);
         cudaFree(s->wave.counts);
         if (s->ev0)

@@ -44,7 +44,10 @@ struct WaveBuffers {
     unsigned* next;
     float* dir;
     unsigned char* vis; // one byte per (level, copy, sample, slot): 1 = light sample visible
-    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] shadow-ray chunk counter
+    unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] / [19] shadow-ray chunk
+                        // counters (level 0 / deeper levels when the chain stage is split), [20] continuation-queue length, [21] its
+                        // chunk counter
+    unsigned* cont;     // [cap] level-0 queue slots of the hits whose chain goes on (wf_primary_kernel -> wf_continue_kernel)
     float* sub;         // multiple rays per pixel: [3][launch pixel][sub-ray] colour of every camera ray, summed by wf_resolve_kernel
     unsigned cap;
 };
@@ -163,6 +166,166 @@ __global__ void __launch_bounds__(128, kSubRays ? CGE_MINB_CHAIN : 8) wf_chain_k
                     }
                 }
             }
+        }
+    }
+    flush_counters(cnt, gcnt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The chain stage in two kernels, so that its tail can hide under the shadow pass (frames without multiple rays per pixel and
+// with recursion on; cge_api.cu launch_render).  The tail of wf_chain_kernel is a handful of pixels whose mirror chains graze the
+// model - up to 4 dependent closest-hit rays of several hundred node visits each, ~0.4 ms that no partition of the frame shortens
+// (on a 1/8 share the schedulers idle 60 % of the kernel, profiles/r02_wf_chain_part8_c5.txt).  The camera rays have no such
+// tail, and level 0 holds most of the frame's direct-lighting evaluations:
+//   wf_primary_kernel   camera rays only; hits go to the level-0 queue, hits that reflect additionally to the continuation
+//                       queue.  When it has finished the level-0 queue is final and its shadow rays start (own stream).
+//   wf_continue_kernel  one lane = the rest of one pixel's chain (levels 1 ..), 32 reflecting pixels per warp.  Runs beside the
+//                       level-0 shadow pass; the deeper levels' shadow rays follow it.
+// Both write exactly the records, links and tags wf_chain_kernel writes (the slot ORDER differs, which nothing depends on).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wf_write_record(const WaveBuffers& wb, unsigned level, unsigned slot, const HitRec& r)
+{
+    float* b = wb.rec + (size_t(level) * kWaveRecFloats) * wb.cap + slot;
+    const size_t c = wb.cap;
+    b[0 * c] = r.ray.o.x, b[1 * c] = r.ray.o.y, b[2 * c] = r.ray.o.z;
+    b[3 * c] = r.ray.d.x, b[4 * c] = r.ray.d.y, b[5 * c] = r.ray.d.z;
+    b[6 * c] = r.ray.t;
+    b[7 * c] = r.normal.x, b[8 * c] = r.normal.y, b[9 * c] = r.normal.z;
+    b[10 * c] = r.m.kd.x, b[11 * c] = r.m.kd.y, b[12 * c] = r.m.kd.z;
+    b[13 * c] = r.m.ks.x, b[14 * c] = r.m.ks.y, b[15 * c] = r.m.ks.z;
+    b[16 * c] = r.m.shininess;
+    const vec3 so = shadow_origin(r);
+    b[17 * c] = so.x, b[18 * c] = so.y, b[19 * c] = so.z;
+}
+
+__global__ void __launch_bounds__(128, 8) wf_primary_kernel(DevScene s, DevCamera cam, DevParams p, WaveBuffers wb, float* __restrict__ rgb,
+    int* __restrict__ ids, Counters* __restrict__ gcnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const bool recursive = (p.features & CGE_FEAT_RECURSIVE) && p.ray_depth > 0;
+    Counters cnt {};
+    int x, y;
+    while (next_tile(p, wb.counts + 16, lane, x, y)) {
+        const bool live = x < p.width && y < p.height;
+        const unsigned pixel = unsigned(y) * unsigned(p.width) + unsigned(x);
+        Ray ray {};
+        Hit h {};
+        bool hit = false;
+        if (live) {
+            ray = generate_ray(cam, x, y, p.width, p.height);
+            h = trace_fast<false>(s, ray.o, ray.d, ray.t);
+            cnt.primary++;
+            hit = h.prim >= 0;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        unsigned base = 0;
+        if (lane == 0 && ballot)
+            base = atomicAdd(wb.counts + 0, unsigned(__popc(ballot)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned slot = base + unsigned(__popc(ballot & below));
+        bool goesOn = false;
+        if (hit) {
+            ray.t = h.t;
+            HitRec r;
+            resolve_hit(s, p.features, fast_hit_rows(s, h), h.gid, ray, r);
+            wf_write_record(wb, 0, slot, r);
+            if (ids)
+                ids[out_pixel_index(p, x, y)] = int(h.gid & ~kSphereBit);
+            goesOn = recursive && !(r.m.ks.x == 0.0f && r.m.ks.y == 0.0f && r.m.ks.z == 0.0f); // computeReflectionRay's sentinel
+            // the tag (.y) of a chain that goes on is written by wf_continue_kernel when the chain has ended
+            wb.meta[slot] = make_uint2(pixel, goesOn ? 0u : 1u);
+        }
+        const unsigned more = __ballot_sync(0xffffffffu, goesOn);
+        unsigned cbase = 0;
+        if (lane == 0 && more)
+            cbase = atomicAdd(wb.counts + 20, unsigned(__popc(more)));
+        cbase = __shfl_sync(0xffffffffu, cbase, 0);
+        if (goesOn)
+            wb.cont[cbase + unsigned(__popc(more & below))] = slot;
+        else if (live) {
+            reference_calls(cnt, hit ? 1 : 0, !hit, p.shadow_rays_per_hit);
+            if (!hit)
+                store_pixel(p, rgb, ids, x, y, v3(0.0f), -1); // primary miss: black (reference src/render.cpp:148)
+        }
+    }
+    flush_counters(cnt, gcnt);
+}
+
+__global__ void __launch_bounds__(128, 8) wf_continue_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned total = wb.counts[20];
+    Counters cnt {};
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0)
+            chunk = atomicAdd(wb.counts + 21, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((unsigned long long)chunk * 32ull >= total)
+            break;
+        const unsigned i = chunk * 32u + lane;
+        const bool live = i < total;
+        unsigned slots[kMaxLevels];
+        unsigned pixel = 0;
+        Ray ray {};
+        if (live) {
+            const unsigned e0 = wb.cont[i];
+            slots[0] = e0;
+            pixel = wb.meta[e0].x;
+            // the reflected ray of the level-0 hit, from its record (computeReflectionRay, src/shading.cpp:40-62)
+            const float* b = wb.rec + e0;
+            const size_t c = wb.cap;
+            HitRec prev;
+            prev.ray.o = v3(b[0 * c], b[1 * c], b[2 * c]);
+            prev.ray.d = v3(b[3 * c], b[4 * c], b[5 * c]);
+            prev.ray.t = b[6 * c];
+            prev.normal = v3(b[7 * c], b[8 * c], b[9 * c]);
+            prev.m.ks = v3(b[13 * c], b[14 * c], b[15 * c]);
+            reflection_ray(prev, ray); // ks != 0 was checked when the entry was queued
+        }
+        bool alive = live, missEnd = false;
+        int n = 1;
+        for (int level = 1; __any_sync(0xffffffffu, alive); level++) {
+            bool hit = false;
+            Hit h {};
+            if (alive) {
+                h = trace_fast<false>(s, ray.o, ray.d, ray.t);
+                cnt.bounce++;
+                hit = h.prim >= 0;
+                if (!hit) {
+                    missEnd = true;
+                    alive = false;
+                }
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            unsigned base = 0;
+            if (lane == 0 && ballot)
+                base = atomicAdd(wb.counts + level, unsigned(__popc(ballot)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+                const unsigned slot = base + unsigned(__popc(ballot & below));
+                slots[level] = slot;
+                ray.t = h.t;
+                HitRec r;
+                resolve_hit(s, p.features, fast_hit_rows(s, h), h.gid, ray, r);
+                wf_write_record(wb, unsigned(level), slot, r);
+                wb.next[size_t(level - 1) * wb.cap + slots[level - 1]] = slot;
+                n = level + 1;
+                Ray nextRay;
+                if (level >= p.ray_depth || !reflection_ray(r, nextRay))
+                    alive = false;
+                else
+                    ray = nextRay;
+            }
+        }
+        if (live) {
+            reference_calls(cnt, n, missEnd, p.shadow_rays_per_hit);
+            const uint2 m = make_uint2(pixel, unsigned(n) | (missEnd ? 256u : 0u));
+            wb.meta[slots[0]].y = m.y; // (32-bit store: the level-0 shadow pass may be reading .x of this entry)
+            for (int k = 1; k < n; k++)
+                wb.meta[size_t(k) * wb.cap + slots[k]] = m;
         }
     }
     flush_counters(cnt, gcnt);
@@ -318,16 +481,16 @@ __device__ __forceinline__ RegroupHit regroup_fetch(const RegroupHit& h, unsigne
 // C3 0.80 -> 0.89 ms with 8).  Both instantiations are launched; the one not selected returns at once (the queue lengths only
 // exist on the device).
 constexpr unsigned kRegroupWideUnits = 1250000u; // 20 M shadow rays with 16 samples per evaluation
-__device__ __forceinline__ unsigned wf_regroup_samples_per_lane(const DevParams& p, const WaveBuffers& wb)
+__device__ __forceinline__ unsigned wf_regroup_samples_per_lane(const DevParams& p, unsigned units)
 {
-    unsigned long long units = 0;
-    for (unsigned k = 0; k < p.levels; k++)
-        units += (unsigned long long)wb.counts[k] * (p.draws_per_hit == 0 ? 1u : (1u << k));
     return units >= kRegroupWideUnits && p.samples_per_hit >= 8 ? 8u : 4u;
 }
 
+// levelBegin / levelEnd: the recursion levels this launch covers (the whole frame, or level 0 and the deeper levels in separate
+// launches when the chain stage is split); counterIdx: its chunk counter in wb.counts
 template <unsigned kGroup>
-__global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt)
+__global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevScene s, DevParams p, WaveBuffers wb, Counters* __restrict__ gcnt,
+    unsigned levelBegin, unsigned levelEnd, unsigned counterIdx)
 {
     __shared__ unsigned char laneOfRank[4][32];
 #if CGE_VIS_SHORT_STACK > 0
@@ -344,9 +507,10 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevSc
     cum[0] = 0;
     for (unsigned k = 0; k < p.levels; k++)
         cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
-    const unsigned long long total = (unsigned long long)cum[p.levels] * groups;
+    const unsigned long long itemBase = (unsigned long long)cum[levelBegin] * groups;
+    const unsigned long long total = (unsigned long long)(cum[levelEnd] - cum[levelBegin]) * groups;
     unsigned long long nshadow = 0;
-    if (!wf_use_visibility_bytes(p, wb) || wf_regroup_samples_per_lane(p, wb) != kGroup)
+    if (!wf_use_visibility_bytes(p, wb) || wf_regroup_samples_per_lane(p, cum[levelEnd] - cum[levelBegin]) != kGroup)
         return;
     // one shadow ray of hit h, sample sg; visits (optional) counts the nodes it walked; updates h.occluder
     auto trace_sample = [&](RegroupHit& h, unsigned sg, unsigned* visits) {
@@ -373,15 +537,15 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevSc
     for (;;) {
         unsigned chunk = 0;
         if (lane == 0)
-            chunk = atomicAdd(wb.counts + 18, 1u);
+            chunk = atomicAdd(wb.counts + counterIdx, 1u);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         const unsigned long long first = (unsigned long long)chunk * 32ull;
         if (first >= total)
             break;
-        const unsigned long long item = first + lane;
+        const unsigned long long item = itemBase + first + lane;
         RegroupHit own {};
         own.occluder = -1;
-        own.valid = item < total ? 1u : 0u;
+        own.valid = first + lane < total ? 1u : 0u;
         unsigned visits = 0;
         if (own.valid) {
             unsigned k = 0;
