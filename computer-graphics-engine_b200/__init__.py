@@ -107,7 +107,8 @@ def lib() -> C.CDLL:
         l.cge_scene_bvh_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
         l.cge_scene_bvh_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.cge_bvh_build_reference_order.argtypes = [C.POINTER(CgeSceneDesc), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] + [C.POINTER(C.c_uint32)] * 3
-        l.cge_bvh_validate.argtypes = [C.POINTER(CgeSceneDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        if hasattr(l, "cge_bvh_validate"):
+            l.cge_bvh_validate.argtypes = [C.POINTER(CgeSceneDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         l.cge_camera_from_trackball.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                                 C.POINTER(CgeCamera)]
         l.cge_fast_bvh_build.argtypes = [C.POINTER(CgeSceneDesc), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p] \
@@ -125,7 +126,8 @@ def lib() -> C.CDLL:
         l.cge_comm_unique_id.argtypes = [C.c_void_p]
         l.cge_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         l.cge_comm_destroy.argtypes = [C.c_void_p]
-        l.cge_comm_host_frame.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        if hasattr(l, "cge_comm_host_frame"):  # (absent from older development builds loaded through CGE_LIB for A/B runs)
+            l.cge_comm_host_frame.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         l.cge_render_distributed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CgeCamera), C.POINTER(CgeParams),
                                              C.c_void_p, C.c_void_p, C.POINTER(CgeStats)]
         l.cge_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]

@@ -132,7 +132,7 @@ struct cge_scene {
     int device = 0;
     int sm_count = 0;
     DevScene dev {};
-    DevBuf<float4> nodes, tris, fnodes, ftris, shade, materials, sph_rows, sph_boxes;
+    DevBuf<float4> nodes, tris, fnodes, f4nodes, ftris, shade, materials, sph_rows, sph_boxes;
     DevBuf<uint32_t> sph_box_off, fpos;
     DevBuf<uint4> qnodes;
     FastBvh fast;
@@ -1243,6 +1243,72 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
         }
     }
 
+    // ---- the fast tree collapsed to 4 children per node (dev_scene.h f4nodes), for the shadow rays: every node takes in the
+    //      children of its larger (by surface area) inner children until it has four -----------------------------------------
+    std::vector<float4> f4nodes;
+    uint32_t f4root = sc->fast.root;
+    if (!sc->fast.nodes.empty()) {
+        struct Cand {
+            float lo[3], hi[3];
+            uint32_t ref;
+        };
+        auto area = [](const Cand& c) {
+            const float ex = c.hi[0] - c.lo[0], ey = c.hi[1] - c.lo[1], ez = c.hi[2] - c.lo[2];
+            return ex * ey + ey * ez + ez * ex;
+        };
+        auto childrenOf = [&](uint32_t inner, Cand& l, Cand& r) {
+            const FastNode& n = sc->fast.nodes[inner];
+            std::memcpy(l.lo, n.l_lo, 12), std::memcpy(l.hi, n.l_hi, 12), l.ref = n.left;
+            std::memcpy(r.lo, n.r_lo, 12), std::memcpy(r.hi, n.r_hi, 12), r.ref = n.right;
+        };
+        // iterative (the tree can be 60 levels deep and has ~n/2 nodes): a work list of (binary inner node, slot of its 4-wide node)
+        std::vector<std::pair<uint32_t, uint32_t>> todo;
+        auto newNode = [&]() {
+            f4nodes.resize(f4nodes.size() + 8, f4(0, 0, 0, 0));
+            return uint32_t(f4nodes.size() / 8 - 1);
+        };
+        f4root = newNode();
+        todo.push_back({ sc->fast.root, f4root });
+        while (!todo.empty()) {
+            const auto [inner, slot] = todo.back();
+            todo.pop_back();
+            Cand c[4];
+            int n = 2;
+            childrenOf(inner, c[0], c[1]);
+            while (n < 4) {
+                int pick = -1;
+                for (int k = 0; k < n; k++)
+                    if (!(c[k].ref & kFastLeafBit) && (pick < 0 || area(c[k]) > area(c[pick])))
+                        pick = k;
+                if (pick < 0)
+                    break;
+                Cand l, r;
+                childrenOf(c[pick].ref, l, r);
+                c[pick] = l;
+                c[n++] = r;
+            }
+            uint32_t refs[4];
+            for (int k = 0; k < 4; k++) {
+                if (k >= n) {
+                    refs[k] = 0x7fffffffu;
+                    for (int a = 0; a < 3; a++)
+                        c[k].lo[a] = 3e38f, c[k].hi[a] = -3e38f;
+                } else if (c[k].ref & kFastLeafBit) {
+                    refs[k] = c[k].ref;
+                } else {
+                    refs[k] = newNode();
+                    todo.push_back({ c[k].ref, refs[k] });
+                }
+            }
+            float4* q = &f4nodes[size_t(slot) * 8];
+            for (int a = 0; a < 3; a++) {
+                q[a] = f4(c[0].lo[a], c[1].lo[a], c[2].lo[a], c[3].lo[a]);
+                q[3 + a] = f4(c[0].hi[a], c[1].hi[a], c[2].hi[a], c[3].hi[a]);
+            }
+            q[6] = f4(bitsf(refs[0]), bitsf(refs[1]), bitsf(refs[2]), bitsf(refs[3]));
+        }
+    }
+
     // ---- the fast tree once more with quantised boxes (dev_scene.h qnodes), for the shadow rays ----------------------------
     std::vector<uint4> qnodes;
     float qlo[3] = { 0, 0, 0 }, qext[3] = { 1, 1, 1 };
@@ -1347,6 +1413,7 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     up(sc->nodes, nodes);
     up(sc->tris, tris);
     up(sc->fnodes, fnodes);
+    up(sc->f4nodes, f4nodes);
     up(sc->qnodes, qnodes);
     up(sc->ftris, ftris);
     up(sc->sph_rows, sphRows);
@@ -1365,6 +1432,8 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     sc->dev.nodes = sc->nodes.p;
     sc->dev.tris = sc->tris.p;
     sc->dev.fnodes = sc->fnodes.p;
+    sc->dev.f4nodes = sc->f4nodes.p;
+    sc->dev.f4root = f4root;
     sc->dev.qnodes = sc->qnodes.p;
     for (int k = 0; k < 3; k++) {
         sc->dev.qlo[k] = qlo[k];
@@ -1460,6 +1529,7 @@ int cge_scene_destroy(cge_scene* sc)
     sc->nodes.release();
     sc->tris.release();
     sc->fnodes.release();
+    sc->f4nodes.release();
     sc->qnodes.release();
     sc->ftris.release();
     sc->sph_rows.release();

@@ -59,6 +59,10 @@ struct DevScene {
     const float4* tris;
     const float4* fnodes;
     const uint4* qnodes; // the FAST tree again, 32 B per inner node, boxes on a 15-bit grid (below): walked by shadow rays
+    const float4* f4nodes; // the FAST tree collapsed to 4 children per node, 8 x float4 (128 B) per node, walked by the shadow rays:
+                           //   rows 0..5 = lower.x[4], lower.y[4], lower.z[4], upper.x[4], upper.y[4], upper.z[4] of the children,
+                           //   row 6 = the 4 child references (packed as in fnodes; 0x7fffffff = no child), row 7 unused
+    uint32_t f4root;       // packed reference of the 4-wide tree's root
     const float4* ftris;
     const float4* shade;
     const float4* materials;

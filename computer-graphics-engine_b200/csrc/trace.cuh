@@ -388,6 +388,13 @@ __device__ __forceinline__ void slab_box_q(const SlabRayQ& r, unsigned wx, unsig
     ext = min3(tfx, tfy, tfz);
 }
 
+#ifndef CGE_VIS_SHORT_STACK
+#define CGE_VIS_SHORT_STACK 0 // > 0: the shadow-ray kernel keeps that many stack entries per lane in shared memory (SharedStack
+                              // below) instead of the per-thread local array.  Measured on B200, shadow pass of
+                              // C5 / a 1/8 share / C3: local array 12.07 / 1.75 / 0.86 ms; 12 shared entries 14.99 / 2.14 / 0.96 ms
+                              // (10 CTAs per SM, 48 registers: 13.39 / 1.98 / 0.88; 16 entries: 13.41 / 1.93 / 0.88): the index
+                              // arithmetic and the overflow test cost more than the L1 transactions they save.  Off.
+#endif
 // ---- traversal stacks ------------------------------------------------------------------------------------------------------
 // LocalStack: a per-thread array (local memory: L1-resident, but every push / pop is an L1 transaction of its own).
 // SharedStack: the first kShort entries of every lane live in shared memory, lane-interleaved (entry e of thread t at
@@ -406,6 +413,7 @@ struct LocalStack {
         x = v[--sp];
         return true;
     }
+    __device__ __forceinline__ unsigned pop_or(unsigned dflt) { return sp > 0 ? v[--sp] : dflt; }
 };
 template <int kShort>
 struct SharedStack {
@@ -435,12 +443,20 @@ struct SharedStack {
         x = sp < kShort ? s[sp][tid] : ovf[sp - kShort];
         return true;
     }
+    __device__ __forceinline__ unsigned pop_or(unsigned dflt)
+    {
+        unsigned x = dflt;
+        pop(x);
+        return x;
+    }
 };
 
 // Shadow rays (src/light.cpp:60-72: closest hit with ray.t = 1 used as a boolean): is ANY triangle accepted with 0 <= t <= 1?
 // Lean specialisation of trace_fast<true>: the bound is the constant 1, so the stack needs no entry distances and no
 // re-culling, and there is no tie bookkeeping.  Returns the blocking triangle (index into ftris), kSphereBlocker, or -1 (visible).
 // kCountVisits: *visits receives the number of inner nodes the ray visited (wf_vis_regroup_kernel ranks a warp's hits by it)
+// stk is used with CGE_VIS_SHORT_STACK > 0 only: otherwise the stack is a plain local array of this function (a stack OBJECT
+// that outlives the call - even the trivial LocalStack - measured 5 % slower: 12.72 vs 12.12 ms on the C5 shadow pass).
 template <bool kCountVisits, typename Stack>
 __device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
 {
@@ -451,7 +467,12 @@ __device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, co
 #else
     const SlabRay sr = slab_ray(o, d);
 #endif
+#if CGE_VIS_SHORT_STACK == 0
+    unsigned rawStack[kFastStackSize];
+    int rawSp = 0;
+#else
     stk.reset();
+#endif
     constexpr unsigned kDone = 0x7fffffffu;
     unsigned cur = s.froot;
     while (cur != kDone) {
@@ -486,20 +507,102 @@ __device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, co
 #endif
             if (hitL && hitR) {
                 const unsigned far = leftFirst ? cr : cl;
+#if CGE_VIS_SHORT_STACK == 0
+                rawStack[rawSp++] = far;
+#else
                 stk.push(far);
+#endif
 #if CGE_PREFETCH == 1
                 prefetch_child(s, far);
 #endif
             }
             if (hitL || hitR)
                 cur = leftFirst ? cl : cr;
-            else if (!stk.pop(cur))
-                cur = kDone;
+            else
+#if CGE_VIS_SHORT_STACK == 0
+                cur = rawSp > 0 ? rawStack[--rawSp] : kDone;
+#else
+                cur = stk.pop_or(kDone);
+#endif
         }
         if (cur == kDone)
             break;
         const unsigned first = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
         for (unsigned i = first; i < first + count; i++) {
+            float t;
+            float4 r5;
+            if (triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, 1.0f, t, r5))
+                return int(i);
+        }
+#if CGE_VIS_SHORT_STACK == 0
+        cur = rawSp > 0 ? rawStack[--rawSp] : kDone;
+#else
+        cur = stk.pop_or(kDone);
+#endif
+    }
+    return s.n_sph && sphere_pass_shadow(s, o, d, 1.0f) ? kSphereBlocker : -1;
+}
+
+#ifndef CGE_SHADOW_BVH4
+#define CGE_SHADOW_BVH4 0 // shadow rays walk the 4-wide collapse of the fast tree (dev_scene.h f4nodes): half the dependent node
+                          // fetches per ray for about the same box tests.  0: the binary tree (A/B in DESIGN.md 5.9)
+#endif
+// The same any-hit walk over the 4-wide tree.  One visit = one 112-byte node = four box tests; the near / far plane of every slab
+// is picked by LOADING the right row (the ray's sign bits choose row offsets once per ray) instead of selecting per box.  Among
+// the children hit the one that starts farthest along the ray is entered first (CGE_SHADOW_FAR_FIRST), the others are pushed.
+template <bool kCountVisits, typename Stack>
+__device__ __forceinline__ int trace_shadow4_on(Stack& stk, const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
+{
+    if (s.n_ftris == 0)
+        return s.n_sph && sphere_pass_shadow(s, o, d, 1.0f) ? kSphereBlocker : -1;
+    const SlabRay sr = slab_ray(o, d);
+    const int nearX = sr.nx ? 3 : 0, farX = 3 - nearX, nearY = sr.ny ? 4 : 1, farY = 5 - nearY, nearZ = sr.nz ? 5 : 2, farZ = 7 - nearZ;
+    stk.reset();
+    constexpr unsigned kDone = 0x7fffffffu;
+    unsigned cur = s.f4root;
+    while (cur != kDone) {
+        while (cur < kDone) {
+            if (kCountVisits)
+                (*visits)++;
+            const float4* nd = s.f4nodes + size_t(cur) * 8;
+            const float4 rf = ldg4(nd + 6);
+            const float4 nx = ldg4(nd + nearX), ny = ldg4(nd + nearY), nz = ldg4(nd + nearZ);
+            const float4 fx = ldg4(nd + farX), fy = ldg4(nd + farY), fz = ldg4(nd + farZ);
+            const unsigned ref[4] = { __float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w) };
+            const float nxs[4] = { nx.x, nx.y, nx.z, nx.w }, nys[4] = { ny.x, ny.y, ny.z, ny.w }, nzs[4] = { nz.x, nz.y, nz.z, nz.w };
+            const float fxs[4] = { fx.x, fx.y, fx.z, fx.w }, fys[4] = { fy.x, fy.y, fy.z, fy.w }, fzs[4] = { fz.x, fz.y, fz.z, fz.w };
+            float ent[4];
+            bool hit[4];
+            int first = -1;
+            float firstEnt = -1.0f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float tn = max3(__fmaf_rn(nxs[c], sr.inv.x, sr.cNear.x), __fmaf_rn(nys[c], sr.inv.y, sr.cNear.y),
+                    __fmaf_rn(nzs[c], sr.inv.z, sr.cNear.z));
+                const float tf = min3(__fmaf_rn(fxs[c], sr.inv.x, sr.cFar.x), __fmaf_rn(fys[c], sr.inv.y, sr.cFar.y),
+                    __fmaf_rn(fzs[c], sr.inv.z, sr.cFar.z));
+                ent[c] = fmaxf(tn, 0.0f);
+                hit[c] = ref[c] != kDone && ent[c] <= tf * 1.000002f && ent[c] <= 1.0001f;
+#if CGE_SHADOW_FAR_FIRST
+                if (hit[c] && ent[c] > firstEnt)
+#else
+                if (hit[c] && (first < 0 || ent[c] < firstEnt))
+#endif
+                    first = c, firstEnt = ent[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (hit[c] && c != first)
+                    stk.push(ref[c]);
+            if (first >= 0)
+                cur = ref[first];
+            else if (!stk.pop(cur))
+                cur = kDone;
+        }
+        if (cur == kDone)
+            break;
+        const unsigned firstTri = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+        for (unsigned i = firstTri; i < firstTri + count; i++) {
             float t;
             float4 r5;
             if (triangle_rows_hit(s.ftris + size_t(i) * kTriRows, o, d, 1.0f, t, r5))
@@ -515,7 +618,11 @@ template <bool kCountVisits = false>
 __device__ __forceinline__ int trace_shadow(const DevScene& s, const vec3 o, const vec3 d, unsigned* visits = nullptr)
 {
     LocalStack stk;
+#if CGE_SHADOW_BVH4
+    return trace_shadow4_on<kCountVisits>(stk, s, o, d, visits);
+#else
     return trace_shadow_on<kCountVisits>(stk, s, o, d, visits);
+#endif
 }
 
 } // namespace cge

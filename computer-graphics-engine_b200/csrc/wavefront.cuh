@@ -432,13 +432,6 @@ __device__ __forceinline__ LightSample wf_sample(const DevScene& s, const DevPar
     return sample_light(L, type, int(si), p, pixel, ctr);
 }
 
-#ifndef CGE_VIS_SHORT_STACK
-#define CGE_VIS_SHORT_STACK 0 // > 0: the shadow-ray kernel keeps that many stack entries per lane in shared memory (trace.cuh
-                              // SharedStack) instead of the per-thread local array.  Measured on B200, shadow pass of
-                              // C5 / a 1/8 share / C3: local array 12.07 / 1.75 / 0.86 ms; 12 shared entries 14.99 / 2.14 / 0.96 ms
-                              // (10 CTAs per SM, 48 registers: 13.39 / 1.98 / 0.88; 16 entries: 13.41 / 1.93 / 0.88): the index
-                              // arithmetic and the overflow test cost more than the L1 transactions they save.  Off.
-#endif
 constexpr int kVisShortStack = CGE_VIS_SHORT_STACK > 0 ? CGE_VIS_SHORT_STACK : 1;
 #ifndef CGE_MINB_VIS
 #define CGE_MINB_VIS 12 // resident 128-thread CTAs per SM the shadow-ray kernel is compiled for (A/B in DESIGN.md 5.5)
@@ -524,7 +517,11 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevSc
             if (h.occluder >= 0 && triangle_rows_hit(s.ftris + size_t(h.occluder) * kTriRows, h.o, d, 1.0f, t, r5)) {
                 v = 0;
             } else {
+#if CGE_SHADOW_BVH4
+                const int blocker = visits ? trace_shadow4_on<true>(stk, s, h.o, d, visits) : trace_shadow4_on<false>(stk, s, h.o, d);
+#else
                 const int blocker = visits ? trace_shadow_on<true>(stk, s, h.o, d, visits) : trace_shadow_on<false>(stk, s, h.o, d);
+#endif
                 if (blocker != -1) {
                     v = 0;
                     if (blocker >= 0)
