@@ -1247,7 +1247,7 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     //      children of its larger (by surface area) inner children until it has four -----------------------------------------
     std::vector<float4> f4nodes;
     uint32_t f4root = sc->fast.root;
-    if (!sc->fast.nodes.empty()) {
+    if (CGE_SHADOW_BVH4 && !sc->fast.nodes.empty()) { // (measured slower than the binary walk, DESIGN.md 5.9: compiled out by default)
         struct Cand {
             float lo[3], hi[3];
             uint32_t ref;

@@ -544,8 +544,11 @@ __device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, co
 }
 
 #ifndef CGE_SHADOW_BVH4
-#define CGE_SHADOW_BVH4 0 // shadow rays walk the 4-wide collapse of the fast tree (dev_scene.h f4nodes): half the dependent node
-                          // fetches per ray for about the same box tests.  0: the binary tree (A/B in DESIGN.md 5.9)
+#define CGE_SHADOW_BVH4 0 // 1: shadow rays walk the 4-wide collapse of the fast tree (dev_scene.h f4nodes): half the dependent node
+                          // fetches per ray for about the same box tests.  Measured on B200, C5 shadow pass: binary
+                          // tree 12.8 ms (same build), 4-wide 19.6 / 16.2 / 15.1 ms at 12 / 10 / 8 CTAs per SM (40 / 48 / 64
+                          // registers: 436 / 348 / 140 bytes of spills): the 28 box values of a node do not fit the register
+                          // budget the latency-bound walk needs.  Off.
 #endif
 // The same any-hit walk over the 4-wide tree.  One visit = one 112-byte node = four box tests; the near / far plane of every slab
 // is picked by LOADING the right row (the ray's sign bits choose row offsets once per ray) instead of selecting per box.  Among
