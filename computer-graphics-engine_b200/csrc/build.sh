@@ -10,7 +10,7 @@ REPO=$(cd "$PKG/.." && pwd)
 EXTRA=${CGE_NVCC_EXTRA:-}
 OUT=${CGE_OUT:-$PKG/libcge.so}
 LOG=${OUT%.so}_ptxas.log   # registers / spills / shared memory per kernel (-Xptxas -v)
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 ${CGE_LINEINFO--lineinfo} -std=c++17 \
     -fmad=false -prec-div=true -prec-sqrt=true \
     -Xcompiler -fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function,-pthread \
     -Xptxas -v $EXTRA \

@@ -91,7 +91,7 @@ struct Scratch {
     size_t gatherPixels = 0;
     // wavefront queues (wavefront.cuh), grown on demand and kept for the next frame
     WaveBuffers wave {};
-    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveSub = 0, waveCont = 0;
+    size_t waveRecFloats = 0, waveMeta = 0, waveNext = 0, waveDirFloats = 0, waveVis = 0, waveSub = 0, waveCont = 0, waveHard = 0;
     // split chain stage (wavefront.cuh wf_primary_kernel / wf_continue_kernel): the level-0 shadow pass runs on auxStream beside
     // the continuation kernel
     cudaStream_t auxStream = nullptr;
@@ -132,7 +132,7 @@ struct cge_scene {
     int device = 0;
     int sm_count = 0;
     DevScene dev {};
-    DevBuf<float4> nodes, tris, fnodes, f4nodes, ftris, shade, materials, sph_rows, sph_boxes;
+    DevBuf<float4> nodes, tris, fnodes, f4nodes, onodes, ftris, shade, materials, sph_rows, sph_boxes;
     DevBuf<uint32_t> sph_box_off, fpos;
     DevBuf<uint4> qnodes;
     FastBvh fast;
@@ -740,8 +740,18 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
         wp.packet_budget = uint32_t(env_int("CGE_PACKET_BUDGET", 48));
         wp.packet_leaf_cost = uint32_t(env_int("CGE_PACKET_LEAF_COST", 4));
         wp.shade_mode = visFits ? 2 : 1;
+        // The light-hull pre-pass (wavefront.cuh wf_vis_cull_kernel): hits none of whose shadow rays can be blocked are settled by one
+        // conservative walk; the shadow-ray kernel traces the rest.  Scenes with spheres keep every hit (a sphere is not judged by
+        // plane tests).  CGE_VIS_CULL=0 switches it off (A/B, tests: the frame is the same bit for bit).
+        // Pays for its extra launch on large launches only (measured on B200, DESIGN.md 5.10: C5 frame 14.20 -> 13.64 ms, but a
+        // 1/8 share 2.38 -> 2.47 ms and C3 1.04 -> 1.08 ms): on from 1.5 Mpixel per launch, CGE_VIS_CULL=0 / 1 forces it.
+        const bool smallLaunch = size_t(myTiles) * 32 < (size_t(3) << 19);
+        wp.vis_cull = visFits && ds.n_sph == 0 && ds.n_ftris > 0 && env_int("CGE_VIS_CULL", smallLaunch ? 0 : 1) ? 1u : 0u;
+        wp.cull_budget = uint32_t(env_int("CGE_CULL_BUDGET", 96));
         if (err == cudaSuccess && visFits)
             err = grow(s->wave.vis, s->waveVis, ws.vis, 1);
+        if (err == cudaSuccess && wp.vis_cull)
+            err = grow(s->wave.hard, s->waveHard, ws.meta, sizeof(unsigned));
         if (err == cudaSuccess && !s->wave.counts)
             err = cudaMalloc(reinterpret_cast<void**>(&s->wave.counts), 64 * sizeof(unsigned));
         if (err == cudaSuccess)
@@ -753,9 +763,18 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
         // Measured on B200: a 1/8 share of C5 (one rank of eight) 2.59 -> 2.52 ms; the whole frame as one pipeline
         // 15.57 -> 15.67 ms and as four concurrent bands 15.33 -> 15.91 ms (bands already fill the tails, and the two shadow
         // launches each end in a tail of their own): on for launches below the band threshold only.
-        const bool smallLaunch = size_t(myTiles) * 32 < (size_t(3) << 19);
         const bool split = visFits && !dp.aa_side && wp.levels > 1 && env_int("CGE_CHAIN_SPLIT", smallLaunch ? 1 : 0);
         auto launchVis = [&](cudaStream_t st, unsigned levelBegin, unsigned levelEnd, unsigned counterIdx) {
+            if (wp.vis_cull) { // (chunk counters 22 / 23 beside the shadow-ray kernel's 18 / 19)
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_vis_cull_kernel, 128, 0);
+                if (err != cudaSuccess)
+                    return;
+                wf_vis_cull_kernel<<<unsigned(sc->sm_count * std::max(perSm, 1)), 128, 0, st>>>(ds, wp, s->wave, levelBegin, levelEnd, counterIdx + 4);
+                err = cudaGetLastError();
+                *launches += 1;
+                if (err != cudaSuccess)
+                    return;
+            }
             auto go = [&](auto kern) {
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
                 if (err == cudaSuccess) {
@@ -1000,6 +1019,12 @@ int fill_stats(const std::vector<Scratch*>& bands, cge_stats* st, uint32_t launc
         st->box_tests += c.box;
         st->tri_tests += c.tri;
         st->reference_shadow_rays += c.reference_shadow;
+        if (b->staged && b->wave.counts) { // the light-hull pre-pass counts in the pipeline's own counter block (wavefront.cuh)
+            unsigned long long culled = 0;
+            CGE_CUDA(cudaMemcpyAsync(&culled, b->wave.counts + 48, sizeof(culled), cudaMemcpyDeviceToHost, b->stream));
+            CGE_CUDA(cudaStreamSynchronize(b->stream));
+            st->shadow_samples_culled += culled;
+        }
         if (b->staged) // summed over the bands (which overlap in time when there are several)
             for (int k = 0; k < 4; k++) {
                 CGE_CUDA(cudaEventElapsedTime(&ms, b->stage[k], b->stage[k + 1]));
@@ -1243,6 +1268,33 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
         }
     }
 
+    // ---- eight octant-sorted copies of the inner nodes for the shadow rays (dev_scene.h onodes, trace.cuh CGE_OCTANT_NODES) ------
+    std::vector<float4> onodes;
+    if (CGE_OCTANT_NODES && sc->fast.nodes.size() >= (size_t(1) << 27)) { // (inner references of copy 7 must stay below 2^31 - 1)
+        delete sc;
+        return fail(CGE_ERR_UNSUPPORTED, "fast BVH has too many inner nodes");
+    }
+    if (CGE_OCTANT_NODES && !sc->fast.nodes.empty()) {
+        const size_t nn = sc->fast.nodes.size();
+        onodes.resize(8 * nn * kNodeRows);
+        for (uint32_t o = 0; o < 8; o++)
+            for (size_t i = 0; i < nn; i++) {
+                const FastNode& n = sc->fast.nodes[i];
+                float ln[3], lf[3], rn[3], rf[3];
+                for (int a = 0; a < 3; a++) {
+                    const bool neg = (o >> a) & 1u;
+                    ln[a] = neg ? n.l_hi[a] : n.l_lo[a], lf[a] = neg ? n.l_lo[a] : n.l_hi[a];
+                    rn[a] = neg ? n.r_hi[a] : n.r_lo[a], rf[a] = neg ? n.r_lo[a] : n.r_hi[a];
+                }
+                auto ref = [&](uint32_t r) { return (r & kFastLeafBit) ? r : r + o * uint32_t(nn); };
+                float4* q = &onodes[(size_t(o) * nn + i) * kNodeRows];
+                q[0] = f4(ln[0], ln[1], ln[2], lf[0]);
+                q[1] = f4(lf[1], lf[2], rn[0], rn[1]);
+                q[2] = f4(rn[2], rf[0], rf[1], rf[2]);
+                q[3] = f4(bitsf(ref(n.left)), bitsf(ref(n.right)), fnodes[i * kNodeRows + 3].z, fnodes[i * kNodeRows + 3].w);
+            }
+    }
+
     // ---- the fast tree collapsed to 4 children per node (dev_scene.h f4nodes), for the shadow rays: every node takes in the
     //      children of its larger (by surface area) inner children until it has four -----------------------------------------
     std::vector<float4> f4nodes;
@@ -1414,6 +1466,7 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     up(sc->tris, tris);
     up(sc->fnodes, fnodes);
     up(sc->f4nodes, f4nodes);
+    up(sc->onodes, onodes);
     up(sc->qnodes, qnodes);
     up(sc->ftris, ftris);
     up(sc->sph_rows, sphRows);
@@ -1433,6 +1486,8 @@ int cge_scene_create(const cge_scene_desc* d, int device, cge_scene** out)
     sc->dev.tris = sc->tris.p;
     sc->dev.fnodes = sc->fnodes.p;
     sc->dev.f4nodes = sc->f4nodes.p;
+    sc->dev.onodes = sc->onodes.p;
+    sc->dev.n_fnodes = uint32_t(sc->fast.nodes.size());
     sc->dev.f4root = f4root;
     sc->dev.qnodes = sc->qnodes.p;
     for (int k = 0; k < 3; k++) {
@@ -1498,6 +1553,7 @@ int cge_scene_destroy(cge_scene* sc)
         cudaFree(s->wave.vis);
         cudaFree(s->wave.sub);
         cudaFree(s->wave.cont);
+        cudaFree(s->wave.hard);
         if (s->auxStream)
             cudaStreamDestroy(s->auxStream);
         if (s->evPrimary)
@@ -1530,6 +1586,7 @@ int cge_scene_destroy(cge_scene* sc)
     sc->tris.release();
     sc->fnodes.release();
     sc->f4nodes.release();
+    sc->onodes.release();
     sc->qnodes.release();
     sc->ftris.release();
     sc->sph_rows.release();

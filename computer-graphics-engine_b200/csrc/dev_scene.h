@@ -58,6 +58,11 @@ struct DevScene {
     const float4* nodes;
     const float4* tris;
     const float4* fnodes;
+    const float4* onodes; // eight copies of fnodes for the shadow rays, copy o (bit 0 / 1 / 2 = the ray moves towards -x / -y / -z) at
+                          // node index o * n_fnodes: q0 = L.near.xyz, L.far.x  q1 = L.far.yz, R.near.xy  q2 = R.near.z, R.far.xyz with
+                          // near = (direction negative on that axis ? upper : lower); q3 as in fnodes, but INNER child references
+                          // are offset by o * n_fnodes, so a walk that starts in copy o stays in it
+    uint32_t n_fnodes;    // inner nodes of the fast tree
     const uint4* qnodes; // the FAST tree again, 32 B per inner node, boxes on a 15-bit grid (below): walked by shadow rays
     const float4* f4nodes; // the FAST tree collapsed to 4 children per node, 8 x float4 (128 B) per node, walked by the shadow rays:
                            //   rows 0..5 = lower.x[4], lower.y[4], lower.z[4], upper.x[4], upper.y[4], upper.z[4] of the children,
@@ -136,6 +141,8 @@ struct DevParams {
     uint32_t debug_cycles;    // CGE_DEV_FLAG_DEBUG_CYCLES
     uint32_t shade_mode;      // wavefront: 1 = wf_shade_kernel<false> traces the shadow rays itself, 2 = visibility bytes (wavefront.cuh)
     uint32_t aa_side;              // raysPerPixelSide when extra.enableMultipleRaysPerPixel is set, else 0
+    uint32_t vis_cull;             // wavefront: the light-hull pre-pass ran, the shadow-ray kernel traces the hard lists (wavefront.cuh)
+    uint32_t cull_budget;          // inner nodes one hull walk of the pre-pass may visit
     uint32_t packet_budget, packet_leaf_cost; // shadow_packet.cuh: node visits a hull walk may spend, and what a leaf counts for
     float packet_fat;              // shadow_packet.cuh: a child box is deferred to the per-ray phase when the packet's hull is wider
                                    // than (the box's largest extent) / packet_fat where it enters the box

@@ -57,37 +57,7 @@ __device__ __forceinline__ unsigned packet_groups(const DevScene& s, const DevPa
     return groups;
 }
 
-// Per-axis constants of the hull test.  Constraint A: o + t * dmin <= hi, constraint B: o + t * dmax >= lo.
-//   all directions positive : B is the lower bound (entry), A the upper bound (exit)
-//   all directions negative : A is the lower bound, B the upper bound
-//   mixed signs             : A and B are both lower bounds, the axis has no upper bound
-// v1 = fma(sel ? hi : lo, k1, c1) is always a lower bound; v2 = fma(sel ? lo : hi, k2, c2) is an upper bound, or with `mixed`
-// a second lower bound.  The constants carry the cancellation slack of trace.cuh slab_ray, doubled: c -+ 2^-21 |c| moves each
-// plane ~8 ulps of the origin's coordinate outwards.
-struct HullAxis {
-    float k1, c1, k2, c2;
-    bool sel, mixed;
-};
-__device__ __forceinline__ HullAxis hull_axis(float o, float dmin, float dmax)
-{
-    auto recip = [](float v, float tiny) { return fabsf(v) > 1e-18f ? fdiv(1.0f, v) : tiny; };
-    HullAxis h;
-    const bool pos = dmin > 0.0f, neg = dmax < 0.0f;
-    const float iA = recip(dmin, pos ? 1e18f : -1e18f); // dmin == 0: no ray moves towards -axis: hi < o rejects
-    const float iB = recip(dmax, neg ? -1e18f : 1e18f);
-    const float cA = -fmul(o, iA), cB = -fmul(o, iB);
-    const float sA = fabsf(cA) * 4.76837158203125e-07f, sB = fabsf(cB) * 4.76837158203125e-07f;
-    h.sel = !pos; // v1 reads hi (constraint A) unless all directions are positive
-    h.mixed = !pos && !neg;
-    if (pos) {
-        h.k1 = iB, h.c1 = cB - sB; // lower
-        h.k2 = iA, h.c2 = cA + sA; // upper
-    } else {
-        h.k1 = iA, h.c1 = cA - sA;                           // lower
-        h.k2 = iB, h.c2 = h.mixed ? cB - sB : cB + sB; // second lower bound, or the upper bound
-    }
-    return h;
-}
+// (HullAxis / hull_axis: wavefront.cuh, shared with the light-hull pre-pass)
 
 template <unsigned kPacket>
 __global__ void __launch_bounds__(128, PacketCfg<kPacket>::kMinBlocks) wf_vis_packet_kernel(DevScene s, DevParams p, WaveBuffers wb,

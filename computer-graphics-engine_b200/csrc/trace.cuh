@@ -21,6 +21,24 @@ constexpr int kFastStackSize = 64;
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+#ifndef CGE_OCTANT_NODES
+#define CGE_OCTANT_NODES 1 // shadow rays walk one of EIGHT copies of the fast tree's inner nodes, chosen once per ray by the signs of its
+                           // direction: in copy o every slab's near plane is stored where the walk reads "near" (dev_scene.h onodes),
+                           // and inner child references already point into copy o.  Removes 12 FSEL + 3 FSETP of ~66 instructions per
+                           // visit; costs 8 x 64 B per inner node of HBM (C5: 8 x 24 MB)
+#endif
+#ifndef CGE_NODE_LD256
+#define CGE_NODE_LD256 1 // 1: the shadow walk fetches a 64-byte node with two 256-bit loads (LDG.E.256, new on sm_100) instead of
+                         // 3 x 128 + 1 x 64 bit: half the load instructions and L1 requests per visit
+#endif
+// 32 bytes (two float4 rows) in one 256-bit read-only load; p must be 32-byte aligned
+__device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 struct Hit {
     float t;
     int prim;      // index into the tree's leaf-ordered primitive array (-1: miss)
@@ -60,12 +78,45 @@ __device__ __forceinline__ bool triangle_rows_tail(const float4* __restrict__ tr
     return true;
 }
 
+#ifndef CGE_TRI_LD256
+#define CGE_TRI_LD256 0 // 1: a triangle's six rows are fetched as three 256-bit loads (rows 0-1, 2-3, 4-5; the record is 96 bytes and
+                        // 32-byte aligned) instead of up to six 128-bit ones.  Measured on B200: slower everywhere (C5
+                        // frame 13.64 -> 13.79 ms, C4 0.85 -> 0.905 ms): most tests end after the plane row, the second 16 bytes are
+                        // fetched for nothing.  Off.
+#endif
 __device__ __forceinline__ bool triangle_rows_hit(const float4* __restrict__ tr, const vec3 o, const vec3 d, float best, float& tOut,
     float4& r5)
 {
+#if CGE_TRI_LD256
+    float4 r0, r1;
+    ldg8(tr, r0, r1);
+    const vec3 n = v3(r0.x, r0.y, r0.z);
+    const float num = fsub(r0.w, dot(o, n)), den = dot(d, n);
+    if ((__float_as_uint(num) ^ __float_as_uint(den)) >> 31 && fabsf(num) >= 1e-30f && fabsf(den) <= 1e6f)
+        return false; // (see triangle_rows_tail)
+    const float t = fdiv(num, den); // I2
+    if (!(t >= 0.0f))
+        return false;
+    if (!(best >= t))
+        return false;
+    const vec3 p = d * t + o;
+    float4 r2, r3;
+    ldg8(tr + 2, r2, r3);
+    if (!(dot(v3(r1.w, r2.x, r2.y), p - v3(r1.x, r1.y, r1.z)) >= 0.0f)) // I3, archive order, short-circuit
+        return false;
+    if (!(dot(v3(r3.y, r3.z, r3.w), p - v3(r2.z, r2.w, r3.x)) >= 0.0f))
+        return false;
+    float4 r4;
+    ldg8(tr + 4, r4, r5);
+    if (!(dot(v3(r4.w, r5.x, r5.y), p - v3(r4.x, r4.y, r4.z)) >= 0.0f))
+        return false;
+    tOut = t;
+    return true;
+#else
     const float4 r0 = ldg4(tr);
     const vec3 n = v3(r0.x, r0.y, r0.z);
     return triangle_rows_tail(tr, n, fsub(r0.w, dot(o, n)), o, d, best, tOut, r5);
+#endif
 }
 
 template <bool kSpheres, bool kCount>
@@ -175,6 +226,18 @@ __device__ __forceinline__ void slab_box(const SlabRay& r, float lox, float loy,
     ext = min3(tfx, tfy, tfz);
 }
 
+// the same test on a node of the octant-sorted copies (dev_scene.h onodes): the near / far plane of every slab was picked when the
+// copy was written, so the 12 selects (and the 3 sign predicates) of slab_box are gone
+__device__ __forceinline__ void slab_box_sorted(const SlabRay& r, float nx, float ny, float nz, float fx, float fy, float fz, float& ent,
+    float& ext)
+{
+    const float tnx = __fmaf_rn(nx, r.inv.x, r.cNear.x), tfx = __fmaf_rn(fx, r.inv.x, r.cFar.x);
+    const float tny = __fmaf_rn(ny, r.inv.y, r.cNear.y), tfy = __fmaf_rn(fy, r.inv.y, r.cFar.y);
+    const float tnz = __fmaf_rn(nz, r.inv.z, r.cNear.z), tfz = __fmaf_rn(fz, r.inv.z, r.cFar.z);
+    ent = fmaxf(max3(tnx, tny, tnz), 0.0f);
+    ext = min3(tfx, tfy, tfz);
+}
+
 // ---- spheres beside the fast tree (dev_scene.h) ------------------------------------------------------------------------------------
 // Would the reference's traversal reach sphere i's leaf?  It tests the box of every node on the way from the root's child down
 // to the leaf with ray.t = FLT_MAX (src/bounding_volume_hierarchy.cpp:334-352); without enableAccelStructure it tests no box.
@@ -238,6 +301,13 @@ __device__ __forceinline__ const float4* fast_hit_rows(const DevScene& s, const 
 constexpr int kSphereBlocker = -2; // trace_shadow: blocked by a sphere (no triangle to remember)
 
 // Fast tree (triangles) + the sphere pass.
+#ifndef CGE_CLOSEST_OCTANT
+#define CGE_CLOSEST_OCTANT 0 // closest-hit rays (camera, reflection) on the octant-sorted node copies too: measured within noise
+                             // (C5 chain stage 1.31 -> 1.25 ms, C4 0.96 -> 0.94 ms in a build that was otherwise slower): off
+#endif
+#ifndef CGE_CLOSEST_LD256
+#define CGE_CLOSEST_LD256 0 // closest-hit rays fetch a node with two 256-bit loads: no change measured, off
+#endif
 template <bool kAnyHit, bool kCount = false>
 __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float tmax, unsigned* nbox = nullptr, unsigned* ntri = nullptr)
 {
@@ -263,7 +333,12 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
     uint2 stack[kFastStackSize]; // (child ref, entry distance bits): re-culled against the best t when popped
     int sp = 0;
     constexpr unsigned kDone = 0x7fffffffu; // not a valid inner-node index
+#if CGE_OCTANT_NODES && CGE_CLOSEST_OCTANT
+    // the copy of the inner nodes sorted for this ray's direction signs (dev_scene.h onodes)
+    unsigned cur = s.froot < kDone ? s.froot + ((sr.nx ? 1u : 0u) | (sr.ny ? 2u : 0u) | (sr.nz ? 4u : 0u)) * s.n_fnodes : s.froot;
+#else
     unsigned cur = s.froot;
+#endif
     auto pop = [&]() -> unsigned {
         while (sp > 0) {
             const uint2 e = stack[--sp];
@@ -277,16 +352,31 @@ __device__ Hit trace_fast(const DevScene& s, const vec3 o, const vec3 d, float t
     // so the two code paths are not interleaved lane by lane.
     while (cur != kDone) {
         while (cur < kDone) { // inner node (leaf references have bit 31 set)
+#if CGE_OCTANT_NODES && CGE_CLOSEST_OCTANT
+            const float4* nd = s.onodes + size_t(cur) * kNodeRows;
+#else
             const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+#endif
+#if CGE_CLOSEST_LD256
+            float4 q0, q1, q2, q3;
+            ldg8(nd + 2, q2, q3);
+            ldg8(nd, q0, q1);
+#else
             const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+#endif
             if (kCount)
                 *nbox += 2;
             // a box is skipped only if it starts clearly beyond the best hit so far; the slab test carries a small
             // multiplicative slack so that rounding can only ADD visits relative to the exact arithmetic
             const float bound = h.t + fmaxf(fabsf(h.t), 1.0f) * 1e-4f;
             float entL, extL, entR, extR;
+#if CGE_OCTANT_NODES && CGE_CLOSEST_OCTANT
+            slab_box_sorted(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
+            slab_box_sorted(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+#else
             slab_box(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
             slab_box(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+#endif
             const bool hitL = entL <= extL * 1.000002f && entL <= bound;
             const bool hitR = entR <= extR * 1.000002f && entR <= bound;
             const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
@@ -474,7 +564,11 @@ __device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, co
     stk.reset();
 #endif
     constexpr unsigned kDone = 0x7fffffffu;
+#if CGE_OCTANT_NODES && !CGE_QNODES
+    unsigned cur = s.froot < kDone ? s.froot + ((sr.nx ? 1u : 0u) | (sr.ny ? 2u : 0u) | (sr.nz ? 4u : 0u)) * s.n_fnodes : s.froot;
+#else
     unsigned cur = s.froot;
+#endif
     while (cur != kDone) {
         while (cur < kDone) {
             if (kCountVisits)
@@ -482,20 +576,42 @@ __device__ __forceinline__ int trace_shadow_on(Stack& stk, const DevScene& s, co
             float entL, extL, entR, extR;
 #if CGE_QNODES
             const uint4* nd = s.qnodes + size_t(cur) * 2;
+#if CGE_NODE_LD256
+            uint4 q0, q1;
+            asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w)
+                : "l"(nd));
+#else
             const uint4 q0 = __ldg(nd), q1 = __ldg(nd + 1);
+#endif
             slab_box_q(sr, q0.x, q0.y, q0.z, entL, extL);
             slab_box_q(sr, q1.x, q1.y, q1.z, entR, extR);
             const unsigned cl = q0.w, cr = q1.w;
 #else
+#if CGE_OCTANT_NODES
+            const float4* nd = s.onodes + size_t(cur) * kNodeRows;
+#else
             const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+#endif
+#if CGE_NODE_LD256
+            float4 q0, q1, q2, q3;
+            ldg8(nd + 2, q2, q3);
+            ldg8(nd, q0, q1);
+#else
             const float4 q3 = ldg4(nd + 3);
             const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2);
+#endif
 #if CGE_PREFETCH == 2
             prefetch_child(s, __float_as_uint(q3.x));
             prefetch_child(s, __float_as_uint(q3.y));
 #endif
+#if CGE_OCTANT_NODES
+            slab_box_sorted(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
+            slab_box_sorted(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+#else
             slab_box(sr, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
             slab_box(sr, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+#endif
             const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
 #endif
             const bool hitL = entL <= extL * 1.000002f && entL <= 1.0001f;

@@ -47,6 +47,8 @@ struct WaveBuffers {
     unsigned* counts;   // [0..15] queue length per level, [16] chain tile counter, [17] shade chunk counter, [18] / [19] shadow-ray chunk
                         // counters (level 0 / deeper levels when the chain stage is split), [20] continuation-queue length, [21] its
                         // chunk counter
+    unsigned* hard;     // [level][cap] queue slots of the hits the light-hull pre-pass could not resolve (wf_vis_cull_kernel); their
+                        // number per level is counts[32 + level]; counts[22] / [23] are that kernel's chunk counters
     unsigned* cont;     // [cap] level-0 queue slots of the hits whose chain goes on (wf_primary_kernel -> wf_continue_kernel)
     float* sub;         // multiple rays per pixel: [3][launch pixel][sub-ray] colour of every camera ray, summed by wf_resolve_kernel
     unsigned cap;
@@ -432,6 +434,287 @@ __device__ __forceinline__ LightSample wf_sample(const DevScene& s, const DevPar
     return sample_light(L, type, int(si), p, pixel, ctr);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// wf_vis_cull_kernel: the light-hull pre-pass of the shadow stage.  One lane = one hit (level, queue slot), whatever its copies
+// and samples: EVERY shadow ray the hit can need leaves the same point o (src/light.cpp:54-58) and ends inside the convex hull
+// of its lights' corner points (src/light.cpp:19-45: position = (v0 + hw * e01) + vw * e02 with hw, vw in [0, 1]; every float
+// operation is monotone, so each coordinate of every sample lies between the values at the corners).  The lane walks the fast tree
+// ONCE with that hull - the per-axis direction box [dmin, dmax] of (corner - o), evaluated per node exactly like a ray's slab test -
+// near child first, and looks at every triangle of every leaf the hull reaches:
+//   * a triangle none of the hull's rays can be accepted by is CLEAR (below: sign / magnitude of the plane parameter, then the
+//     four side planes of the pyramid (o, light corners) pushed outwards by a margin that covers the rounding of the archive's
+//     test);
+//   * if every triangle met is clear and the stack runs empty, no ray of the hit can be blocked: all its visibility bytes are 1
+//     and it is finished - one walk of ~25 nodes instead of copies x samples walks;
+//   * the first triangle that is not clear (or an exhausted budget) sends the hit to the HARD list of its level, which is what
+//     wf_vis_regroup_kernel then traces ray by ray, exactly as before.
+// The pre-pass only ever answers "certainly visible"; every decision it does not make is made by the unchanged per-ray code, so
+// frames are bit-identical with and without it (CGE_VIS_CULL=0).  Scenes with spheres skip it (their test is not a plane test).
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-axis constants of the hull test.  Constraint A: o + t * dmin <= hi, constraint B: o + t * dmax >= lo.
+//   all directions positive : B is the lower bound (entry), A the upper bound (exit)
+//   all directions negative : A is the lower bound, B the upper bound
+//   mixed signs             : A and B are both lower bounds, the axis has no upper bound
+// v1 = fma(sel ? hi : lo, k1, c1) is always a lower bound; v2 = fma(sel ? lo : hi, k2, c2) is an upper bound, or with `mixed`
+// a second lower bound.  The constants carry the cancellation slack of trace.cuh slab_ray, doubled: c -+ 2^-21 |c| moves each
+// plane ~8 ulps of the origin's coordinate outwards.
+struct HullAxis {
+    float k1, c1, k2, c2;
+    bool sel, mixed;
+};
+__device__ __forceinline__ HullAxis hull_axis(float o, float dmin, float dmax)
+{
+    auto recip = [](float v, float tiny) { return fabsf(v) > 1e-18f ? fdiv(1.0f, v) : tiny; };
+    HullAxis h;
+    const bool pos = dmin > 0.0f, neg = dmax < 0.0f;
+    const float iA = recip(dmin, pos ? 1e18f : -1e18f); // dmin == 0: no ray moves towards -axis: hi < o rejects
+    const float iB = recip(dmax, neg ? -1e18f : 1e18f);
+    const float cA = -fmul(o, iA), cB = -fmul(o, iB);
+    const float sA = fabsf(cA) * 4.76837158203125e-07f, sB = fabsf(cB) * 4.76837158203125e-07f;
+    h.sel = !pos; // v1 reads hi (constraint A) unless all directions are positive
+    h.mixed = !pos && !neg;
+    if (pos) {
+        h.k1 = iB, h.c1 = cB - sB; // lower
+        h.k2 = iA, h.c2 = cA + sA; // upper
+    } else {
+        h.k1 = iA, h.c1 = cA - sA;                           // lower
+        h.k2 = iB, h.c2 = h.mixed ? cB - sB : cB + sB; // second lower bound, or the upper bound
+    }
+    return h;
+}
+
+// The points between which every shadowed sample of light L lies (n = 1, 2 or 4; 0: the light casts no shadow ray)
+__device__ __forceinline__ unsigned light_corners(const float* __restrict__ L, const DevParams& p, vec3 c[4])
+{
+    auto ld3 = [&](int k) { return v3(__ldg(L + 1 + k), __ldg(L + 2 + k), __ldg(L + 3 + k)); };
+    const unsigned type = __float_as_uint(__ldg(L));
+    unsigned samples, draws;
+    light_counts(type, p, samples, draws);
+    if (type == CGE_LIGHT_POINT) {
+        c[0] = ld3(0);
+        return (p.features & CGE_FEAT_HARD_SHADOW) ? 1u : 0u;
+    }
+    if (samples == 0)
+        return 0;
+    if (type == CGE_LIGHT_SEGMENT) {
+        const vec3 e0 = ld3(0), e1 = ld3(3);
+        c[0] = e0;                     // w = 0: (e1 - e0) * 0 + e0
+        c[1] = (e1 - e0) * 1.0f + e0;  // w = 1, evaluated like sample_light
+        return 2;
+    }
+    const vec3 v0 = ld3(0), e01 = ld3(3), e02 = ld3(6);
+    c[0] = v0;
+    c[1] = v0 + e01;
+    c[2] = (v0 + e01) + e02;
+    c[3] = v0 + e02;
+    return 4;
+}
+
+// Can NO ray o + t * d, t in [0, 1], d inside the hull, be accepted by triangle tr?  (true = certainly not)
+//   a[4] = light corners - o (pyramid edges; used when `pyramid`), dmin / dmax = their per-axis bounds, dLen >= |d| of every ray,
+//   mag = coordinate magnitude of the configuration (sets the absolute rounding scale)
+__device__ __forceinline__ bool cull_triangle_clear(const float4* __restrict__ tr, const vec3 o, const vec3 dmin, const vec3 dmax, float dLen,
+    bool pyramid, const vec3* a, float mag)
+{
+    const float4 r0 = ldg4(tr);
+    const vec3 n = v3(r0.x, r0.y, r0.z);
+    const float num = fsub(r0.w, dot(o, n)); // I2's numerator, the archive's own operations: its sign is the archive's sign
+    // range of the denominators dot(d, n) over the hull, widened by the rounding of a three-term product sum
+    const float ex0 = n.x * dmin.x, ex1 = n.x * dmax.x, ey0 = n.y * dmin.y, ey1 = n.y * dmax.y, ez0 = n.z * dmin.z, ez1 = n.z * dmax.z;
+    const float denEps = (fmaxf(fabsf(ex0), fabsf(ex1)) + fmaxf(fabsf(ey0), fabsf(ey1)) + fmaxf(fabsf(ez0), fabsf(ez1))) * 1e-6f;
+    const float denLo = fminf(ex0, ex1) + fminf(ey0, ey1) + fminf(ez0, ez1) - denEps;
+    const float denHi = fmaxf(ex0, ex1) + fmaxf(ey0, ey1) + fmaxf(ez0, ez1) + denEps;
+    // 0 <= num / den <= 1 needs a den with num's sign and |den| >= |num| (a NaN plane fails both comparisons: never accepted)
+    const bool viaPos = num >= 0.0f && denHi * 1.000001f >= num, viaNeg = num <= 0.0f && denLo * 1.000001f <= num;
+    if (!viaPos && !viaNeg)
+        return true;
+    if (!pyramid)
+        return false;
+    // The rays that can reach the plane meet it under an angle whose cosine is at least cosMin; the archive's hit point then lies
+    // within ~(few ulp of the coordinates) / cosMin of the exact one.  A hull that contains rays parallel to the plane cannot be
+    // judged by distances at all.
+    const float denMin = viaPos && viaNeg ? 0.0f : viaPos ? fmaxf(denLo, 0.0f) : fmaxf(-denHi, 0.0f);
+    const float nLen = fsqrt(dot(n, n));
+    const float cosMin = denMin / (dLen * nLen);
+    if (!(cosMin > 1e-3f))
+        return false;
+    const float margin = mag * 4e-6f / fminf(cosMin, 1.0f);
+    const float4 r1 = ldg4(tr + 1), r2 = ldg4(tr + 2), r3 = ldg4(tr + 3), r4 = ldg4(tr + 4);
+    const vec3 w0 = v3(r1.x, r1.y, r1.z) - o, w1 = v3(r2.z, r2.w, r3.x) - o, w2 = v3(r4.x, r4.y, r4.z) - o;
+    const vec3 m = (a[0] + a[1]) + (a[2] + a[3]); // a direction inside the pyramid
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        vec3 pn = cross(a[i], a[(i + 1) & 3]);
+        const float inside = dot(pn, m), len = fsqrt(dot(pn, pn));
+        if (!(fabsf(inside) > 1e-3f * len * fsqrt(dot(m, m))))
+            continue; // degenerate side (the origin lies in the light's plane): no judgement from this plane
+        const float sgn = inside > 0.0f ? -1.0f : 1.0f, thr = margin * len;
+        if (sgn * dot(pn, w0) > thr && sgn * dot(pn, w1) > thr && sgn * dot(pn, w2) > thr)
+            return true; // the whole triangle lies outside this side of the pyramid, by more than the margin
+    }
+    return false;
+}
+
+#ifndef CGE_MINB_CULL
+#define CGE_MINB_CULL 8
+#endif
+__global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScene s, DevParams p, WaveBuffers wb,
+    unsigned levelBegin, unsigned levelEnd, unsigned counterIdx)
+{
+    const unsigned lane = threadIdx.x & 31, below = (1u << lane) - 1u;
+    const bool fold = p.draws_per_hit == 0;
+    const unsigned S = p.samples_per_hit;
+    unsigned cum[kMaxLevels + 1], hitsBefore[kMaxLevels + 1]; // direct-lighting evaluations before level k; hits of this launch before it
+    cum[0] = 0;
+    for (unsigned k = 0; k < p.levels; k++)
+        cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
+    hitsBefore[levelBegin] = 0;
+    for (unsigned k = levelBegin; k < levelEnd; k++)
+        hitsBefore[k + 1] = hitsBefore[k] + wb.counts[k];
+    const unsigned total = hitsBefore[levelEnd];
+    // one parallelogram light: the pyramid (o, corners) is known and its side planes can clear triangles; otherwise only the
+    // direction box of all lights' corners is used
+    const bool pyramid = s.n_lights == 1 && __float_as_uint(__ldg(s.lights)) == CGE_LIGHT_PARALLELOGRAM;
+    float lightMag = 0.0f;
+    for (unsigned li = 0; li < s.n_lights; li++) {
+        vec3 c[4];
+        const unsigned nc = light_corners(s.lights + size_t(li) * kLightFloats, p, c);
+        for (unsigned j = 0; j < nc; j++)
+            lightMag = fmaxf(lightMag, fmaxf(fmaxf(fabsf(c[j].x), fabsf(c[j].y)), fabsf(c[j].z)));
+    }
+    constexpr unsigned kDone = 0x7fffffffu;
+    constexpr float kInf = __builtin_huge_valf();
+    unsigned long long nResolved = 0;
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0)
+            chunk = atomicAdd(wb.counts + counterIdx, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const unsigned first = chunk * 32u;
+        if (first >= total)
+            break;
+        const unsigned item = first + lane;
+        bool hardHit = false;
+        unsigned k = levelBegin, e = 0;
+        if (item < total) {
+            while (item >= hitsBefore[k + 1])
+                k++;
+            e = item - hitsBefore[k];
+            const float* b = wb.rec + (size_t(k) * kWaveRecFloats + 17) * wb.cap + e;
+            const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
+            // the hull: per-axis bounds of (corner - o) over all lights; for the single parallelogram also the four edges
+            vec3 a[4];
+            vec3 dmin = v3(kInf), dmax = v3(-kInf);
+            unsigned corners = 0;
+            for (unsigned li = 0; li < s.n_lights; li++) {
+                vec3 c[4];
+                const unsigned nc = light_corners(s.lights + size_t(li) * kLightFloats, p, c);
+                for (unsigned j = 0; j < nc; j++) {
+                    const vec3 d = c[j] - o;
+                    if (pyramid)
+                        a[j] = d;
+                    dmin = v3(fminf(dmin.x, d.x), fminf(dmin.y, d.y), fminf(dmin.z, d.z));
+                    dmax = v3(fmaxf(dmax.x, d.x), fmaxf(dmax.y, d.y), fmaxf(dmax.z, d.z));
+                }
+                corners += nc;
+            }
+            const bool finite = fabsf(dmin.x) <= 3e38f && fabsf(dmin.y) <= 3e38f && fabsf(dmin.z) <= 3e38f && fabsf(dmax.x) <= 3e38f
+                && fabsf(dmax.y) <= 3e38f && fabsf(dmax.z) <= 3e38f;
+            if (corners == 0 || s.n_ftris == 0) {
+                hardHit = false; // nothing casts or nothing blocks a shadow ray: every byte is 1
+            } else if (!finite) {
+                hardHit = true;
+            } else {
+                const HullAxis hx = hull_axis(o.x, dmin.x, dmax.x), hy = hull_axis(o.y, dmin.y, dmax.y), hz = hull_axis(o.z, dmin.z, dmax.z);
+                const bool anyMixed = hx.mixed || hy.mixed || hz.mixed;
+                const float mx = fmaxf(fabsf(dmin.x), fabsf(dmax.x)), my = fmaxf(fabsf(dmin.y), fabsf(dmax.y)), mz = fmaxf(fabsf(dmin.z), fabsf(dmax.z));
+                const float dLen = fsqrt(mx * mx + my * my + mz * mz) * 1.0001f;
+                const float mag = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + lightMag;
+                auto hull_box = [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float& ent, float& ext) {
+                    const float ax = __fmaf_rn(hx.sel ? hix : lox, hx.k1, hx.c1), bx = __fmaf_rn(hx.sel ? lox : hix, hx.k2, hx.c2);
+                    const float ay = __fmaf_rn(hy.sel ? hiy : loy, hy.k1, hy.c1), by = __fmaf_rn(hy.sel ? loy : hiy, hy.k2, hy.c2);
+                    const float az = __fmaf_rn(hz.sel ? hiz : loz, hz.k1, hz.c1), bz = __fmaf_rn(hz.sel ? loz : hiz, hz.k2, hz.c2);
+                    ent = fmaxf(max3(ax, ay, az), 0.0f);
+                    if (!anyMixed) {
+                        ext = min3(bx, by, bz);
+                    } else {
+                        ent = fmaxf(ent, max3(hx.mixed ? bx : 0.0f, hy.mixed ? by : 0.0f, hz.mixed ? bz : 0.0f));
+                        ext = min3(hx.mixed ? kInf : bx, hy.mixed ? kInf : by, hz.mixed ? kInf : bz);
+                    }
+                };
+                unsigned stack[kFastStackSize];
+                int sp = 0;
+                unsigned cur = s.froot;
+                unsigned budget = p.cull_budget; // inner nodes this walk may visit before it gives the hit up
+                while (cur != kDone) {
+                    while (cur < kDone) {
+                        if (budget-- == 0) {
+                            hardHit = true;
+                            break;
+                        }
+                        const float4* nd = s.fnodes + size_t(cur) * kNodeRows;
+                        float4 q0, q1, q2, q3;
+#if CGE_NODE_LD256
+                        ldg8(nd + 2, q2, q3);
+                        ldg8(nd, q0, q1);
+#else
+                        q3 = ldg4(nd + 3), q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2);
+#endif
+                        float entL, extL, entR, extR;
+                        hull_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
+                        hull_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+                        const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
+                        const bool hitL = entL <= extL * 1.000008f && entL <= 1.0001f;
+                        const bool hitR = entR <= extR * 1.000008f && entR <= 1.0001f;
+                        const bool leftFirst = hitL && (!hitR || entL <= entR);
+                        if (hitL && hitR)
+                            stack[sp++] = leftFirst ? cr : cl;
+                        if (hitL || hitR)
+                            cur = leftFirst ? cl : cr;
+                        else
+                            cur = sp > 0 ? stack[--sp] : kDone;
+                    }
+                    if (hardHit || cur == kDone)
+                        break;
+                    const unsigned firstTri = cur & 0x0fffffffu, count = ((cur >> 28) & 7u) + 1u;
+                    for (unsigned i = firstTri; i < firstTri + count; i++)
+                        if (!cull_triangle_clear(s.ftris + size_t(i) * kTriRows, o, dmin, dmax, dLen, pyramid, a, mag)) {
+                            hardHit = true;
+                            break;
+                        }
+                    if (hardHit)
+                        break;
+                    cur = sp > 0 ? stack[--sp] : kDone;
+                }
+            }
+            if (!hardHit) { // every visibility byte of the hit (all copies, all samples) is 1
+                const unsigned cnt = wb.counts[k], copies = fold ? 1u : (1u << k);
+                unsigned char* v = wb.vis + size_t(cum[k]) * S + e;
+                for (unsigned j = 0; j < copies * S; j++)
+                    v[size_t(j) * cnt] = 1;
+                nResolved += copies * S;
+            }
+        }
+        // the hard hits of this warp keep their order: one atomic per warp and level reserves their run of the list
+        for (unsigned kk = levelBegin; kk < levelEnd; kk++) {
+            const unsigned ballot = __ballot_sync(0xffffffffu, hardHit && k == kk);
+            if (!ballot)
+                continue;
+            unsigned base = 0;
+            if (lane == 0)
+                base = atomicAdd(wb.counts + 32 + kk, unsigned(__popc(ballot)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hardHit && k == kk)
+                wb.hard[size_t(kk) * wb.cap + base + unsigned(__popc(ballot & below))] = e;
+        }
+    }
+    // light samples settled without a ray: a 64-bit counter in counts[48..49] (cge_stats::shadow_samples_culled)
+    for (int off = 16; off > 0; off >>= 1)
+        nResolved += __shfl_down_sync(0xffffffffu, nResolved, off);
+    if (lane == 0 && nResolved)
+        atomicAdd(reinterpret_cast<unsigned long long*>(wb.counts + 48), nResolved);
+}
+
 constexpr int kVisShortStack = CGE_VIS_SHORT_STACK > 0 ? CGE_VIS_SHORT_STACK : 1;
 #ifndef CGE_MINB_VIS
 #define CGE_MINB_VIS 12 // resident 128-thread CTAs per SM the shadow-ray kernel is compiled for (A/B in DESIGN.md 5.5)
@@ -496,14 +779,19 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevSc
     const bool fold = p.draws_per_hit == 0;
     const unsigned S = p.samples_per_hit;
     const unsigned groups = (S + kGroup - 1) / kGroup;
-    unsigned cum[kMaxLevels + 1]; // in units (direct-lighting evaluations)
-    cum[0] = 0;
-    for (unsigned k = 0; k < p.levels; k++)
+    // cum: direct-lighting evaluations before level k (the layout of the visibility bytes); work: the evaluations this kernel
+    // traces - the same, or with the light-hull pre-pass (p.vis_cull) those of the hard hits only (wb.hard, counts[32 + k])
+    const bool culled = p.vis_cull != 0;
+    unsigned cum[kMaxLevels + 1], work[kMaxLevels + 1];
+    cum[0] = work[0] = 0;
+    for (unsigned k = 0; k < p.levels; k++) {
         cum[k + 1] = cum[k] + wb.counts[k] * (fold ? 1u : (1u << k));
-    const unsigned long long itemBase = (unsigned long long)cum[levelBegin] * groups;
-    const unsigned long long total = (unsigned long long)(cum[levelEnd] - cum[levelBegin]) * groups;
+        work[k + 1] = work[k] + wb.counts[culled ? 32 + k : k] * (fold ? 1u : (1u << k));
+    }
+    const unsigned long long itemBase = (unsigned long long)work[levelBegin] * groups;
+    const unsigned long long total = (unsigned long long)(work[levelEnd] - work[levelBegin]) * groups;
     unsigned long long nshadow = 0;
-    if (!wf_use_visibility_bytes(p, wb) || wf_regroup_samples_per_lane(p, cum[levelEnd] - cum[levelBegin]) != kGroup)
+    if (!wf_use_visibility_bytes(p, wb) || wf_regroup_samples_per_lane(p, work[levelEnd] - work[levelBegin]) != kGroup)
         return;
     // one shadow ray of hit h, sample sg; visits (optional) counts the nodes it walked; updates h.occluder
     auto trace_sample = [&](RegroupHit& h, unsigned sg, unsigned* visits) {
@@ -546,11 +834,11 @@ __global__ void __launch_bounds__(128, CGE_MINB_VIS) wf_vis_regroup_kernel(DevSc
         unsigned visits = 0;
         if (own.valid) {
             unsigned k = 0;
-            while (item >= (unsigned long long)cum[k + 1] * groups)
+            while (item >= (unsigned long long)work[k + 1] * groups)
                 k++;
-            const unsigned inLevel = unsigned(item - (unsigned long long)cum[k] * groups), cnt = wb.counts[k];
-            const unsigned block = inLevel / cnt;
-            own.k = k, own.cnt = cnt, own.e = inLevel - block * cnt;
+            const unsigned inLevel = unsigned(item - (unsigned long long)work[k] * groups), cnt = wb.counts[culled ? 32 + k : k];
+            const unsigned block = inLevel / cnt, idx = inLevel - block * cnt;
+            own.k = k, own.cnt = wb.counts[k], own.e = culled ? wb.hard[size_t(k) * wb.cap + idx] : idx;
             own.path = block / groups, own.g = block - own.path * groups;
             const uint2 m = wb.meta[size_t(k) * wb.cap + own.e];
             own.pixel = wf_pixel(m);

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CGE_ABI_VERSION 3
+#define CGE_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------------------------ */
 enum {
@@ -224,6 +224,8 @@ typedef struct cge_stats {
     float total_ms;           /* device time including uploads of camera/params and the D2H copy     */
     uint32_t kernel_launches; /* kernels launched by this call                                        */
     float stage_ms[4];        /* wavefront pipeline: wf_chain / wf_visibility / wf_shade / wf_fold device times */
+    uint64_t shadow_samples_culled; /* light samples (shadow rays and samples that need none) of hits the light-hull pre-pass proved
+                                       unoccluded: settled without a ray, not counted in shadow_rays (ABI 4) */
 } cge_stats;
 
 typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene + BVH on ONE GPU */
@@ -231,6 +233,7 @@ typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene +
 /* ---- development switches (environment variables read at call time; A/B measurements and tests only, not part of the ABI:
  *      every setting produces the same frame bit for bit) -----------------------------------------------------------------
  *   CGE_ZERO_SHADING_CULL=0   trace the shadow ray of light samples whose Phong term is exactly zero as well
+ *   CGE_VIS_CULL=0            wavefront pipeline without the light-hull pre-pass (every shadow ray is traced)
  *   CGE_BANDS=n               number of concurrent bands a frame / rank partition is rendered in (1 = one pipeline)
  *   CGE_REGROUP=0             shadow pass without the in-warp regrouping (wf_vis_grouped_kernel)
  *   CGE_SAH_BUILD=host        build the FAST traversal tree with the host builder instead of the GPU builder

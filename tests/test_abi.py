@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(cge):
     for n in names:
         assert hasattr(lib, n), f"libcge.so does not export {n}"
     assert set(names) == set(cge.ABI_SYMBOLS)
-    assert lib.cge_abi_version() == 3
+    assert lib.cge_abi_version() == 4
 
 
 def test_struct_sizes_match_header(cge):

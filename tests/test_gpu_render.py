@@ -25,6 +25,17 @@ RGB_TOL = 1e-3
 ID_MISMATCH_BUDGET = 1e-4
 
 
+def same_rays_answered(a, b):
+    """Two pipelines answered the same rays: camera and reflection rays equal; shadow rays equal too, except that the light-hull
+    pre-pass of the wavefront pipeline (wavefront.cuh wf_vis_cull_kernel) settles whole hits without tracing - it reports the
+    light SAMPLES it settled, which include samples that needed no ray, so the traced counts bracket each other."""
+    if a["primary_rays"] != b["primary_rays"] or a["bounce_rays"] != b["bounce_rays"]:
+        return False
+    if not a["shadow_samples_culled"] and not b["shadow_samples_culled"]:
+        return a["shadow_rays"] == b["shadow_rays"]
+    return all(x["shadow_rays"] <= y["shadow_rays"] + y["shadow_samples_culled"] for x, y in ((a, b), (b, a)))
+
+
 def flat_for(cge, cfg, small_standin=True):
     if cfg["scene"].startswith("standin:"):
         return cge.standin.make("dragon", n=40) if small_standin else cge.standin.make("dragon")
@@ -178,7 +189,7 @@ def test_full_size_properties(cge, name):
         # the two production pipelines (one thread per pixel, wavefront) walk the same tree with the same arithmetic: identical bits
         for fl in (cge.FLAG_PER_THREAD, cge.FLAG_WAVEFRONT):
             rgb_t, ids_t, st_t = sc.render(cfg, traversal=1, flags=fl)
-            assert st_t["reference_rays"] == st_f["reference_rays"] and st_t["gpu_rays"] == st_f["gpu_rays"]
+            assert st_t["reference_rays"] == st_f["reference_rays"] and same_rays_answered(st_t, st_f)
             assert np.array_equal(ids_t, ids_f) and rgb_t.tobytes() == rgb_f.tobytes()
         err, nan_mm = compare_images(rgb_f, rgb_r)
         assert nan_mm <= ID_MISMATCH_BUDGET * ids_f.size
@@ -375,6 +386,58 @@ def test_zero_shading_cull_changes_no_bit(cge, name, monkeypatch):
             assert st1["shadow_rays"] < st0["shadow_rays"] and st1["reference_rays"] == st0["reference_rays"]
 
 
+@pytest.mark.parametrize("name,size,extra", [
+    ("c3_teapot_soft", (256, 144), {}),
+    ("c3_teapot_soft", (128, 72), {"parallelogram_samples": 3}),
+    ("c5_dragon", (192, 108), {}),
+    ("c5_dragon", (96, 54), {"ray_depth": 1}),
+])
+def test_light_hull_prepass_changes_no_bit(cge, name, size, extra, monkeypatch):
+    """The light-hull pre-pass of the wavefront pipeline (wf_vis_cull_kernel: one conservative walk per hit with the hull of its
+    lights; hits no shadow ray of which can be blocked are settled without tracing) only ever answers "certainly visible":
+    fewer rays traced, the frame identical bit for bit, with the chain stage split or not, in one pipeline or in bands."""
+    cfg = cge.configs.get(name, *size)
+    cfg.update(extra)
+    with cge.Scene(flat_for(cge, cfg)) as sc:
+        monkeypatch.setenv("CGE_VIS_CULL", "0")
+        rgb0, ids0, st0 = sc.render(cfg, traversal=1, flags=cge.FLAG_WAVEFRONT)
+        rgb_t, _, st_t = sc.render(cfg, traversal=1, flags=cge.FLAG_PER_THREAD)
+        assert st0["shadow_samples_culled"] == 0 and st0["shadow_rays"] == st_t["shadow_rays"] and rgb0.tobytes() == rgb_t.tobytes()
+        monkeypatch.setenv("CGE_VIS_CULL", "1")
+        for split, bands in (("0", "1"), ("1", "1"), ("0", "3")):
+            monkeypatch.setenv("CGE_CHAIN_SPLIT", split)
+            monkeypatch.setenv("CGE_BANDS", bands)
+            rgb1, ids1, st1 = sc.render(cfg, traversal=1, flags=cge.FLAG_WAVEFRONT)
+            assert rgb1.tobytes() == rgb0.tobytes() and np.array_equal(ids1, ids0), (split, bands)
+            assert 0 < st1["shadow_samples_culled"] and st1["shadow_rays"] < st0["shadow_rays"]
+            assert st0["shadow_rays"] <= st1["shadow_rays"] + st1["shadow_samples_culled"]
+            assert st1["reference_rays"] == st0["reference_rays"] and same_rays_answered(st1, st0)
+
+
+def test_light_hull_prepass_with_every_light_kind_and_off_for_spheres(cge, monkeypatch):
+    """Point + segment + parallelogram lights at once (the hull is then the direction box of all their corner points, without the
+    pyramid planes); a scene with spheres keeps every hit for the per-ray kernel."""
+    C = cge.configs
+    base = {"width": 160, "height": 96, "ray_depth": 2, "segment_samples": 5, "parallelogram_samples": 3, "seed": 5,
+            "camera": {"fov_deg": 60.0, "dist": 2.5, "look_at": [0.0, 0.3, 0.0], "rotation_deg": [15.0, 35.0, 0.0]},
+            "features": C.FEAT_SHADING | C.FEAT_ACCEL_STRUCTURE | C.FEAT_SOFT_SHADOW | C.FEAT_HARD_SHADOW | C.FEAT_RECURSIVE}
+    mixed = cge.scenefile.load(C.SCENE_DIR / "mixed.cges")
+    mk = cge.scenefile.load(C.SCENE_DIR / "monkey.cges")
+    mk.lights = mixed.lights
+    for flat, spheres in ((mk, False), (mixed, True)):
+        cfg = dict(base, scene="-", camera=dict(base["camera"], dist=4.0 if spheres else 2.5))
+        with cge.Scene(flat) as sc:
+            monkeypatch.setenv("CGE_VIS_CULL", "0")
+            rgb0, ids0, st0 = sc.render(cfg, traversal=1, flags=cge.FLAG_WAVEFRONT)
+            monkeypatch.setenv("CGE_VIS_CULL", "1")
+            rgb1, ids1, st1 = sc.render(cfg, traversal=1, flags=cge.FLAG_WAVEFRONT)
+            assert st0["stage_ms"][1] > 0 and rgb1.tobytes() == rgb0.tobytes() and np.array_equal(ids1, ids0)
+            if spheres:
+                assert st1["shadow_samples_culled"] == 0 and st1["shadow_rays"] == st0["shadow_rays"]
+            else:
+                assert st1["shadow_samples_culled"] > 0 and st1["shadow_rays"] < st0["shadow_rays"]
+
+
 def test_zero_shading_cull_off_for_unbounded_colours(cge):
     """(kd * Lc) * 0 is NaN when the product overflows: with a light colour beyond the bound the cull must stay off."""
     import copy
@@ -396,6 +459,8 @@ def test_concurrent_bands_change_no_bit(cge, name, monkeypatch):
     """cge_render renders large frames as concurrent bands of tile rows, each a pipeline on its own stream (cge_api.cu
     launch_bands): the frame, the ids, the packed bitmap and the ray counters must not depend on the number of bands."""
     cfg = cge.configs.get(name)
+    # (the light-hull pre-pass is switched on by launch size, which the band count changes: pinned, so that the counters compare)
+    monkeypatch.setenv("CGE_VIS_CULL", "1")
     with cge.Scene(cge.load_scene(cfg)) as sc:
         monkeypatch.setenv("CGE_BANDS", "1")
         rgb1, ids1, st1 = sc.render(cfg, traversal=1)
@@ -408,7 +473,7 @@ def test_concurrent_bands_change_no_bit(cge, name, monkeypatch):
             rgb, ids, st = sc.render(cfg, traversal=1)
             rgba, _ = sc.render_rgba8(cfg)
             assert rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1) and rgba.tobytes() == rgba1.tobytes()
-            for k in ("primary_rays", "bounce_rays", "shadow_rays", "reference_rays", "reference_shadow_rays"):
+            for k in ("primary_rays", "bounce_rays", "shadow_rays", "shadow_samples_culled", "reference_rays", "reference_shadow_rays"):
                 assert st[k] == st1[k], k
 
 

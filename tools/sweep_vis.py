@@ -1,6 +1,6 @@
 """A/B sweep over the environment-tunable variants of the shadow-ray pass (development aid): kernel ms per variant, every
 variant checked bit-identical to the first.  usage: sweep_vis.py cfg[:scale] "K=V,K=V" "K=V" ...   (SWEEP_PART=n: 1/n share)"""
-import importlib, json, os, sys
+import hashlib, importlib, json, os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -28,5 +28,6 @@ with pkg.Scene(pkg.load_scene(cfg)) as sc:
         if base is None:
             base = rgb.tobytes()
         print(json.dumps({"cfg": name, "w": cfg["width"], "part": part[1], "variant": v, "kernel_ms": round(best["kernel_ms"], 3),
-                          "stages": [round(x, 3) for x in best["stage_ms"]], "shadow_rays": best["shadow_rays"],
-                          "identical": rgb.tobytes() == base}), flush=True)
+                          "stages": [round(x, 3) for x in best["stage_ms"]], "shadow_rays": best["shadow_rays"], "culled": best.get("shadow_samples_culled"),
+                          "identical": rgb.tobytes() == base,
+                          "sha": hashlib.sha256(rgb.tobytes()).hexdigest()[:12]}), flush=True)
