@@ -18,8 +18,8 @@ it as gpu_unique_mrays_s.
   e2e         the same frame through the host-facing C-ABI call: per step H2D of the light list + camera / params, the
               kernels, and the D2H copy of the W*H*12-byte frame into page-locked host memory (N > 1: every rank copies the
               rows it rendered into the shared host frame of cge_comm_host_frame over its own PCIe link).
-  roofline    the dominant kernel against the bound that operates on it (warp-instruction issue), with the DRAM figures and
-              the SURVEY-defined reference-algorithm bytes beside it; DESIGN.md "Measurement".
+  roofline    the dominant kernel against the bound that operates on it (the L1 data pipe: one wavefront per cycle and SM), with the
+              issue-slot and DRAM figures and the SURVEY-defined reference-algorithm bytes beside it; DESIGN.md "Measurement".
   cpu_baseline / --impl reference   the unmodified reference renderer (oracle/_ref) on the host cores, thread sweep included.
   configs     BASELINE.json's other configurations (C1-C4): frame time, Mrays/s and a parity check against the committed
               goldens each (N > 1: C4 through the distributed path).
@@ -322,6 +322,7 @@ def main():
         last = None
         kernel_ms = []
         stage_ms = []
+        cull_ms = []
         walls, totals = [], []
         for _ in range(steps):
             flush.fill_(1.0)  # L2 flush between timed iterations (untimed)
@@ -332,6 +333,7 @@ def main():
             total += time.perf_counter() - t0
             kernel_ms.append(last["kernel_ms"])
             stage_ms.append(last["stage_ms"])
+            cull_ms.append(last.get("vis_cull_ms", 0.0))
             walls.append((time.perf_counter() - t0) * 1e3)
             totals.append(last["total_ms"])
             if sampler:
@@ -342,6 +344,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         last["stage_ms_mean"] = [float(x) for x in np.mean(np.asarray(stage_ms), axis=0)]
+        last["vis_cull_ms_mean"] = float(np.mean(cull_ms))
         # per-rank breakdown (stderr): wall clock of the call, device time incl. gather / copies (ev0 -> ev2), kernels only (ev0 -> ev1)
         row = torch.tensor([np.mean(walls), np.mean(totals), np.mean(kernel_ms)] + last["stage_ms_mean"], dtype=torch.float64, device="cuda")
         rows = [torch.zeros_like(row) for _ in range(world)] if world > 1 else [row]
@@ -357,8 +360,8 @@ def main():
     total_s, st, kernel_ms, clocks = timed(step_device, args.warmup, args.steps, sample_clocks=True)
     # whole-frame ray counts: sum over ranks; this rank's share of the shadow rays (the dominant kernel's work): max over ranks
     cnt = torch.tensor([st["reference_rays"], st["gpu_rays"], st["primary_rays"], st["bounce_rays"], st["shadow_rays"],
-                        st["reference_shadow_rays"]], dtype=torch.float64, device="cuda")
-    my_shadow = torch.tensor([float(st["shadow_rays"])], dtype=torch.float64, device="cuda")
+                        st["reference_shadow_rays"], st.get("shadow_samples_culled", 0)], dtype=torch.float64, device="cuda")
+
     # Stage timings for the roofline: the timed steps above may render the frame as concurrent bands (cge_api.cu launch_bands),
     # whose stage boundaries overlap in time, so a kernel's duration is taken from K more steps of the same frame rendered as
     # ONE pipeline (CGE_BANDS=1): same kernels, same work, CUDA events on the launching stream.
@@ -366,11 +369,15 @@ def main():
     single_s, st1, kernel_ms1, _ = timed(step_device, 1, args.steps)
     del os.environ["CGE_BANDS"]
     single_ms = single_s / args.steps * 1e3
-    kms = torch.tensor([float(np.mean(kernel_ms1))] + st1["stage_ms_mean"], dtype=torch.float64, device="cuda")
+    kms = torch.tensor([float(np.mean(kernel_ms1))] + st1["stage_ms_mean"] + [st1["vis_cull_ms_mean"]], dtype=torch.float64, device="cuda")
+    # (of the single-pipeline steps the roofline is measured on: whether the light-hull pre-pass runs depends on the launch size)
+    culled = torch.tensor([float(st1.get("shadow_samples_culled", 0))], dtype=torch.float64, device="cuda")
+    my_shadow = torch.tensor([float(st1["shadow_rays"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
         dist.all_reduce(my_shadow, op=dist.ReduceOp.MAX)
+        dist.all_reduce(culled, op=dist.ReduceOp.SUM)
     ref_rays, gpu_rays = float(cnt[0]), float(cnt[1])
     ms_per_step = total_s / args.steps * 1e3
     value = ref_rays / ms_per_step / 1e3
@@ -461,32 +468,47 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak_hbm, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    pipeline_ms, chain_ms, vis_ms, shade_ms, fold_ms = [float(x) for x in kms]
-    stage_names = ["wf_chain_kernel", DOMINANT, "wf_shade_kernel", "wf_fold_kernel"]
-    stage_vals = [chain_ms, vis_ms, shade_ms, fold_ms]
+    pipeline_ms, chain_ms, stage_vis_ms, shade_ms, fold_ms, cull_ms = [float(x) for x in kms]
+    # the shadow-ray stage = (light-hull pre-pass, when the launch is large enough for it) + the shadow-ray kernel; the kernel's own
+    # live duration is the stage minus the pre-pass (both from CUDA events on the launching stream, cge_stats::vis_cull_ms)
+    prepass = float(culled[0]) > 0
+    vis_ms = stage_vis_ms - cull_ms
+    stage_names = ["wf_chain_kernel", "shadow_stage", "wf_shade_kernel", "wf_fold_kernel"]
+    stage_vals = [chain_ms, stage_vis_ms, shade_ms, fold_ms]
     roof = None
     if vis_ms > 0 and int(np.argmax(stage_vals)) == 1:
-        # The kernel is bound by warp-instruction issue, not by bytes: ncu shows the DRAM pipe at ~4 % and the
-        # schedulers at ~70 %.  achieved = warp instructions of the launch / live CUDA-event duration; the instruction count is
-        # ncu's smsp__inst_executed.sum of the committed capture of this kernel on this workload (whole frame, one GPU), scaled
-        # to this launch by its share of the frame's shadow rays when the frame is split over several GPUs.
+        # What bounds the kernel: the L1 data pipe.  ncu shows l1tex__data_pipe_lsu_wavefronts at 82-84 % of
+        # its peak of one wavefront per cycle and SM (every lane of a warp fetches its own BVH node, so a load instruction costs one
+        # wavefront per distinct line), the schedulers at 55-59 % and DRAM at 3 %.  achieved = wavefronts of the launch / its live
+        # CUDA-event duration; the wavefront and instruction counts are ncu's, from the committed capture of this kernel on this
+        # workload (whole frame, one GPU, with or without the pre-pass as in this run), scaled to this launch by the shadow rays it
+        # traces (max over ranks) over the capture's.
         sm_mhz = float((clocks or {}).get("sm_mhz") or 0.0) or 1965.0
+        key = DOMINANT if prepass else DOMINANT + "_nocull"
+        cap_rays = prof.get(key + "_shadow_rays")
+        share = float(my_shadow[0]) / float(cap_rays) if cap_rays else float(my_shadow[0]) / max(float(cnt[4]), 1.0)
+        wavefronts = prof.get(key + "_l1_wavefronts")
+        warp_inst = prof.get(key + "_warp_instructions")
+        tpi = prof.get(key + "_threads_per_inst")
+        dram_bytes = prof.get(key)
+        peak_gwf = N_SMS * sm_mhz * 1e6 / 1e9
         peak_ginst = N_SMS * SCHEDULERS_PER_SM * sm_mhz * 1e6 / 1e9
-        share = float(my_shadow[0]) / max(float(cnt[4]), 1.0)
-        warp_inst = prof.get(DOMINANT + "_warp_instructions")
-        tpi = prof.get(DOMINANT + "_threads_per_inst")
-        dram_bytes = prof.get(DOMINANT)
-        roof = {"bound": "issue", "kernel": "cge::" + DOMINANT + "<8>" if world == 1 else "cge::" + DOMINANT,
-                "kernel_ms": vis_ms, "share_of_step": vis_ms / single_ms, "unit": "Gwarp-inst/s", "peak": peak_ginst,
-                "peak_source": f"{N_SMS} SMs x {SCHEDULERS_PER_SM} schedulers x {sm_mhz:.0f} MHz (SM clock sampled under load)"}
-        if warp_inst:
-            achieved = warp_inst * share / (vis_ms * 1e-3) / 1e9
-            roof.update(achieved=achieved, frac=achieved / peak_ginst,
-                        lane_frac=None if not tpi else achieved / peak_ginst * tpi / 32.0,
-                        threads_per_inst=tpi, warp_instructions_per_launch=warp_inst * share,
-                        instruction_source=prof.get(DOMINANT + "_source"))
+        roof = {"bound": "l1", "kernel": "cge::" + DOMINANT + ("<8>" if world == 1 else ""), "kernel_ms": vis_ms,
+                "share_of_step": vis_ms / single_ms, "unit": "Gwavefronts/s", "peak": peak_gwf,
+                "peak_source": f"L1 data pipe: {N_SMS} SMs x 1 wavefront per cycle x {sm_mhz:.0f} MHz (SM clock sampled under load)",
+                "light_hull_prepass": prepass, "shadow_rays_traced_this_launch": float(my_shadow[0]),
+                "counter_source": prof.get(key + "_source")}
+        if wavefronts:
+            achieved = wavefronts * share / (vis_ms * 1e-3) / 1e9
+            roof.update(achieved=achieved, frac=achieved / peak_gwf, l1_wavefronts_per_launch=wavefronts * share)
         else:
-            roof.update(achieved=None, frac=None, lane_frac=None)
+            roof.update(achieved=None, frac=None)
+        if warp_inst:
+            ginst = warp_inst * share / (vis_ms * 1e-3) / 1e9
+            roof["issue"] = {"achieved": ginst, "peak": peak_ginst, "unit": "Gwarp-inst/s", "frac": ginst / peak_ginst,
+                             "lane_frac": None if not tpi else ginst / peak_ginst * tpi / 32.0, "threads_per_inst": tpi,
+                             "warp_instructions_per_launch": warp_inst * share,
+                             "peak_source": f"{N_SMS} SMs x {SCHEDULERS_PER_SM} schedulers x {sm_mhz:.0f} MHz"}
         roof["traffic"] = None if not dram_bytes else dram_bytes * share
         roof["hbm"] = {"achieved_gbs": None if not dram_bytes else dram_bytes * share / (vis_ms * 1e-3) / 1e9, "peak_gbs": peak_hbm,
                        "frac": None if not dram_bytes else dram_bytes * share / (vis_ms * 1e-3) / 1e9 / peak_hbm, "peak_source": peak_src,
@@ -497,22 +519,22 @@ def main():
             shadow_ref_rays = float(cnt[5])
             roof["reference_algorithm"] = {
                 "bytes_per_ray": bytes_per_ray, "box_tests_per_ray": box_per_ray, "tri_tests_per_ray": tri_per_ray, "source": bytes_src,
-                "gbs": shadow_ref_rays * share * bytes_per_ray / (vis_ms * 1e-3) / 1e9,
+                "gbs": shadow_ref_rays / max(world, 1) * bytes_per_ray / (stage_vis_ms * 1e-3) / 1e9,
                 "note": "SURVEY.md 8(d)'s algorithmic bytes: 32 B per box test + 48 B per triangle test of the reference's EXHAUSTIVE "
-                        "traversal x the shadow rays this launch answers, over its duration.  The fast tree answers the same rays "
+                        "traversal x the shadow rays one rank's shadow stage answers, over the stage's duration.  The fast tree answers the same rays "
                         "with ~3x fewer box and ~40x fewer triangle tests, so this is work avoided, not bandwidth achieved "
                         "(it exceeds the HBM peak): reported for comparison with the survey, not as a roofline fraction"}
         if fast_counts:
             req = 32.0 * fast_counts["box_tests_per_ray"] + 16.0 * fast_counts["tri_tests_per_ray"]
             roof["fast_tree"] = {**fast_counts, "requested_bytes_per_ray": req,
-                                 "requested_gbs": float(cnt[4]) * req / (vis_ms * 1e-3) / 1e9,
+                                 "requested_gbs": float(cnt[4]) * req / (stage_vis_ms * 1e-3) / 1e9,
                                  "note": "bytes the SAH traversal itself requests (served by L1/L2)"}
         roof["measured_on"] = (f"{args.steps} steps of the same frame as ONE pipeline per GPU (CGE_BANDS=1, {single_ms:.3f} ms per step, max "
                                "over ranks): the timed `value` steps may run the frame as concurrent bands whose stage boundaries overlap")
-        roof["stage_ms"] = {**dict(zip(stage_names, stage_vals)), "pipeline": pipeline_ms}
+        roof["stage_ms"] = {**dict(zip(stage_names, stage_vals)), "wf_vis_cull_kernel": cull_ms, DOMINANT: vis_ms, "pipeline": pipeline_ms}
     elif pipeline_ms > 0:
-        roof = {"bound": "issue", "kernel": "cge::render_kernel", "kernel_ms": pipeline_ms, "share_of_step": pipeline_ms / single_ms,
-                "achieved": None, "peak": None, "frac": None, "unit": "Gwarp-inst/s", "traffic": None,
+        roof = {"bound": "l1", "kernel": "cge::render_kernel", "kernel_ms": pipeline_ms, "share_of_step": pipeline_ms / single_ms,
+                "achieved": None, "peak": None, "frac": None, "unit": "Gwavefronts/s", "traffic": None,
                 "note": "no ncu capture of this workload's kernel is committed: duration only"}
 
     line = {
@@ -522,7 +544,8 @@ def main():
         "frames_per_s": 1e3 / ms_per_step,
         "gpu_unique_mrays_s": gpu_rays / ms_per_step / 1e3,
         "rays_per_frame": {"reference_equivalent": ref_rays, "gpu_unique": gpu_rays, "primary": float(cnt[2]),
-                           "bounce": float(cnt[3]), "shadow": float(cnt[4])},
+                           "bounce": float(cnt[3]), "shadow": float(cnt[4]),
+                           "shadow_samples_settled_by_light_hull_prepass": float(cnt[6])},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes,
                 "delivery": "cge_render into page-locked host memory" if world == 1 else

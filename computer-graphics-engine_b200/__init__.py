@@ -69,7 +69,7 @@ class CgeStats(C.Structure):
         ("reference_shadow_rays", C.c_uint64),
         ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
         ("stage_ms", C.c_float * 4),
-        ("shadow_samples_culled", C.c_uint64),
+        ("shadow_samples_culled", C.c_uint64), ("vis_cull_ms", C.c_float),
     ]
 
     def as_dict(self) -> dict:

@@ -102,6 +102,8 @@ struct Scratch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t stage[5] = {}; // wavefront stage boundaries: chain | shadow rays | shading | fold |
     bool staged = false;       // stage[] recorded by the last launch
+    cudaEvent_t evCull = nullptr; // behind the light-hull pre-pass, inside the shadow-ray stage (cge_stats::vis_cull_ms)
+    bool cullTimed = false;
     // a frame rendered in concurrent bands (cge_render) uses one Scratch per band: kernels done / output copied
     cudaEvent_t bandDone = nullptr, copyDone = nullptr;
     // band b runs on a stream of priority (greatest - b), so that earlier bands win the SMs and finish (and leave for the
@@ -240,6 +242,7 @@ int acquire_scratch(cge_scene* sc, size_t pixels, bool wantIds, size_t gatherPix
         CGE_CUDA(cudaEventCreate(&s->ev2));
         for (auto& ev : s->stage)
             CGE_CUDA(cudaEventCreate(&ev));
+        CGE_CUDA(cudaEventCreate(&s->evCull));
         CGE_CUDA(cudaEventCreateWithFlags(&s->bandDone, cudaEventDisableTiming));
         CGE_CUDA(cudaEventCreateWithFlags(&s->copyDone, cudaEventDisableTiming));
         CGE_CUDA(cudaMalloc(&s->tileCounter, 64));
@@ -698,6 +701,7 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
     CGE_CUDA(cudaMemsetAsync(s->tileCounter, 0, 64, s->stream));
     CGE_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(Counters), s->stream));
     s->staged = false;
+    s->cullTimed = false;
     const Variant v = choose_variant(ds, *p, dp);
     cudaEvent_t* stage = s->stage;
     const unsigned myTiles = dp.tile_count;
@@ -774,6 +778,10 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
                 *launches += 1;
                 if (err != cudaSuccess)
                     return;
+                if (st == s->stream && levelBegin == 0 && levelEnd == wp.levels) { // (the whole stage on the main stream: timed)
+                    cudaEventRecord(s->evCull, st);
+                    s->cullTimed = true;
+                }
             }
             auto go = [&](auto kern) {
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 128, 0);
@@ -1024,6 +1032,10 @@ int fill_stats(const std::vector<Scratch*>& bands, cge_stats* st, uint32_t launc
             CGE_CUDA(cudaMemcpyAsync(&culled, b->wave.counts + 48, sizeof(culled), cudaMemcpyDeviceToHost, b->stream));
             CGE_CUDA(cudaStreamSynchronize(b->stream));
             st->shadow_samples_culled += culled;
+        }
+        if (b->staged && b->cullTimed) {
+            CGE_CUDA(cudaEventElapsedTime(&ms, b->stage[1], b->evCull));
+            st->vis_cull_ms += ms;
         }
         if (b->staged) // summed over the bands (which overlap in time when there are several)
             for (int k = 0; k < 4; k++) {
@@ -1574,6 +1586,8 @@ int cge_scene_destroy(cge_scene* sc)
         for (auto& ps : s->prioStream)
             if (ps)
                 cudaStreamDestroy(ps);
+        if (s->evCull)
+            cudaEventDestroy(s->evCull);
         if (s->bandDone)
             cudaEventDestroy(s->bandDone);
         if (s->copyDone)

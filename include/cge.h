@@ -226,6 +226,7 @@ typedef struct cge_stats {
     float stage_ms[4];        /* wavefront pipeline: wf_chain / wf_visibility / wf_shade / wf_fold device times */
     uint64_t shadow_samples_culled; /* light samples (shadow rays and samples that need none) of hits the light-hull pre-pass proved
                                        unoccluded: settled without a ray, not counted in shadow_rays (ABI 4) */
+    float vis_cull_ms;        /* the part of stage_ms[1] spent in that pre-pass (0 when it did not run or ran beside the chain stage) */
 } cge_stats;
 
 typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene + BVH on ONE GPU */

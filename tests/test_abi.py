@@ -30,7 +30,7 @@ def test_struct_sizes_match_header(cge):
     # sizes the C header implies (checked against the ctypes mirrors used by the tests and bench)
     assert C.sizeof(cge.CgeCamera) == 36
     assert C.sizeof(cge.CgeParams) == 64
-    assert C.sizeof(cge.CgeStats) == 96  # 7 x u64, 2 x f32, u32, 4 x f32 (= 84, padded to 88), u64
+    assert C.sizeof(cge.CgeStats) == 104  # 7 x u64, 2 x f32, u32, 4 x f32 (= 84, padded to 88), u64, f32 (padded to 104)
     assert C.sizeof(cge.CgeSceneDesc) == 32 + 7 * 8 + 8 + 2 * 8
 
 

@@ -22,7 +22,11 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "local_load", "local_store", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
         "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
-        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.avg",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_ld.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct"]
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -30,5 +34,5 @@ for vals in rows[2:]:
     d = dict(zip(hdr, vals))
     print("kernel:", d.get("Kernel Name", "?")[:80])
     for h, u in zip(hdr, units):
-        if any(h == w or h.startswith(w) for w in WANT) and ".max" not in h and ".min" not in h and ".per_second" not in h and "pct_of_peak_sustained_elapsed" not in h.replace("sm__throughput.avg.pct_of_peak_sustained_elapsed","").replace("dram__throughput.avg.pct_of_peak_sustained_elapsed","").replace("lts__throughput.avg.pct_of_peak_sustained_elapsed",""):
+        if any(h == w or h.startswith(w) for w in WANT) and ".max" not in h and ".min" not in h and ".per_second" not in h and "pct_of_peak_sustained_elapsed" not in h.replace("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed","").replace("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed","").replace("sm__throughput.avg.pct_of_peak_sustained_elapsed","").replace("dram__throughput.avg.pct_of_peak_sustained_elapsed","").replace("lts__throughput.avg.pct_of_peak_sustained_elapsed",""):
             print(f"  {h} = {d[h]} {u}")
