@@ -366,8 +366,9 @@ def main():
     # whose stage boundaries overlap in time, so a kernel's duration is taken from K more steps of the same frame rendered as
     # ONE pipeline (CGE_BANDS=1): same kernels, same work, CUDA events on the launching stream.
     os.environ["CGE_BANDS"] = "1"
+    os.environ["CGE_CHAIN_SPLIT"] = "0"  # (small launches run the level-0 shadow rays beside the chain stage: no clean stage boundary)
     single_s, st1, kernel_ms1, _ = timed(step_device, 1, args.steps)
-    del os.environ["CGE_BANDS"]
+    del os.environ["CGE_BANDS"], os.environ["CGE_CHAIN_SPLIT"]
     single_ms = single_s / args.steps * 1e3
     kms = torch.tensor([float(np.mean(kernel_ms1))] + st1["stage_ms_mean"] + [st1["vis_cull_ms_mean"]], dtype=torch.float64, device="cuda")
     # (of the single-pipeline steps the roofline is measured on: whether the light-hull pre-pass runs depends on the launch size)
@@ -529,8 +530,9 @@ def main():
             roof["fast_tree"] = {**fast_counts, "requested_bytes_per_ray": req,
                                  "requested_gbs": float(cnt[4]) * req / (stage_vis_ms * 1e-3) / 1e9,
                                  "note": "bytes the SAH traversal itself requests (served by L1/L2)"}
-        roof["measured_on"] = (f"{args.steps} steps of the same frame as ONE pipeline per GPU (CGE_BANDS=1, {single_ms:.3f} ms per step, max "
-                               "over ranks): the timed `value` steps may run the frame as concurrent bands whose stage boundaries overlap")
+        roof["measured_on"] = (f"{args.steps} steps of the same frame as ONE pipeline per GPU (CGE_BANDS=1 CGE_CHAIN_SPLIT=0, {single_ms:.3f} ms per step, max "
+                               "over ranks): the timed `value` steps may run the frame as concurrent bands, or its level-0 shadow rays beside "
+                               "the chain stage, whose stage boundaries overlap")
         roof["stage_ms"] = {**dict(zip(stage_names, stage_vals)), "wf_vis_cull_kernel": cull_ms, DOMINANT: vis_ms, "pipeline": pipeline_ms}
     elif pipeline_ms > 0:
         roof = {"bound": "l1", "kernel": "cge::render_kernel", "kernel_ms": pipeline_ms, "share_of_step": pipeline_ms / single_ms,

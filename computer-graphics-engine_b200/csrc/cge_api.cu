@@ -938,7 +938,10 @@ unsigned nBandsFor(const cge_scene* sc, const LightSet& ls, const cge_params& p,
     unsigned n = 1;
     const bool wave = choose_variant(scene_for(sc, p, ls), p, dp).wave;
     if (wave)
-        n = pixels >= (size_t(3) << 20) ? 4 : pixels >= (size_t(3) << 19) ? 2 : 1; // a 1 Mpixel share (C5 on 8 GPUs) is faster in one piece
+        // bands of at least 1.5 Mpixel, the size from which the light-hull pre-pass of the shadow stage pays (launch_render): a
+        // 4 Mpixel share (C5 on 2 GPUs) measured 7.58 ms as 4 bands without it, 7.15 ms as 2 bands with it; a 1 Mpixel share (8 GPUs)
+        // is faster in one piece
+        n = pixels >= (size_t(6) << 20) ? 4 : pixels >= (size_t(3) << 20) ? 2 : 1;
     else if (hostCopy)
         n = pixels >= (size_t(2) << 20) ? 4 : 1;
     n = unsigned(std::max(env_int("CGE_BANDS", int(n)), 1));

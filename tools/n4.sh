@@ -1,0 +1,7 @@
+N=${N:-4}
+run() { echo "== $*"; env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${STEPS:-8} --warmup 3 --no-cpu-baseline --no-configs 2>>gpurun_out/n$N.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.readlines()[-1])
+r=d.get('roofline',{})
+print('ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), 'match', d.get('frame_matches_1gpu'), 'stages', {k:round(v,3) for k,v in r.get('stage_ms',{}).items()}, 'prepass', r.get('light_hull_prepass'), 'frac', r.get('frac'))"; }
+for v in "$@"; do run $v; done
