@@ -14,7 +14,8 @@ reflection subtrees counted, src/render.cpp:100,118), so both arms are rated on 
 arms is the frame-time ratio.  The rays the GPU actually traverses (it traces each mirror chain once) are reported beside
 it as gpu_unique_mrays_s.
 
-  value       scene + BVH resident in HBM, frame written to a device buffer on rank 0 (N > 1: including the NCCL gather).
+  value       scene + BVH resident in HBM, frame written to a device buffer on rank 0 (N > 1: every rank's kernels store their pixels
+              into rank 0's frame over NVLink peer memory; the NCCL send / recv delivery is timed beside it as nccl_gather).
   e2e         the same frame through the host-facing C-ABI call: per step H2D of the light list + camera / params, the
               kernels, and the D2H copy of the W*H*12-byte frame into page-locked host memory (N > 1: every rank copies the
               rows it rendered into the shared host frame of cge_comm_host_frame over its own PCIe link).
@@ -287,7 +288,11 @@ def main():
     cam = pkg.camera_from_cfg(cfg)
 
     # device frame (value arm) and page-locked host frame (e2e arm; N > 1: the host frame every rank maps)
+    # N > 1: the device frame lives on rank 0 and is mapped into every rank (cge_comm_peer_frame): the render kernels of every rank
+    # store their pixels straight into it over NVLink; `nccl_gather` below times the NCCL send / recv delivery beside it
     frame_dev = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+    peer_ptr = comm.peer_frame(H * W * 12) if comm else None
+    peer_view = pkg.device_view(peer_ptr, (H, W, 3)) if comm and rank == 0 else None
     pinned = pkg.PinnedBuffer((H, W, 3), np.float32) if world == 1 else None
     host_frame = comm.host_frame((H, W, 3), np.float32) if comm else pinned.array
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
@@ -297,9 +302,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def step_gather():
+        _, _, st = comm.render(scene, cfg, device_ptrs=(frame_dev.data_ptr(), 0), camera=cam)
+        return st
+
     def step_device():
         if comm:
-            _, _, st = comm.render(scene, cfg, device_ptrs=(frame_dev.data_ptr(), 0), camera=cam)
+            _, _, st = comm.render(scene, cfg, peer_frame=peer_ptr, camera=cam)
         else:
             st = scene.render_device(cfg, frame_dev.data_ptr(), camera=cam)
         return st
@@ -385,14 +394,20 @@ def main():
 
     # the gathered frame must be the 1-GPU frame, bit for bit: an untimed whole-frame render on rank 0 against both deliveries
     frame_check = None
+    gather_ms = None
     if comm:
         step_e2e()
+        gather_s, _, _, _ = timed(step_gather, 2, args.steps)  # the same frame delivered by ncclSend / ncclRecv + one unpack launch
+        gather_ms = gather_s / args.steps * 1e3
+        step_device()
+        barrier()
+        peer_dev = peer_view.cpu().numpy() if rank == 0 else None
         gathered_dev = frame_dev.cpu().numpy() if rank == 0 else None
         if rank == 0:
             one, _, _ = scene.render(cfg, want_ids=False, camera=cam)
-            frame_check = {"frame_matches_1gpu": bool(frame_hash(one) == frame_hash(gathered_dev) == frame_hash(host_frame)),
-                           "sha256_16": {"one_gpu": frame_hash(one), "gathered_device_frame": frame_hash(gathered_dev),
-                                         "shared_host_frame": frame_hash(host_frame)}}
+            frame_check = {"frame_matches_1gpu": bool(frame_hash(one) == frame_hash(peer_dev) == frame_hash(gathered_dev) == frame_hash(host_frame)),
+                           "sha256_16": {"one_gpu": frame_hash(one), "peer_device_frame": frame_hash(peer_dev),
+                                         "gathered_device_frame": frame_hash(gathered_dev), "shared_host_frame": frame_hash(host_frame)}}
         dist.barrier()
 
     # fast-tree test counts of this frame (one untimed counting render, per-thread kernel: 64 B per node visit = two box
@@ -561,6 +576,10 @@ def main():
     }
     if frame_check:
         line.update(frame_check)
+        line["delivery"] = ("every rank's render kernels store their pixels into rank 0's device frame over NVLink peer memory "
+                            "(cge_comm_peer_frame, CGE_FLAG_PEER_FRAME), a 4-byte all-reduce signals completion")
+        line["nccl_gather"] = {"ms_per_step": gather_ms, "note": "the same frame delivered by ncclSend / ncclRecv of compact rows + one "
+                                                                   "unpack launch on rank 0 (the default of cge_render_distributed)"}
     if roof:
         line["roofline"] = roof
     if cpu:

@@ -22,7 +22,7 @@ LIB_PATH = Path(os.environ.get("CGE_LIB", _PKG / "libcge.so"))  # CGE_LIB: devel
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
 FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_OUTPUT_RGBA8 = 1, 2, 4, 8
-FLAG_PARTITION_TILE_ROWS, FLAG_SHARED_HOST_FRAME = 16, 32
+FLAG_PARTITION_TILE_ROWS, FLAG_SHARED_HOST_FRAME, FLAG_PEER_FRAME = 16, 32, 64
 # development switches (include/cge.h CGE_DEV_FLAG_*): force one of the two production pipelines / the per-pixel cost map
 FLAG_PER_THREAD, FLAG_WAVEFRONT, FLAG_DEBUG_CYCLES = 1 << 16, 1 << 17, 1 << 18
 UNIQUE_ID_BYTES = 128
@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "cge_bvh_build_reference_order", "cge_bvh_validate", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
-    "cge_comm_destroy", "cge_comm_host_frame", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
+    "cge_comm_destroy", "cge_comm_host_frame", "cge_comm_peer_frame", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
 ]
 
 _lib = None
@@ -129,6 +129,8 @@ def lib() -> C.CDLL:
         l.cge_comm_destroy.argtypes = [C.c_void_p]
         if hasattr(l, "cge_comm_host_frame"):  # (absent from older development builds loaded through CGE_LIB for A/B runs)
             l.cge_comm_host_frame.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        if hasattr(l, "cge_comm_peer_frame"):
+            l.cge_comm_peer_frame.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         l.cge_render_distributed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CgeCamera), C.POINTER(CgeParams),
                                              C.c_void_p, C.c_void_p, C.POINTER(CgeStats)]
         l.cge_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
@@ -390,13 +392,27 @@ class Comm:
         buf = (C.c_char * nbytes).from_address(ptr.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def peer_frame(self, nbytes: int) -> int:
+        """Collective: a device frame on rank 0 that every rank's kernels can store into (cge_comm_peer_frame); returns this
+        process's device pointer to it, for ``render(..., peer_frame=ptr)``."""
+        ptr = C.c_void_p()
+        _check(lib().cge_comm_peer_frame(self.handle, int(nbytes), C.byref(ptr)))
+        return int(ptr.value)
+
     def render(self, scene: Scene, cfg: dict, traversal: int = TRAVERSAL_FAST, want_ids: bool = False, rgb_out=None,
-               ids_out=None, device_ptrs=None, camera: CgeCamera | None = None, shared_frame=None, shared_ids=None, flags: int = 0):
-        """cge_render_distributed.  shared_frame: a Comm.host_frame array every rank passes (CGE_FLAG_SHARED_HOST_FRAME)."""
+               ids_out=None, device_ptrs=None, camera: CgeCamera | None = None, shared_frame=None, shared_ids=None, flags: int = 0,
+               peer_frame: int | None = None):
+        """cge_render_distributed.  shared_frame: a Comm.host_frame array every rank passes (CGE_FLAG_SHARED_HOST_FRAME);
+        peer_frame: this rank's pointer from Comm.peer_frame (CGE_FLAG_PEER_FRAME)."""
         cam = camera or camera_from_cfg(cfg)
         p = params_from_cfg(cfg, traversal, want_ids, (0, 1), flags)
         H, W = cfg["height"], cfg["width"]
         st = CgeStats()
+        if peer_frame is not None:
+            p.flags |= FLAG_PEER_FRAME
+            _check(lib().cge_render_distributed(scene.handle, self.handle, C.byref(cam), C.byref(p), C.c_void_p(peer_frame), None,
+                                                C.byref(st)))
+            return None, None, st.as_dict()
         if device_ptrs is not None:
             p.flags |= FLAG_RGB_DEVICE_PTR
             rgb_ptr, ids_ptr = device_ptrs
@@ -415,6 +431,15 @@ class Comm:
                 ids = ids_out if ids_out is not None else np.full((H, W), -1, np.int32)
         _check(lib().cge_render_distributed(scene.handle, self.handle, C.byref(cam), C.byref(p), _p(rgb), _p(ids), C.byref(st)))
         return rgb, ids, st.as_dict()
+
+
+def device_view(ptr: int, shape, typestr: str = "<f4"):
+    """A torch tensor over device memory the library owns (e.g. rank 0's Comm.peer_frame), without a copy (tests / bench only)."""
+    import torch
+
+    class _View:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_View(), device="cuda")
 
 
 # ---- device KATs (libIntersect functions evaluated on the GPU) ---------------------------------------------

@@ -162,6 +162,7 @@ struct cge_comm {
         size_t bytes;
     };
     std::vector<HostFrame> host_frames; // cge_comm_host_frame mappings, released with the communicator
+    std::vector<HostFrame> peer_frames; // cge_comm_peer_frame: rank 0's device frames (owned there, IPC mappings elsewhere)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -2292,6 +2293,12 @@ int cge_comm_destroy(cge_comm* c)
     if (!c)
         return CGE_OK;
     const NcclApi* api = nccl_api();
+    for (const auto& f : c->peer_frames) {
+        if (c->rank == 0)
+            cudaFree(f.ptr);
+        else
+            cudaIpcCloseMemHandle(f.ptr);
+    }
     for (const auto& f : c->host_frames) {
         cudaHostUnregister(f.ptr);
         munmap(f.ptr, f.bytes);
@@ -2365,6 +2372,51 @@ int cge_comm_host_frame(cge_comm* comm, uint64_t bytes, void** out)
     return CGE_OK;
 }
 
+int cge_comm_peer_frame(cge_comm* comm, uint64_t bytes, void** out)
+{
+    if (!comm || !out || bytes == 0)
+        return fail(CGE_ERR_INVALID_ARG, "bad peer frame arguments");
+    const NcclApi* api = nccl_api();
+    if (!api)
+        return fail(CGE_ERR_NCCL, "libnccl.so.2 not found");
+    CGE_CUDA(cudaSetDevice(comm->device));
+    ncclComm_t nc = static_cast<ncclComm_t>(comm->nccl);
+    cudaIpcMemHandle_t handle {};
+    void* ptr = nullptr;
+    bool okHere = true;
+    if (comm->rank == 0) // the frame lives on rank 0's GPU; its handle travels over the communicator
+        okHere = cudaMalloc(&ptr, size_t(bytes)) == cudaSuccess && cudaIpcGetMemHandle(&handle, ptr) == cudaSuccess;
+    char* dHandle = nullptr;
+    int* dOk = nullptr;
+    CGE_CUDA(cudaMalloc(&dHandle, sizeof handle));
+    CGE_CUDA(cudaMalloc(&dOk, sizeof(int)));
+    cudaMemcpy(dHandle, &handle, sizeof handle, cudaMemcpyHostToDevice);
+    ncclResult_t nr = comm->n_ranks > 1 ? api->Broadcast(dHandle, dHandle, sizeof handle, ncclChar, 0, nc, nullptr) : ncclSuccess;
+    cudaError_t ce = cudaMemcpy(&handle, dHandle, sizeof handle, cudaMemcpyDeviceToHost); // (legacy stream: ordered after the broadcast)
+    if (comm->rank != 0)
+        okHere = nr == ncclSuccess && ce == cudaSuccess && cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    int ok = okHere ? 1 : 0, okAll = 0;
+    cudaMemcpy(dOk, &ok, sizeof(int), cudaMemcpyHostToDevice);
+    if (nr == ncclSuccess && comm->n_ranks > 1)
+        nr = api->AllReduce(dOk, dOk, 1, ncclInt, ncclMin, nc, nullptr);
+    cudaMemcpy(&okAll, dOk, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dHandle);
+    cudaFree(dOk);
+    if (nr != ncclSuccess || !okAll) {
+        cudaGetLastError();
+        if (ptr && okHere) {
+            if (comm->rank == 0)
+                cudaFree(ptr);
+            else
+                cudaIpcCloseMemHandle(ptr);
+        }
+        return fail(nr != ncclSuccess ? CGE_ERR_NCCL : CGE_ERR_CUDA, "could not map rank 0's device frame on every rank (CUDA IPC / peer access)");
+    }
+    comm->peer_frames.push_back({ ptr, size_t(bytes) });
+    *out = ptr;
+    return CGE_OK;
+}
+
 int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam, const cge_params* pIn, float* rgbOut,
     int32_t* idsOut, cge_stats* st)
 {
@@ -2379,11 +2431,22 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         return rc;
     const bool wantIds = (p.flags & CGE_FLAG_WANT_PRIM_IDS) != 0;
     const bool rgba8 = p.flags & CGE_FLAG_OUTPUT_RGBA8;
-    const bool devOut = p.flags & CGE_FLAG_RGB_DEVICE_PTR;
+    const bool devOut = (p.flags & CGE_FLAG_RGB_DEVICE_PTR) || (p.flags & CGE_FLAG_PEER_FRAME);
     // every rank writes its rows into the shared host frame itself (not with bloom: it needs the gathered frame on one GPU)
     const bool shared = (p.flags & CGE_FLAG_SHARED_HOST_FRAME) && comm->n_ranks > 1 && !(p.features & CGE_FEAT_BLOOM_EFFECT);
-    if (!cam || ((comm->rank == 0 || shared) && !rgbOut))
+    // every rank's kernels store straight into rank 0's device frame (cge_comm_peer_frame)
+    const bool peer = (p.flags & CGE_FLAG_PEER_FRAME) && comm->n_ranks > 1;
+    if (!cam || ((comm->rank == 0 || shared || peer) && !rgbOut))
         return fail(CGE_ERR_INVALID_ARG, "null camera or output");
+    if ((p.flags & CGE_FLAG_PEER_FRAME) && (wantIds || rgba8 || (p.flags & CGE_FLAG_SHARED_HOST_FRAME)))
+        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_PEER_FRAME delivers the float frame on rank 0's GPU (no ids, no RGBA8, no host frame)");
+    if (p.flags & CGE_FLAG_PEER_FRAME) {
+        bool known = false;
+        for (const auto& f : comm->peer_frames)
+            known = known || (f.ptr == rgbOut && f.bytes >= size_t(p.width) * size_t(p.height) * 12);
+        if (!known)
+            return fail(CGE_ERR_INVALID_ARG, "CGE_FLAG_PEER_FRAME: rgb_out must be the pointer cge_comm_peer_frame returned on this rank");
+    }
     if (sc->device != comm->device)
         return fail(CGE_ERR_INVALID_ARG, "scene and communicator live on different devices");
     if ((rgba8 || (p.flags & CGE_FLAG_SHARED_HOST_FRAME)) && devOut)
@@ -2407,19 +2470,19 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     // a rank's share: units = tile rows rank, rank + R, ...; COMPACT layout (dev_scene.h): units(r) blocks of 4 x W pixels
     auto unitsOf = [&](unsigned r) { return dp.n_tiles_y > r ? (dp.n_tiles_y - r + R - 1) / R : 0u; };
     const unsigned myUnits = unitsOf(rank);
-    const bool compact = R > 1 && (rank != 0 || shared); // rank 0 renders straight into the frame it gathers
+    const bool compact = R > 1 && (rank != 0 || shared) && !peer; // rank 0 renders straight into the frame it gathers
     dp.compact_units = compact ? std::max(myUnits, 1u) : 0u;
     const size_t blockPixels = size_t(kTileH) * W;
     size_t othersPixels = 0;
     UnpackRows up {};
-    if (rank == 0 && !shared)
+    if (rank == 0 && !shared && !peer)
         for (unsigned r = 1; r < R; r++) {
             up.offset[r] = unsigned(othersPixels / blockPixels);
             up.units[r] = unitsOf(r);
             othersPixels += size_t(unitsOf(r)) * blockPixels;
         }
     Scratch* s = nullptr;
-    rc = acquire_scratch(sc, compact ? std::max<size_t>(size_t(myUnits) * blockPixels, 1) : pixels, true, std::max<size_t>(othersPixels, 1), &s);
+    rc = acquire_scratch(sc, compact ? std::max<size_t>(size_t(myUnits) * blockPixels, 1) : peer ? size_t(1) : pixels, true, std::max<size_t>(othersPixels, 1), &s);
     if (rc) {
         release_scratch(sc, s);
         return rc;
@@ -2442,7 +2505,7 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         return rc;
     }
     cudaEventRecord(s->ev0, s->stream);
-    float* frame = (rank == 0 && devOut) ? rgbOut : s->rgb;
+    float* frame = ((rank == 0 && devOut) || peer) ? rgbOut : s->rgb;
     int* frameIds = wantIds ? ((rank == 0 && devOut && idsOut) ? idsOut : s->ids) : nullptr;
     if (nBands > 1) {
         std::vector<uint2> ranges;
@@ -2481,6 +2544,11 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         if (wantIds && idsOut)
             copyOut(reinterpret_cast<char*>(idsOut), reinterpret_cast<const char*>(s->ids), 4);
         // the frame is complete when every rank's copy has landed: a 4-byte all-reduce behind the copies on every stream
+        nr = api->AllReduce(s->tileCounter, s->tileCounter, 1, ncclInt, ncclSum, nc, s->stream);
+    } else if (rc == CGE_OK && peer) {
+        // ---- the pixels are already in rank 0's frame: every rank's kernels stored them there over NVLink.  Kernel completion
+        // makes a rank's stores visible; the 4-byte all-reduce behind the kernels on every stream completes on rank 0 only after
+        // every rank has got there ------------------------------------------------------------------------------------------------
         nr = api->AllReduce(s->tileCounter, s->tileCounter, 1, ncclInt, ncclSum, nc, s->stream);
     } else if (rc == CGE_OK && R > 1) {
         // ---- gather on rank 0: the other ranks send their compact rows as they are, one unpack launch scatters all of them ----

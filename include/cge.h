@@ -179,9 +179,12 @@ enum {
                                           NaN -> 0) on the GPU, so the D2H copy is 4 instead of 12 bytes per pixel */
     CGE_FLAG_PARTITION_TILE_ROWS = 1u << 4, /* part_index / part_count deal whole tile rows (runs of 4 complete image rows) instead
                                           of single 8x4 tiles; cge_render_distributed always partitions this way */
-    CGE_FLAG_SHARED_HOST_FRAME = 1u << 5    /* cge_render_distributed: rgb_out is the frame cge_comm_host_frame returned (the same
+    CGE_FLAG_SHARED_HOST_FRAME = 1u << 5,   /* cge_render_distributed: rgb_out is the frame cge_comm_host_frame returned (the same
                                           on every rank); each rank copies the rows it rendered straight into it over its own
                                           PCIe link instead of rank 0 gathering the frame and copying all of it */
+    CGE_FLAG_PEER_FRAME = 1u << 6           /* cge_render_distributed: rgb_out is the pointer cge_comm_peer_frame returned on this rank
+                                          (rank 0's device frame, mapped into every rank): the kernels of every rank store their
+                                          pixels straight into it over NVLink - no gather, no staging buffer, no unpack */
 };
 /* Development switches (A/B measurements and the tests that prove both production pipelines bit-identical); not needed by a
  * caller, every setting renders the same frame. */
@@ -335,12 +338,20 @@ int cge_comm_destroy(cge_comm* comm);
  *   CGE_FLAG_SHARED_HOST_FRAME   rgb_out (and prim_id_out) are frames from cge_comm_host_frame, the same memory on every rank: each
  *                                rank copies the rows it rendered straight into it over its own PCIe link (one strided copy), and a
  *                                4-byte all-reduce tells every rank when the frame is complete.  No device-side gather at all.
+ *   CGE_FLAG_PEER_FRAME          rgb_out is this rank's pointer from cge_comm_peer_frame: ONE device frame on rank 0 that every rank's
+ *                                render kernels store into directly (peer memory over NVLink / NVSwitch); a 4-byte all-reduce behind
+ *                                the kernels tells every rank when the frame is complete on rank 0.  Float frame, no prim_id_out.
  * The image does not depend on the number of ranks (bit-identical to cge_render). */
 int cge_render_distributed(cge_scene* scene, cge_comm* comm, const cge_camera* camera, const cge_params* params,
                            float* rgb_out, int32_t* prim_id_out, cge_stats* stats_out);
 /* Collective over the communicator: `bytes` of host memory mapped by every rank (POSIX shared memory, page-locked in each
  * process), for CGE_FLAG_SHARED_HOST_FRAME.  *out is this process's address of it.  Released by cge_comm_destroy. */
 int cge_comm_host_frame(cge_comm* comm, uint64_t bytes, void** out);
+/* Collective over the communicator: `bytes` of device memory on rank 0 that every rank can address (CUDA IPC; the ranks are
+ * separate processes on one node with peer access to rank 0's GPU), for CGE_FLAG_PEER_FRAME.  *out is this process's device
+ * pointer to it: on rank 0 the frame itself (readable like any device buffer once cge_render_distributed has returned), on the
+ * other ranks a mapping of it.  Released by cge_comm_destroy. */
+int cge_comm_peer_frame(cge_comm* comm, uint64_t bytes, void** out);
 
 /* pinned host memory for rgb_out / prim_id_out so the D2H copy runs at full PCIe speed (optional) */
 int cge_host_alloc(void** out, uint64_t bytes);

@@ -74,6 +74,18 @@ def test_distributed_entry_on_one_rank_equals_cge_render(cge, name, size):
             p.flags |= cge.FLAG_RGB_DEVICE_PTR
             assert cge.lib().cge_render_distributed(sc.handle, comm.handle, C.byref(cam), C.byref(p), guard.ctypes.data, None,
                                                     C.byref(stc)) == cge.ERR_UNSUPPORTED
+            # the peer frame (rank 0's device frame every rank's kernels store into; with one rank: the frame itself).  The N-rank
+            # case needs N processes and N GPUs: tools/multi_gpu_check.py and bench.py compare its frame with the 1-GPU frame.
+            H, W = cfg["height"], cfg["width"]
+            pf = comm.peer_frame(H * W * 12)
+            comm.render(sc, cfg, peer_frame=pf)
+            assert cge.device_view(pf, (H, W, 3)).cpu().numpy().tobytes() == rgb.tobytes()
+            with pytest.raises(cge.CgeError) as e:  # a pointer the communicator did not hand out
+                comm.render(sc, cfg, peer_frame=pf + 256)
+            assert e.value.code == cge.ERR_INVALID_ARG
+            pw = cge.params_from_cfg(cfg, cge.TRAVERSAL_FAST, True, (0, 1), cge.FLAG_PEER_FRAME)  # no primitive ids in this mode
+            assert cge.lib().cge_render_distributed(sc.handle, comm.handle, C.byref(cam), C.byref(pw), C.c_void_p(pf), None,
+                                                    C.byref(stc)) == cge.ERR_UNSUPPORTED
     finally:
         comm.close()
 

@@ -39,6 +39,12 @@ for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_s
         shared_ids[:] = -7
         dist.barrier()
         _, _, sts = comm.render(sc, cfg, want_ids=True, shared_frame=shared_rgb, shared_ids=shared_ids)
+        # ... and with every rank's kernels storing straight into rank 0's device frame over NVLink (no gather either)
+        pf = comm.peer_frame(H * W * 12)
+        dist.barrier()
+        _, _, stp = comm.render(sc, cfg, peer_frame=pf)
+        _, _, stp = comm.render(sc, cfg, peer_frame=pf)
+        peer_rgb = pkg.device_view(pf, (H, W, 3)).cpu().numpy() if rank == 0 else None
         rgba = np.zeros((H, W, 4), np.uint8)
         import ctypes as C
         p8 = pkg.params_from_cfg(cfg, pkg.TRAVERSAL_FAST, False, (0, 1), pkg.FLAG_OUTPUT_RGBA8)
@@ -51,9 +57,11 @@ for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_s
             same = rgb.tobytes() == rgb1.tobytes() and np.array_equal(ids, ids1)
             same_shared = shared_rgb.tobytes() == rgb1.tobytes() and np.array_equal(shared_ids, ids1)
             same8 = rc8 == 0 and np.array_equal(rgba, rgba1)
-            ok &= same and same_shared and same8
+            same_peer = peer_rgb.tobytes() == rgb1.tobytes()
+            ok &= same and same_shared and same8 and same_peer
             print(json.dumps({"cfg": spec, "w": cfg["width"], "h": cfg["height"], "ranks": world, "bit_identical_to_1gpu": bool(same),
-                              "shared_host_frame_identical": bool(same_shared), "rgba8_identical": bool(same8),
+                              "shared_host_frame_identical": bool(same_shared), "rgba8_identical": bool(same8), "peer_frame_identical": bool(same_peer),
+                              "peer_total_ms": round(stp["total_ms"], 3),
                               "shared_total_ms": round(sts["total_ms"], 3),
                               "dist_total_ms": round(st["total_ms"], 3), "dist_kernel_ms_rank0": round(st["kernel_ms"], 3),
                               "single_kernel_ms": round(st1["kernel_ms"], 3), "launches_rank0": st["kernel_launches"]}), flush=True)
