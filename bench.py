@@ -306,6 +306,10 @@ def main():
         _, _, st = comm.render(scene, cfg, device_ptrs=(frame_dev.data_ptr(), 0), camera=cam)
         return st
 
+    def step_dynamic():
+        _, _, st = comm.render(scene, cfg, peer_frame=peer_ptr, camera=cam, flags=pkg.FLAG_DYNAMIC_TILES)
+        return st
+
     def step_device():
         if comm:
             _, _, st = comm.render(scene, cfg, peer_frame=peer_ptr, camera=cam)
@@ -394,19 +398,26 @@ def main():
 
     # the gathered frame must be the 1-GPU frame, bit for bit: an untimed whole-frame render on rank 0 against both deliveries
     frame_check = None
-    gather_ms = None
+    gather_ms = dynamic_ms = None
     if comm:
         step_e2e()
         gather_s, _, _, _ = timed(step_gather, 2, args.steps)  # the same frame delivered by ncclSend / ncclRecv + one unpack launch
         gather_ms = gather_s / args.steps * 1e3
+        # ... and with a quarter of every rank's tile rows dealt at run time by a counter beside rank 0's frame (CGE_FLAG_DYNAMIC_TILES)
+        dyn_s, _, _, _ = timed(step_dynamic, 2, args.steps)
+        dynamic_ms = dyn_s / args.steps * 1e3
+        barrier()
+        dyn_dev = peer_view.cpu().numpy() if rank == 0 else None
         step_device()
         barrier()
         peer_dev = peer_view.cpu().numpy() if rank == 0 else None
         gathered_dev = frame_dev.cpu().numpy() if rank == 0 else None
         if rank == 0:
             one, _, _ = scene.render(cfg, want_ids=False, camera=cam)
-            frame_check = {"frame_matches_1gpu": bool(frame_hash(one) == frame_hash(peer_dev) == frame_hash(gathered_dev) == frame_hash(host_frame)),
+            frame_check = {"frame_matches_1gpu": bool(frame_hash(one) == frame_hash(peer_dev) == frame_hash(gathered_dev) == frame_hash(host_frame)
+                                                      == frame_hash(dyn_dev)),
                            "sha256_16": {"one_gpu": frame_hash(one), "peer_device_frame": frame_hash(peer_dev),
+                                         "peer_device_frame_dynamic_tiles": frame_hash(dyn_dev),
                                          "gathered_device_frame": frame_hash(gathered_dev), "shared_host_frame": frame_hash(host_frame)}}
         dist.barrier()
 
@@ -578,6 +589,10 @@ def main():
         line.update(frame_check)
         line["delivery"] = ("every rank's render kernels store their pixels into rank 0's device frame over NVLink peer memory "
                             "(cge_comm_peer_frame, CGE_FLAG_PEER_FRAME), a 4-byte all-reduce signals completion")
+        line["dynamic_tiles"] = {"ms_per_step": dynamic_ms,
+                                 "note": "the same frame with CGE_FLAG_DYNAMIC_TILES: the first quarter of every rank's tile rows is a pool of "
+                                         "chunks dealt at run time by an atomic counter beside rank 0's frame (over NVLink) to whichever GPU "
+                                         "has finished its static rows; measured beside the static partition that `value` uses"}
         line["nccl_gather"] = {"ms_per_step": gather_ms, "note": "the same frame delivered by ncclSend / ncclRecv of compact rows + one "
                                                                    "unpack launch on rank 0 (the default of cge_render_distributed)"}
     if roof:

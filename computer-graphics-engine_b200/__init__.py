@@ -22,7 +22,7 @@ LIB_PATH = Path(os.environ.get("CGE_LIB", _PKG / "libcge.so"))  # CGE_LIB: devel
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = range(6)
 TRAVERSAL_REFERENCE, TRAVERSAL_FAST = 0, 1
 FLAG_WANT_PRIM_IDS, FLAG_RGB_DEVICE_PTR, FLAG_COUNT_TESTS, FLAG_OUTPUT_RGBA8 = 1, 2, 4, 8
-FLAG_PARTITION_TILE_ROWS, FLAG_SHARED_HOST_FRAME, FLAG_PEER_FRAME = 16, 32, 64
+FLAG_PARTITION_TILE_ROWS, FLAG_SHARED_HOST_FRAME, FLAG_PEER_FRAME, FLAG_DYNAMIC_TILES = 16, 32, 64, 128
 # development switches (include/cge.h CGE_DEV_FLAG_*): force one of the two production pipelines / the per-pixel cost map
 FLAG_PER_THREAD, FLAG_WAVEFRONT, FLAG_DEBUG_CYCLES = 1 << 16, 1 << 17, 1 << 18
 UNIQUE_ID_BYTES = 128

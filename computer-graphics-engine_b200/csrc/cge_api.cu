@@ -102,6 +102,7 @@ struct Scratch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t stage[5] = {}; // wavefront stage boundaries: chain | shadow rays | shading | fold |
     bool staged = false;       // stage[] recorded by the last launch
+    unsigned* grant = nullptr;    // { tile_first, tile_count, part_index } of a dynamically dealt chunk (grant_kernel)
     cudaEvent_t evCull = nullptr; // behind the light-hull pre-pass, inside the shadow-ray stage (cge_stats::vis_cull_ms)
     bool cullTimed = false;
     // a frame rendered in concurrent bands (cge_render) uses one Scratch per band: kernels done / output copied
@@ -162,7 +163,9 @@ struct cge_comm {
         size_t bytes;
     };
     std::vector<HostFrame> host_frames; // cge_comm_host_frame mappings, released with the communicator
-    std::vector<HostFrame> peer_frames; // cge_comm_peer_frame: rank 0's device frames (owned there, IPC mappings elsewhere)
+    std::vector<HostFrame> peer_frames; // cge_comm_peer_frame: rank 0's device frames (owned there, IPC mappings elsewhere); each is
+                                        // followed by the tile counter of CGE_FLAG_DYNAMIC_TILES (at bytes rounded up to 256)
+    std::vector<uint32_t> peer_grants;  // grants taken from that counter so far, per frame (the same number on every rank)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1592,6 +1595,8 @@ int cge_scene_destroy(cge_scene* sc)
                 cudaStreamDestroy(ps);
         if (s->evCull)
             cudaEventDestroy(s->evCull);
+        if (s->grant)
+            cudaFree(s->grant);
         if (s->bandDone)
             cudaEventDestroy(s->bandDone);
         if (s->copyDone)
@@ -2372,6 +2377,31 @@ int cge_comm_host_frame(cge_comm* comm, uint64_t bytes, void** out)
     return CGE_OK;
 }
 
+namespace {
+inline size_t peer_counter_offset(size_t bytes) { return (bytes + 255) / 256 * 256; }
+
+// Dynamic tile dealing (CGE_FLAG_DYNAMIC_TILES): the head of a pipeline takes the next chunk of the frame's pool from the counter
+// beside rank 0's frame - a system-scope atomic over NVLink - and leaves it where the pipeline's kernels read their tile range
+// (DevParams::grant).  Chunk c belongs to the tile list of rank c % nRanks: chunk c / nRanks of the first pool rows of that list.
+__global__ void grant_kernel(unsigned* counter, unsigned base, unsigned nRanks, unsigned chunksPerOwner, unsigned chunkRows, unsigned poolPct,
+    unsigned nTilesX, unsigned nTilesY, unsigned* grant)
+{
+    const unsigned idx = atomicAdd_system(counter, 1u) - base;
+    unsigned first = 0, count = 0, owner = 0;
+    if (idx < nRanks * chunksPerOwner) {
+        owner = idx % nRanks;
+        const unsigned j = idx / nRanks;
+        const unsigned rows = nTilesY > owner ? (nTilesY - owner + nRanks - 1) / nRanks : 0u;
+        const unsigned pool = rows * poolPct / 100u;
+        if (j * chunkRows < pool) {
+            first = j * chunkRows * nTilesX;
+            count = min(chunkRows, pool - j * chunkRows) * nTilesX;
+        }
+    }
+    grant[0] = first, grant[1] = count, grant[2] = owner;
+}
+} // namespace
+
 int cge_comm_peer_frame(cge_comm* comm, uint64_t bytes, void** out)
 {
     if (!comm || !out || bytes == 0)
@@ -2385,7 +2415,9 @@ int cge_comm_peer_frame(cge_comm* comm, uint64_t bytes, void** out)
     void* ptr = nullptr;
     bool okHere = true;
     if (comm->rank == 0) // the frame lives on rank 0's GPU; its handle travels over the communicator
-        okHere = cudaMalloc(&ptr, size_t(bytes)) == cudaSuccess && cudaIpcGetMemHandle(&handle, ptr) == cudaSuccess;
+        okHere = cudaMalloc(&ptr, peer_counter_offset(size_t(bytes)) + 256) == cudaSuccess
+            && cudaMemset(static_cast<char*>(ptr) + peer_counter_offset(size_t(bytes)), 0, 256) == cudaSuccess
+            && cudaIpcGetMemHandle(&handle, ptr) == cudaSuccess;
     char* dHandle = nullptr;
     int* dOk = nullptr;
     CGE_CUDA(cudaMalloc(&dHandle, sizeof handle));
@@ -2413,6 +2445,7 @@ int cge_comm_peer_frame(cge_comm* comm, uint64_t bytes, void** out)
         return fail(nr != ncclSuccess ? CGE_ERR_NCCL : CGE_ERR_CUDA, "could not map rank 0's device frame on every rank (CUDA IPC / peer access)");
     }
     comm->peer_frames.push_back({ ptr, size_t(bytes) });
+    comm->peer_grants.push_back(0u);
     *out = ptr;
     return CGE_OK;
 }
@@ -2440,10 +2473,16 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         return fail(CGE_ERR_INVALID_ARG, "null camera or output");
     if ((p.flags & CGE_FLAG_PEER_FRAME) && (wantIds || rgba8 || (p.flags & CGE_FLAG_SHARED_HOST_FRAME)))
         return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_PEER_FRAME delivers the float frame on rank 0's GPU (no ids, no RGBA8, no host frame)");
+    size_t peerIdx = 0;
+    if ((p.flags & CGE_FLAG_DYNAMIC_TILES) && !(p.flags & CGE_FLAG_PEER_FRAME))
+        return fail(CGE_ERR_UNSUPPORTED, "CGE_FLAG_DYNAMIC_TILES needs CGE_FLAG_PEER_FRAME (dealt chunks have no fixed place in a rank's buffer)");
     if (p.flags & CGE_FLAG_PEER_FRAME) {
         bool known = false;
-        for (const auto& f : comm->peer_frames)
-            known = known || (f.ptr == rgbOut && f.bytes >= size_t(p.width) * size_t(p.height) * 12);
+        for (size_t i = 0; i < comm->peer_frames.size(); i++) {
+            const auto& f = comm->peer_frames[i];
+            if (f.ptr == rgbOut && f.bytes >= size_t(p.width) * size_t(p.height) * 12)
+                known = true, peerIdx = i;
+        }
         if (!known)
             return fail(CGE_ERR_INVALID_ARG, "CGE_FLAG_PEER_FRAME: rgb_out must be the pointer cge_comm_peer_frame returned on this rank");
     }
@@ -2481,6 +2520,19 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
             up.units[r] = unitsOf(r);
             othersPixels += size_t(unitsOf(r)) * blockPixels;
         }
+    // ---- dynamic tile dealing: the first poolPct % of every rank's tile rows form a pool of chunks that is dealt by a counter in
+    // rank 0's memory to whichever rank gets there first; each rank renders the rest of its rows (the static part) as before, then
+    // K pipelines that each take one chunk (or nothing) ------------------------------------------------------------------------
+    const bool dynamic = peer && (p.flags & CGE_FLAG_DYNAMIC_TILES) && !dp.aa_side;
+    const unsigned poolPct = dynamic ? unsigned(std::min(std::max(env_int("CGE_DYNAMIC_POOL_PCT", 25), 1), 90)) : 0u;
+    const unsigned chunksPerOwner = unsigned(std::min(std::max(env_int("CGE_DYNAMIC_CHUNKS", 2), 1), 8));
+    const unsigned kGrants = chunksPerOwner + 1; // pipelines per rank: N * K grants >= N * chunksPerOwner chunks, every chunk is taken
+    const unsigned poolRows = unitsOf(rank) * poolPct / 100u, maxPoolRows = unitsOf(0) * poolPct / 100u;
+    const unsigned chunkRows = std::max(1u, (maxPoolRows + chunksPerOwner - 1) / chunksPerOwner);
+    if (dynamic) {
+        dp.tile_first = poolRows * dp.n_tiles_x;
+        dp.tile_count -= std::min(dp.tile_count, poolRows * dp.n_tiles_x);
+    }
     Scratch* s = nullptr;
     rc = acquire_scratch(sc, compact ? std::max<size_t>(size_t(myUnits) * blockPixels, 1) : peer ? size_t(1) : pixels, true, std::max<size_t>(othersPixels, 1), &s);
     if (rc) {
@@ -2511,12 +2563,57 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         std::vector<uint2> ranges;
         for (unsigned b = 0; b < nBands; b++) {
             const unsigned f0 = unsigned(uint64_t(dp.tile_count) * b / nBands), f1 = unsigned(uint64_t(dp.tile_count) * (b + 1) / nBands);
-            ranges.push_back(make_uint2(f0, f1 - f0));
+            ranges.push_back(make_uint2(dp.tile_first + f0, f1 - f0));
         }
         rc = launch_bands(sc, ls, bands, ranges, false, cam, &p, dp, frame, frameIds, &launches,
             [&](unsigned, Scratch* sb) { cudaEventRecord(sb->bandDone, sb->stream); });
     } else {
         rc = launch_render(sc, ls, s, cam, &p, dp, frame, frameIds, &launches);
+    }
+    std::vector<Scratch*> dyn; // one Scratch (queues, counters, grant) per dynamic pipeline; two streams, alternating
+    if (rc == CGE_OK && dynamic) {
+        unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(rgbOut) + peer_counter_offset(comm->peer_frames[peerIdx].bytes));
+        const unsigned base = comm->peer_grants[peerIdx];
+        comm->peer_grants[peerIdx] += R * kGrants; // (unsigned wrap-around is fine: the kernel subtracts modulo 2^32)
+        cudaEventRecord(s->copyDone, s->stream);   // the static part of this rank is queued: the dealt chunks follow it
+        DevParams gp = dp;
+        gp.tile_first = 0;
+        gp.tile_count = chunkRows * dp.n_tiles_x; // sizes the launch; the grant says what is rendered
+        cudaStream_t dynStream[2] = { nullptr, nullptr };
+        for (unsigned g = 0; g < kGrants && rc == CGE_OK; g++) {
+            Scratch* sd = nullptr;
+            rc = acquire_scratch(sc, 1, false, 0, &sd);
+            if (sd)
+                dyn.push_back(sd);
+            if (rc != CGE_OK)
+                break;
+            if (g < 2) {
+                // a dealt chunk starts when this rank's own rows have left their shadow stage (the chunk's chain stage then runs beside
+                // their shading and fold stages); frames of the single per-thread kernel: when that kernel has finished
+                dynStream[g] = sd->baseStream;
+                bool staged = true;
+                for (Scratch* b : bands)
+                    staged = staged && b->staged;
+                if (staged)
+                    for (Scratch* b : bands)
+                        cudaStreamWaitEvent(dynStream[g], b->stage[2], 0);
+                else
+                    cudaStreamWaitEvent(dynStream[g], s->copyDone, 0);
+            }
+            sd->stream = dynStream[g % 2];
+            if (!sd->grant)
+                rc = cudaMalloc(&sd->grant, 16) == cudaSuccess ? CGE_OK : fail(CGE_ERR_CUDA, "grant buffer");
+            if (rc != CGE_OK)
+                break;
+            grant_kernel<<<1, 1, 0, sd->stream>>>(counter, base, R, chunksPerOwner, chunkRows, poolPct, dp.n_tiles_x, dp.n_tiles_y, sd->grant);
+            launches++;
+            gp.grant = sd->grant;
+            rc = launch_render(sc, ls, sd, cam, &p, gp, frame, nullptr, &launches);
+        }
+        for (unsigned g = 0; g < 2 && g < dyn.size(); g++) {
+            cudaEventRecord(dyn[g]->bandDone, dynStream[g]); // (recorded after the last pipeline queued on that stream)
+            cudaStreamWaitEvent(s->stream, dyn[g]->bandDone, 0);
+        }
     }
     cudaEventRecord(s->ev1, s->stream);
     ncclResult_t nr = ncclSuccess;
@@ -2607,8 +2704,17 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
         rc = fail(CGE_ERR_CUDA, std::string("render_distributed: ") + cudaGetErrorString(e));
     for (unsigned b = 1; b < bands.size(); b++)
         cudaStreamSynchronize(bands[b]->stream);
-    if (rc == CGE_OK)
-        rc = fill_stats(bands, st, launches);
+    for (Scratch* sd : dyn) {
+        cudaStreamSynchronize(sd->stream);
+        sd->stream = sd->baseStream;
+    }
+    if (rc == CGE_OK) {
+        std::vector<Scratch*> all = bands;
+        all.insert(all.end(), dyn.begin(), dyn.end());
+        rc = fill_stats(all, st, launches);
+    }
+    for (Scratch* sd : dyn)
+        release_scratch(sc, sd);
     for (Scratch* b : bands)
         release_scratch(sc, b);
     return rc;

@@ -135,6 +135,10 @@ struct DevParams {
     // this launch renders entries [tile_first, tile_first + tile_count) of the partition's tile list (entry k = tile
     // part_index + k * part_count); the whole list unless the frame is rendered in bands (cge_api.cu cge_render)
     uint32_t tile_first, tile_count;
+    // dynamic tile dealing across GPUs (cge_render_distributed with CGE_FLAG_DYNAMIC_TILES): when set, the launch renders the chunk a
+    // grant kernel took from the frame's shared counter just before it - { tile_first, tile_count, part_index } in device memory
+    // (tile_count = 0: the pool was empty, the launch has nothing to do).  The fields above then only size the launch.
+    const uint32_t* grant;
     uint32_t n_tiles_x, n_tiles_y;
     uint32_t levels;          // ray_depth + 1 when recursive, else 1
     uint32_t units_per_lane;  // direct-lighting evaluations a pixel can need: levels (fold) or 2^levels - 1

@@ -214,12 +214,15 @@ __device__ __forceinline__ bool next_tile(const DevParams& p, unsigned* tileCoun
     if (lane == 0)
         k = atomicAdd(tileCounter, 1u);
     k = __shfl_sync(0xffffffffu, k, 0);
-    if (k >= p.tile_count)
+    unsigned first = p.tile_first, count = p.tile_count, part = p.part_index;
+    if (p.grant) // a chunk of some rank's tile list, dealt to this launch by the frame's shared counter (dev_scene.h)
+        first = __ldg(p.grant), count = __ldg(p.grant + 1), part = __ldg(p.grant + 2);
+    if (k >= count)
         return false;
     if (kOut)
         *kOut = k;
     // multi-GPU: the tile list is interleaved across ranks in units of part_unit tiles (dev_scene.h part_tile_of)
-    const unsigned tile = part_tile_of(p.part_unit, p.part_index, p.part_count, p.tile_first + k);
+    const unsigned tile = part_tile_of(p.part_unit, part, p.part_count, first + k);
     x = int(tile % p.n_tiles_x) * kTileW + int(lane % kTileW);
     y = int(tile / p.n_tiles_x) * kTileH + int(lane / kTileW);
     return true;

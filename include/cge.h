@@ -182,9 +182,13 @@ enum {
     CGE_FLAG_SHARED_HOST_FRAME = 1u << 5,   /* cge_render_distributed: rgb_out is the frame cge_comm_host_frame returned (the same
                                           on every rank); each rank copies the rows it rendered straight into it over its own
                                           PCIe link instead of rank 0 gathering the frame and copying all of it */
-    CGE_FLAG_PEER_FRAME = 1u << 6           /* cge_render_distributed: rgb_out is the pointer cge_comm_peer_frame returned on this rank
+    CGE_FLAG_PEER_FRAME = 1u << 6,          /* cge_render_distributed: rgb_out is the pointer cge_comm_peer_frame returned on this rank
                                           (rank 0's device frame, mapped into every rank): the kernels of every rank store their
                                           pixels straight into it over NVLink - no gather, no staging buffer, no unpack */
+    CGE_FLAG_DYNAMIC_TILES = 1u << 7        /* cge_render_distributed with CGE_FLAG_PEER_FRAME: part of every rank's tile rows forms a pool
+                                          of chunks dealt at run time - by an atomic counter beside rank 0's frame, over NVLink - to
+                                          whichever GPU has finished its own rows first (the reference deals its rows the same way:
+                                          src/render.cpp:277-280, schedule(guided)) */
 };
 /* Development switches (A/B measurements and the tests that prove both production pipelines bit-identical); not needed by a
  * caller, every setting renders the same frame. */

@@ -45,6 +45,13 @@ for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_s
         _, _, stp = comm.render(sc, cfg, peer_frame=pf)
         _, _, stp = comm.render(sc, cfg, peer_frame=pf)
         peer_rgb = pkg.device_view(pf, (H, W, 3)).cpu().numpy() if rank == 0 else None
+        # ... and with part of the tile rows dealt dynamically between the GPUs (a counter beside rank 0's frame)
+        if rank == 0:
+            pkg.device_view(pf, (H, W, 3)).fill_(-3.0)
+        dist.barrier()
+        _, _, std_ = comm.render(sc, cfg, peer_frame=pf, flags=pkg.FLAG_DYNAMIC_TILES)
+        _, _, std_ = comm.render(sc, cfg, peer_frame=pf, flags=pkg.FLAG_DYNAMIC_TILES)
+        dyn_rgb = pkg.device_view(pf, (H, W, 3)).cpu().numpy() if rank == 0 else None
         rgba = np.zeros((H, W, 4), np.uint8)
         import ctypes as C
         p8 = pkg.params_from_cfg(cfg, pkg.TRAVERSAL_FAST, False, (0, 1), pkg.FLAG_OUTPUT_RGBA8)
@@ -58,10 +65,13 @@ for spec in (sys.argv[1:] or ["c1_cornell", "c4_monkey_mirror:0.5", "c3_teapot_s
             same_shared = shared_rgb.tobytes() == rgb1.tobytes() and np.array_equal(shared_ids, ids1)
             same8 = rc8 == 0 and np.array_equal(rgba, rgba1)
             same_peer = peer_rgb.tobytes() == rgb1.tobytes()
-            ok &= same and same_shared and same8 and same_peer
+            same_dyn = dyn_rgb.tobytes() == rgb1.tobytes()
+            ok &= same and same_shared and same8 and same_peer and same_dyn
             print(json.dumps({"cfg": spec, "w": cfg["width"], "h": cfg["height"], "ranks": world, "bit_identical_to_1gpu": bool(same),
                               "shared_host_frame_identical": bool(same_shared), "rgba8_identical": bool(same8), "peer_frame_identical": bool(same_peer),
                               "peer_total_ms": round(stp["total_ms"], 3),
+                              "dynamic_tiles_identical": bool(same_dyn), "dynamic_total_ms": round(std_["total_ms"], 3),
+                              "dynamic_launches_rank0": std_["kernel_launches"],
                               "shared_total_ms": round(sts["total_ms"], 3),
                               "dist_total_ms": round(st["total_ms"], 3), "dist_kernel_ms_rank0": round(st["kernel_ms"], 3),
                               "single_kernel_ms": round(st1["kernel_ms"], 3), "launches_rank0": st["kernel_launches"]}), flush=True)

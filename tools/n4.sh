@@ -3,5 +3,5 @@ run() { echo "== $*"; env "$@" python -m torch.distributed.run --nnodes=1 --npro
 import json,sys
 d=json.loads(sys.stdin.readlines()[-1])
 r=d.get('roofline',{})
-print('ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), 'match', d.get('frame_matches_1gpu'), 'stages', {k:round(v,3) for k,v in r.get('stage_ms',{}).items()}, 'prepass', r.get('light_hull_prepass'), 'frac', r.get('frac'))"; }
+print('ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), 'match', d.get('frame_matches_1gpu'), 'stages', {k:round(v,3) for k,v in r.get('stage_ms',{}).items()}, 'prepass', r.get('light_hull_prepass'), 'frac', r.get('frac'), 'gather', d.get('nccl_gather',{}).get('ms_per_step'), 'dynamic', d.get('dynamic_tiles',{}).get('ms_per_step'))"; }
 for v in "$@"; do run $v; done
