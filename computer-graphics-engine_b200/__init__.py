@@ -505,6 +505,28 @@ def partition_tiles(width: int, height: int, part_index: int, part_count: int, t
     return [t for u in range(part_index, n_units, part_count) for t in range(u * unit, min((u + 1) * unit, n_tiles))]
 
 
+def dynamic_tile_plan(width: int, height: int, n_ranks: int, pool_pct: int = 25, chunks_per_owner: int = 2):
+    """Host-side statement of CGE_FLAG_DYNAMIC_TILES (csrc/cge_api.cu cge_render_distributed / grant_kernel): the first
+    pool_pct % of every rank's tile rows (entries of its tile-row partition list) form the pool, cut into chunks_per_owner
+    chunks per rank; chunk c belongs to rank c % n_ranks.  Returns (static tile lists per rank, the tile list of every
+    chunk in grant order); a chunk can be empty."""
+    tiles_x, tiles_y = (width + 7) // 8, (height + 3) // 4
+    rows = [(tiles_y - r + n_ranks - 1) // n_ranks if tiles_y > r else 0 for r in range(n_ranks)]
+    pool = [rw * pool_pct // 100 for rw in rows]
+    chunk_rows = max(1, -(-pool[0] // chunks_per_owner)) if pool else 1
+    lists = [partition_tiles(width, height, r, n_ranks, tile_rows=True) for r in range(n_ranks)]
+    if n_ranks == 1:
+        lists = [list(range(tiles_x * tiles_y))]
+    static = [lists[r][pool[r] * tiles_x:] for r in range(n_ranks)]
+    chunks = []
+    for c in range(n_ranks * chunks_per_owner):
+        owner, j = c % n_ranks, c // n_ranks
+        first = j * chunk_rows
+        count = min(chunk_rows, pool[owner] - first) if first < pool[owner] else 0
+        chunks.append(lists[owner][first * tiles_x:(first + count) * tiles_x])
+    return static, chunks
+
+
 def load_scene(cfg: dict) -> FlatScene:
     """Flat scene for a config: a committed .cges fixture, or the procedurally generated dragon stand-in."""
     if cfg["scene"].startswith("standin:"):

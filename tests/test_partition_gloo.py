@@ -36,6 +36,17 @@ for (w, h) in [(3840, 2160), (1024, 1024), (33, 17), (8, 4), (7, 3)]:
         ok &= allt == list(range(n_tiles))
         ok &= max(len(g) for g in gathered) - min(len(g) for g in gathered) <= unit
         ok &= all((t // unit) % world == r for r, g in enumerate(gathered) for t in g)
+    # dynamic dealing (CGE_FLAG_DYNAMIC_TILES): every rank derives the same plan; its static rows plus the pool's chunks cover every
+    # tile exactly once, chunk c lies in rank c % world's rows, and whoever takes the chunks - here: rank (c * 7) % world - the union holds
+    for pct, chunks in ((25, 2), (10, 1), (90, 8), (1, 3)):
+        static, pool = pkg.dynamic_tile_plan(w, h, world, pct, chunks)
+        taken = [t for c, ch in enumerate(pool) if (c * 7) % world == rank for t in ch]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, static[rank] + taken)
+        tiles_x = (w + 7) // 8
+        ok &= sorted(t for g in gathered for t in g) == list(range(tiles_x * ((h + 3) // 4)))
+        ok &= all((t // tiles_x) % world == c % world for c, ch in enumerate(pool) for t in ch)
+        ok &= len(pool) == world * chunks
 flag = torch.tensor([1 if ok else 0])
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
