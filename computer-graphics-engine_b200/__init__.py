@@ -433,6 +433,25 @@ class Comm:
         return rgb, ids, st.as_dict()
 
 
+def device_to_host(ptr: int, shape, dtype=np.float32) -> np.ndarray:
+    """Copy of device memory the library owns (e.g. rank 0's Comm.peer_frame) through the CUDA runtime (tests only; no torch)."""
+    out = np.empty(shape, dtype)
+    rt = None
+    for name in ("libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so.12", "libcudart.so"):
+        try:
+            rt = C.CDLL(name)
+            break
+        except OSError:
+            continue
+    if rt is None:
+        raise OSError("libcudart not found")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rc = rt.cudaMemcpy(out.ctypes.data, C.c_void_p(int(ptr)), out.nbytes, 2)  # cudaMemcpyDeviceToHost
+    if rc != 0:
+        raise RuntimeError(f"cudaMemcpy failed: {rc}")
+    return out
+
+
 def device_view(ptr: int, shape, typestr: str = "<f4"):
     """A torch tensor over device memory the library owns (e.g. rank 0's Comm.peer_frame), without a copy (tests / bench only)."""
     import torch

@@ -79,7 +79,7 @@ def test_distributed_entry_on_one_rank_equals_cge_render(cge, name, size):
             H, W = cfg["height"], cfg["width"]
             pf = comm.peer_frame(H * W * 12)
             comm.render(sc, cfg, peer_frame=pf)
-            assert cge.device_view(pf, (H, W, 3)).cpu().numpy().tobytes() == rgb.tobytes()
+            assert cge.device_to_host(pf, (H, W, 3)).tobytes() == rgb.tobytes()
             with pytest.raises(cge.CgeError) as e:  # a pointer the communicator did not hand out
                 comm.render(sc, cfg, peer_frame=pf + 256)
             assert e.value.code == cge.ERR_INVALID_ARG
