@@ -1,5 +1,5 @@
 N=${N:-4}
-run() { echo "== $*"; env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${STEPS:-8} --warmup 3 --no-cpu-baseline --no-configs 2>>gpurun_out/n$N.err | python -c "
+run() { echo "== $*"; env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${STEPS:-8} --warmup 3 --no-cpu-baseline --no-configs ${EXTRA:-} 2>>gpurun_out/n$N.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.readlines()[-1])
 r=d.get('roofline',{})
