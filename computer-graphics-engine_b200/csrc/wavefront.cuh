@@ -1,4 +1,4 @@
-// wavefront.cuh — the production pipeline of CGE_TRAVERSAL_FAST: three kernels over compact queues in HBM.
+// wavefront.cuh — the production pipeline of CGE_TRAVERSAL_FAST: kernels over compact queues in HBM.
 //
 // Why: in the one-thread-per-pixel kernel a pixel is 1 ray (a miss) or up to (levels + 16 * (2^levels - 1)) rays (a
 // mirror chain with soft shadows); measured on config C5 the slowest 8x4 tile costs 350x the median tile and the last
@@ -10,6 +10,9 @@
 //                    counted with __ballot_sync, ONE atomicAdd per warp reserves a contiguous run of queue slots, and
 //                    each lane writes its hit record (SoA, coalesced) at base + __popc(ballot & lanes_below).
 //                    Consecutive queue slots are therefore neighbouring pixels.
+//   wf_vis_cull_kernel / wf_vis_regroup_kernel   the shadow stage: every shadow ray of the frame as one visibility byte.  The
+//                    light-hull pre-pass settles, with ONE conservative walk per hit, the hits none of whose rays can be blocked
+//                    and compacts the others into per-level hard lists; the per-ray kernel traces those (both further down).
 //   wf_shade_kernel  one lane = one direct-lighting evaluation (pixel, level, reflection copy) = one
 //                    computeLightContribution call of the reference: all its shadow rays, in the reference's sample
 //                    order.  Work items are numbered copy-major inside a level, so a warp holds 32 neighbouring pixels

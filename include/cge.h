@@ -241,7 +241,10 @@ typedef struct cge_scene cge_scene; /* opaque: device-resident flattened scene +
 /* ---- development switches (environment variables read at call time; A/B measurements and tests only, not part of the ABI:
  *      every setting produces the same frame bit for bit) -----------------------------------------------------------------
  *   CGE_ZERO_SHADING_CULL=0   trace the shadow ray of light samples whose Phong term is exactly zero as well
- *   CGE_VIS_CULL=0            wavefront pipeline without the light-hull pre-pass (every shadow ray is traced)
+ *   CGE_VIS_CULL=0 | 1        wavefront pipeline without / with the light-hull pre-pass whatever the launch size (default: from
+ *                             1.5 Mpixel per launch); CGE_CULL_BUDGET=n: inner nodes one hull walk may visit (96)
+ *   CGE_CHAIN_SPLIT=0 | 1     chain stage as one kernel / as camera rays + continuation beside the level-0 shadow rays
+ *   CGE_DYNAMIC_POOL_PCT=n, CGE_DYNAMIC_CHUNKS=n   CGE_FLAG_DYNAMIC_TILES: share of every rank's tile rows in the pool (25), chunks per rank (2)
  *   CGE_BANDS=n               number of concurrent bands a frame / rank partition is rendered in (1 = one pipeline)
  *   CGE_REGROUP=0             shadow pass without the in-warp regrouping (wf_vis_grouped_kernel)
  *   CGE_SAH_BUILD=host        build the FAST traversal tree with the host builder instead of the GPU builder
