@@ -291,8 +291,16 @@ def main():
     # N > 1: the device frame lives on rank 0 and is mapped into every rank (cge_comm_peer_frame): the render kernels of every rank
     # store their pixels straight into it over NVLink; `nccl_gather` below times the NCCL send / recv delivery beside it
     frame_dev = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-    peer_ptr = comm.peer_frame(H * W * 12) if comm else None
-    peer_view = pkg.device_view(peer_ptr, (H, W, 3)) if comm and rank == 0 else None
+    peer_ptr = None
+    if comm:
+        try:  # collective: succeeds or fails on every rank together (no CUDA IPC / peer access between the GPUs: NCCL gather instead)
+            if os.environ.get("CGE_BENCH_NO_PEER"):  # (exercises the fallback)
+                raise pkg.CgeError(pkg.ERR_UNSUPPORTED, "disabled by CGE_BENCH_NO_PEER")
+            peer_ptr = comm.peer_frame(H * W * 12)
+        except pkg.CgeError as e:
+            if rank == 0:
+                print(f"[bench] peer frame unavailable ({e}): the frame is delivered by the NCCL gather", file=sys.stderr)
+    peer_view = pkg.device_view(peer_ptr, (H, W, 3)) if peer_ptr and rank == 0 else None
     pinned = pkg.PinnedBuffer((H, W, 3), np.float32) if world == 1 else None
     host_frame = comm.host_frame((H, W, 3), np.float32) if comm else pinned.array
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
@@ -311,6 +319,8 @@ def main():
         return st
 
     def step_device():
+        if comm and peer_ptr is None:
+            return step_gather()
         if comm:
             _, _, st = comm.render(scene, cfg, peer_frame=peer_ptr, camera=cam)
         else:
@@ -404,20 +414,22 @@ def main():
         gather_s, _, _, _ = timed(step_gather, 2, args.steps)  # the same frame delivered by ncclSend / ncclRecv + one unpack launch
         gather_ms = gather_s / args.steps * 1e3
         # ... and with a quarter of every rank's tile rows dealt at run time by a counter beside rank 0's frame (CGE_FLAG_DYNAMIC_TILES)
-        dyn_s, _, _, _ = timed(step_dynamic, 2, args.steps)
-        dynamic_ms = dyn_s / args.steps * 1e3
-        barrier()
-        dyn_dev = peer_view.cpu().numpy() if rank == 0 else None
-        step_device()
-        barrier()
-        peer_dev = peer_view.cpu().numpy() if rank == 0 else None
+        dyn_dev = peer_dev = None
+        if peer_ptr is not None:
+            dyn_s, _, _, _ = timed(step_dynamic, 2, args.steps)
+            dynamic_ms = dyn_s / args.steps * 1e3
+            barrier()
+            dyn_dev = peer_view.cpu().numpy() if rank == 0 else None
+            step_device()
+            barrier()
+            peer_dev = peer_view.cpu().numpy() if rank == 0 else None
         gathered_dev = frame_dev.cpu().numpy() if rank == 0 else None
         if rank == 0:
             one, _, _ = scene.render(cfg, want_ids=False, camera=cam)
-            frame_check = {"frame_matches_1gpu": bool(frame_hash(one) == frame_hash(peer_dev) == frame_hash(gathered_dev) == frame_hash(host_frame)
-                                                      == frame_hash(dyn_dev)),
-                           "sha256_16": {"one_gpu": frame_hash(one), "peer_device_frame": frame_hash(peer_dev),
-                                         "peer_device_frame_dynamic_tiles": frame_hash(dyn_dev),
+            frames = [one, gathered_dev, host_frame] + ([peer_dev, dyn_dev] if peer_ptr is not None else [])
+            frame_check = {"frame_matches_1gpu": bool(len({frame_hash(f) for f in frames}) == 1),
+                           "sha256_16": {"one_gpu": frame_hash(one), "peer_device_frame": frame_hash(peer_dev) if peer_dev is not None else None,
+                                         "peer_device_frame_dynamic_tiles": frame_hash(dyn_dev) if dyn_dev is not None else None,
                                          "gathered_device_frame": frame_hash(gathered_dev), "shared_host_frame": frame_hash(host_frame)}}
         dist.barrier()
 
@@ -588,7 +600,8 @@ def main():
     if frame_check:
         line.update(frame_check)
         line["delivery"] = ("every rank's render kernels store their pixels into rank 0's device frame over NVLink peer memory "
-                            "(cge_comm_peer_frame, CGE_FLAG_PEER_FRAME), a 4-byte all-reduce signals completion")
+                            "(cge_comm_peer_frame, CGE_FLAG_PEER_FRAME), a 4-byte all-reduce signals completion") if peer_ptr is not None else \
+            "ncclSend / ncclRecv of compact rows + one unpack launch on rank 0 (no peer access between the GPUs of this box)"
         line["dynamic_tiles"] = {"ms_per_step": dynamic_ms,
                                  "note": "the same frame with CGE_FLAG_DYNAMIC_TILES: the first quarter of every rank's tile rows is a pool of "
                                          "chunks dealt at run time by an atomic counter beside rank 0's frame (over NVLink) to whichever GPU "
