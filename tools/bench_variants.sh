@@ -1,3 +1,5 @@
+# development aid: bench.py on N GPUs under a list of environment variants, one summary line each.
+# usage: N=2 [STEPS=8] [EXTRA="--scale 0.5"] tools/bench_variants.sh X=0 CGE_BANDS=2 "CGE_VIS_CULL=0 CGE_BANDS=2"
 N=${N:-4}
 run() { echo "== $*"; env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${STEPS:-8} --warmup 3 --no-cpu-baseline --no-configs ${EXTRA:-} 2>>gpurun_out/n$N.err | python -c "
 import json,sys
