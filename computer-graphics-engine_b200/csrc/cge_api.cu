@@ -771,7 +771,9 @@ int launch_render(cge_scene* sc, const LightSet& ls, Scratch* s, const cge_camer
         // Measured on B200: a 1/8 share of C5 (one rank of eight) 2.59 -> 2.52 ms; the whole frame as one pipeline
         // 15.57 -> 15.67 ms and as four concurrent bands 15.33 -> 15.91 ms (bands already fill the tails, and the two shadow
         // launches each end in a tail of their own): on for launches below the band threshold only.
-        const bool split = visFits && !dp.aa_side && wp.levels > 1 && env_int("CGE_CHAIN_SPLIT", smallLaunch ? 1 : 0);
+        // (not when the pixels go to rank 0's frame over NVLink: on 8 GPUs the unsplit steps of the same run took 2.67 ms against
+        //  2.92 ms, on 2 GPUs at 1 Mpixel per rank 2.61 against 2.63 ms - DESIGN.md 6)
+        const bool split = visFits && !dp.aa_side && wp.levels > 1 && env_int("CGE_CHAIN_SPLIT", smallLaunch && !dp.chain_unsplit ? 1 : 0);
         auto launchVis = [&](cudaStream_t st, unsigned levelBegin, unsigned levelEnd, unsigned counterIdx) {
             if (wp.vis_cull) { // (chunk counters 22 / 23 beside the shadow-ray kernel's 18 / 19)
                 err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wf_vis_cull_kernel, 128, 0);
@@ -2523,6 +2525,7 @@ int cge_render_distributed(cge_scene* sc, cge_comm* comm, const cge_camera* cam,
     // ---- dynamic tile dealing: the first poolPct % of every rank's tile rows form a pool of chunks that is dealt by a counter in
     // rank 0's memory to whichever rank gets there first; each rank renders the rest of its rows (the static part) as before, then
     // K pipelines that each take one chunk (or nothing) ------------------------------------------------------------------------
+    dp.chain_unsplit = peer ? 1u : 0u;
     const bool dynamic = peer && (p.flags & CGE_FLAG_DYNAMIC_TILES) && !dp.aa_side;
     const unsigned poolPct = dynamic ? unsigned(std::min(std::max(env_int("CGE_DYNAMIC_POOL_PCT", 25), 1), 90)) : 0u;
     const unsigned chunksPerOwner = unsigned(std::min(std::max(env_int("CGE_DYNAMIC_CHUNKS", 2), 1), 8));

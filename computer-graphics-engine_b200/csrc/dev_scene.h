@@ -145,6 +145,7 @@ struct DevParams {
     uint32_t debug_cycles;    // CGE_DEV_FLAG_DEBUG_CYCLES
     uint32_t shade_mode;      // wavefront: 1 = wf_shade_kernel<false> traces the shadow rays itself, 2 = visibility bytes (wavefront.cuh)
     uint32_t aa_side;              // raysPerPixelSide when extra.enableMultipleRaysPerPixel is set, else 0
+    uint32_t chain_unsplit;        // host-side hint: keep the chain stage in one kernel (cge_render_distributed with the peer frame)
     uint32_t vis_cull;             // wavefront: the light-hull pre-pass ran, the shadow-ray kernel traces the hard lists (wavefront.cuh)
     uint32_t cull_budget;          // inner nodes one hull walk of the pre-pass may visit
     uint32_t packet_budget, packet_leaf_cost; // shadow_packet.cuh: node visits a hull walk may spend, and what a leaf counts for
