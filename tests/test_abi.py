@@ -34,6 +34,21 @@ def test_struct_sizes_match_header(cge):
     assert C.sizeof(cge.CgeSceneDesc) == 32 + 7 * 8 + 8 + 2 * 8
 
 
+def test_flag_constants_match_header(cge):
+    """The ctypes glue's flag values are the header's (include/cge.h is what a maintainer binds; the glue must not drift)."""
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "cge.h").read_text(), flags=re.S)
+    header = {name: 1 << int(shift) for name, shift in re.findall(r"\b(CGE_(?:DEV_)?FLAG_[A-Z0-9_]+)\s*=\s*1u\s*<<\s*(\d+)", text)}
+    assert len(header) >= 10
+    glue = {"CGE_FLAG_WANT_PRIM_IDS": 1, "CGE_FLAG_RGB_DEVICE_PTR": cge.FLAG_RGB_DEVICE_PTR, "CGE_FLAG_COUNT_TESTS": cge.FLAG_COUNT_TESTS,
+            "CGE_FLAG_OUTPUT_RGBA8": cge.FLAG_OUTPUT_RGBA8, "CGE_FLAG_PARTITION_TILE_ROWS": cge.FLAG_PARTITION_TILE_ROWS,
+            "CGE_FLAG_SHARED_HOST_FRAME": cge.FLAG_SHARED_HOST_FRAME, "CGE_FLAG_PEER_FRAME": cge.FLAG_PEER_FRAME,
+            "CGE_FLAG_DYNAMIC_TILES": cge.FLAG_DYNAMIC_TILES, "CGE_DEV_FLAG_PER_THREAD": cge.FLAG_PER_THREAD,
+            "CGE_DEV_FLAG_WAVEFRONT": cge.FLAG_WAVEFRONT, "CGE_DEV_FLAG_DEBUG_CYCLES": cge.FLAG_DEBUG_CYCLES}
+    for name, value in glue.items():
+        assert header[name] == value, name
+    assert len(set(header.values())) == len(header)  # no two flags share a bit
+
+
 def test_camera_matches_reference_trackball(cge, ref):
     for name in cge.configs.CONFIGS:
         cfg = cge.configs.get(name)
