@@ -17,8 +17,10 @@
 //     [features] enable_soft_shadow = false
 //     [render]   ray_depth = 5, segment_light_samples = 25, parallelogram_light_samples = 5, rays_per_pixel_side = 3,
 //                bloom_scalar = 0.3, bloom_threshold = 0.4, bloom_debug_option = 0, seed = 0, timestamp = true
-// The scene is a flat scene file (include/cge_scene_file.h) inside data_path: OBJ / MTL / PNG parsing is host I/O outside the
-// hot path.  Lights from the config replace the file's, as loadSceneFromFile does (src/scene.cpp:96-102).
+// The scene is what the reference's config names (src/config.cpp:216-235): a built-in scene (number or name: its OBJ / MTL / PNG
+// files are read from data_path by host/cge_scene_io.hpp, the loaders' bit-identical mirror) or an OBJ file in data_path - or a
+// flat scene file (include/cge_scene_file.h).  Lights from the config replace a file's, as loadSceneFromFile does
+// (src/scene.cpp:94-103); a built-in scene keeps its own.
 // Only a TOML subset is read: tables, arrays of tables, booleans, numbers, basic strings, (nested, multi-line) arrays.
 #include <cctype>
 #include <chrono>
@@ -34,6 +36,7 @@
 #include <vector>
 
 #include "cge_engine.hpp"
+#include "cge_scene_io.hpp"
 
 using namespace cge_engine;
 
@@ -285,7 +288,20 @@ int main(int argc, char** argv)
         if (const Value* ws = cfg.find("window_size"); ws && ws->kind == Value::Array && ws->arr.size() >= 2)
             windowSize = { int(ws->arr[0].num), int(ws->arr[1].num) };
         const std::string dataPath = getString(cfg, { "data_path" }, ".");
-        const std::string sceneName = getString(cfg, { "scene" }, "none");
+        // scene (src/config.cpp:216-235): a SceneType number, one of the built-in scenes' names, or a file in data_path - an OBJ
+        // file as in the reference, or a flat scene file (include/cge_scene_file.h)
+        std::string sceneName = getString(cfg, { "scene" }, "none");
+        std::optional<SceneType> sceneType;
+        if (const Value* sv = cfg.find("scene"); sv && sv->kind == Value::Number)
+            sceneType = SceneType(int(sv->num));
+        else
+            sceneType = deserializeSceneType(sceneName);
+        static const char* const kSceneNames[] = { "single_triangle", "cube", "cube_textured", "cornell_box", "cornell_box_parallelogram_light",
+            "monkey", "teapot", "dragon", "spheres", "custom" };
+        if (sceneType && (int(*sceneType) < 0 || int(*sceneType) > int(Custom)))
+            throw std::runtime_error("scene number out of range");
+        if (sceneType)
+            sceneName = kSceneNames[int(*sceneType)]; // (serialize(), src/config.cpp:376-402: names the output bitmaps)
         const std::string outputDir = getString(cfg, { "output_dir" }, ".");
         Features features;
         features.enableShading = getBool(cfg, { "features", "enable_shading" }, false);
@@ -327,8 +343,8 @@ int main(int argc, char** argv)
         const bool timestamp = getBool(cfg, { "render", "timestamp" }, true);
 
         if (printOnly) {
-            std::printf("window_size %d %d\nscene %s\ndata_path %s\noutput_dir %s\n", windowSize.x, windowSize.y, sceneName.c_str(),
-                dataPath.c_str(), outputDir.c_str());
+            std::printf("window_size %d %d\nscene %s%s\ndata_path %s\noutput_dir %s\n", windowSize.x, windowSize.y, sceneName.c_str(),
+                sceneType ? " (built-in)" : "", dataPath.c_str(), outputDir.c_str());
             std::printf("features shading %d recursive %d hard_shadow %d soft_shadow %d normal_interp %d texture_mapping %d accel_structure %d\n",
                 features.enableShading, features.enableRecursive, features.enableHardShadow, features.enableSoftShadow,
                 features.enableNormalInterp, features.enableTextureMapping, features.enableAccelStructure);
@@ -346,27 +362,41 @@ int main(int argc, char** argv)
         }
 
         // ---- src/main.cpp:478-535 -----------------------------------------------------------------------------------------
-        Scene scene = loadFlatScene(joinPath(dataPath, sceneName));
+        // lights of the config (src/config.cpp:336-372); they replace a scene FILE's lights (loadSceneFromFile, src/scene.cpp:94-103), a
+        // built-in scene keeps its own (src/main.cpp:491-500)
+        std::vector<std::variant<PointLight, SegmentLight, ParallelogramLight>> cfgLights;
+        bool haveCfgLights = false;
         if (const Value* lights = cfg.find("lights"); lights && lights->kind == Value::Array) {
-            scene.lights.clear();
+            haveCfgLights = true;
             for (const Value& l : lights->arr) {
                 const std::string type = getString(l, { "type" }, "none");
                 const vec3 zero(0.0f);
                 if (type == "point") {
-                    scene.lights.emplace_back(PointLight { toVec3(l.find("position"), zero), toVec3(l.find("color"), zero) });
+                    cfgLights.emplace_back(PointLight { toVec3(l.find("position"), zero), toVec3(l.find("color"), zero) });
                 } else if (type == "segment") {
-                    scene.lights.emplace_back(SegmentLight { vec3At(l, "endpoints", 0, zero), vec3At(l, "endpoints", 1, zero),
+                    cfgLights.emplace_back(SegmentLight { vec3At(l, "endpoints", 0, zero), vec3At(l, "endpoints", 1, zero),
                         vec3At(l, "colors", 0, zero), vec3At(l, "colors", 1, zero) });
                 } else if (type == "parallelogram") {
-                    scene.lights.emplace_back(ParallelogramLight { toVec3(l.find("corner"), zero), vec3At(l, "edges", 0, zero),
+                    cfgLights.emplace_back(ParallelogramLight { toVec3(l.find("corner"), zero), vec3At(l, "edges", 0, zero),
                         vec3At(l, "edges", 1, zero), vec3At(l, "colors", 0, zero), vec3At(l, "colors", 1, zero), vec3At(l, "colors", 2, zero),
                         vec3At(l, "colors", 3, zero) });
                 } else {
                     std::fprintf(stderr, "Unknown light type: %s -- Skip\n", type.c_str());
                 }
             }
+        }
+        Scene scene;
+        const bool isObj = sceneName.size() > 4 && sceneName.compare(sceneName.size() - 4, 4, ".obj") == 0;
+        if (sceneType) {
+            scene = loadScenePrebuilt(*sceneType, dataPath);
+        } else if (isObj) {
+            scene = loadSceneFromFile(joinPath(dataPath, sceneName), cfgLights);
         } else {
-            std::fprintf(stderr, "WARN: No lights found in config file, keeping the scene file's.\n");
+            scene = loadFlatScene(joinPath(dataPath, sceneName));
+            if (haveCfgLights)
+                scene.lights = cfgLights;
+            else
+                std::fprintf(stderr, "WARN: No lights found in config file, keeping the scene file's.\n");
         }
         std::string stem = sceneName.substr(sceneName.find_last_of('/') + 1);
         stem = stem.substr(0, stem.find_last_of('.'));

@@ -138,3 +138,56 @@ field_of_view = 50.0
     assert r.returncode == 1 and "does not exist" in r.stderr
     r = run_cli(base + "window_size = [1, 2\n", tmp_path)
     assert r.returncode == 1 and "config line" in r.stderr
+
+
+def test_cli_renders_an_obj_scene(cge, ref, tmp_path):
+    """The scene named by the config is an OBJ file in data_path, as in the reference (src/config.cpp:216-235, src/main.cpp:491-500):
+    host/cge_scene_io.hpp loads OBJ + MTL (quads, several materials, shared vertices), the config's lights are the scene's lights.
+    The bitmap must equal the one rendered from the same scene exported as a flat scene file by tests/cpp/scene_export."""
+    data = tmp_path / "data"
+    data.mkdir()
+    (data / "room.mtl").write_text("newmtl floor\nKd 0.7 0.7 0.6\nKs 0.2 0.2 0.2\nNs 30\nnewmtl block\nKd 0.2 0.4 0.9\nNs 5\n")
+    (data / "room.obj").write_text(
+        "mtllib room.mtl\n"
+        "v -2 0 -2\nv 2 0 -2\nv 2 0 2\nv -2 0 2\n"
+        "v -0.5 0 -0.5\nv 0.5 0 -0.5\nv 0.5 0 0.5\nv -0.5 0 0.5\nv -0.5 1 -0.5\nv 0.5 1 -0.5\nv 0.5 1 0.5\nv -0.5 1 0.5\n"
+        "o floor\nusemtl floor\nf 4 3 2 1\n"
+        "o block\nusemtl block\nf 9 10 6 5\nf 10 11 7 6\nf 11 12 8 7\nf 12 9 5 8\nf 12 11 10 9\n")
+    out = tmp_path / "out"
+    r = run_cli(f"""
+window_size = [240, 160]
+data_path = "{data}"
+scene = "room.obj"
+output_dir = "{out}"
+[features]
+enable_shading = true
+enable_hard_shadow = true
+enable_recursive = true
+enable_accel_structure = true
+[render]
+ray_depth = 2
+timestamp = false
+[[cameras]]
+field_of_view = 50.0
+distance_from_look_at = 5.0
+look_at = [0.0, 0.4, 0.0]
+rotation = [30.0, 35.0, 0.0]
+[[lights]]
+type = "point"
+position = [1.5, 3.0, -2.0]
+color = [1.0, 0.95, 0.9]
+""", tmp_path)
+    assert r.returncode == 0, r.stderr
+    flat_path = tmp_path / "room.cges"
+    subprocess.run([str(ROOT / "tests" / "cpp" / "scene_export"), "obj", str(data / "room.obj"), "0", str(flat_path)], check=True)
+    flat = cge.scenefile.load(flat_path)
+    assert len(flat.meshes) == 2 and flat.n_triangles == 12 and len(flat.vertices) == 4 + 5 * 4
+    flat.set_lights([(0, [1.5, 3.0, -2.0, 1.0, 0.95, 0.9])])
+    cfg = dict(cge.configs.get("c1_cornell", 240, 160), ray_depth=2,
+               camera={"fov_deg": 50.0, "dist": 5.0, "look_at": [0.0, 0.4, 0.0], "rotation_deg": [30.0, 35.0, 0.0]})
+    with cge.Scene(flat) as sc:
+        rgb, ids, _ = sc.render(cfg)
+    assert (ids >= 0).mean() > 0.3
+    want = tmp_path / "want.bmp"
+    ref.write_bmp(rgb, want)
+    assert (out / "room_cam_0.bmp").read_bytes() == want.read_bytes()
