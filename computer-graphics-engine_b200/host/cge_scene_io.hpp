@@ -175,7 +175,8 @@ inline void loadMtl(const std::string& path, std::map<std::string, int>& byName,
         return; // (the OBJ loader only warns about a missing material library: the faces keep material id -1)
     ObjMaterial cur;
     std::string name;
-    bool haveD = false;
+    bool haveD = false;  // reset by every newmtl
+    bool haveKd = false; // NOT reset by newmtl (the library the reference uses keeps it for the whole file)
     auto flush = [&]() {
         if (!name.empty()) {
             byName.insert({ name, int(out.size()) }); // the first material of a name wins
@@ -203,6 +204,7 @@ inline void loadMtl(const std::string& path, std::map<std::string, int>& byName,
             c.p = t + 2;
             for (float& f : cur.diffuse)
                 f = c.real();
+            haveKd = true;
         } else if (is("Ks")) {
             c.p = t + 2;
             for (float& f : cur.specular)
@@ -224,6 +226,8 @@ inline void loadMtl(const std::string& path, std::map<std::string, int>& byName,
             if (*c.p == '-')
                 throw std::runtime_error("map_Kd texture options are not supported: " + path);
             cur.diffuseTexname = c.word();
+            if (!haveKd) // a diffuse texture without any Kd so far: the loader's default grey
+                cur.diffuse[0] = cur.diffuse[1] = cur.diffuse[2] = float(0.6);
         }
     }
     flush();

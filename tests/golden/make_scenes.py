@@ -41,6 +41,12 @@ def main():
         print(f"{name}: meshes={len(s.meshes)} verts={len(s.vertices)} tris={len(s.triangles)} "
               f"spheres={len(s.spheres)} lights={len(s.lights)} textures={len(s.textures)}")
 
+    # --- fixtures of tests/test_scene_io.py only (the mirrored loaders): the textured quad of the Custom scene (a material without Kd)
+    #     and a quad mesh through loadMesh(file, centerAndNormalize = true) ------------------------------------------------------------
+    (OUT.parent / "loader").mkdir(exist_ok=True)
+    refharness.export_prebuilt(CUSTOM, data_dir, OUT.parent / "loader" / "custom.cges")
+    refharness.export_obj(DATA / "monkey-rotated-quad.obj", True, OUT.parent / "loader" / "monkey_quad.cges")
+
     # --- C3: teapot + one parallelogram light (area light above / in front of the pot) ---------------
     s = pkg.load(OUT / "teapot.cges")
     s.set_lights([pkg.parallelogram_light(

@@ -25,17 +25,26 @@ def tool():
 # SceneType (reference src/scene.h:15-26) -> fixture exported by the reference's own loadScenePrebuilt
 PREBUILT = [(0, "single_triangle", "triangle"), (1, "cube", "cube"), (2, "cube-textured", "cube_textured"), (3, "CornellBox", "cornell"),
             (4, "cornell_box_parallelogram_light", "cornell_parallelogram"), (5, "Monkey", "monkey"), (6, "teapot", "teapot"),
-            (8, "spheres", "spheres")]
+            (8, "spheres", "spheres"), (9, "custom", "custom")]  # custom: a textured quad whose material has no Kd (loader default 0.6)
 
 
 @pytest.mark.parametrize("number,name,fixture", PREBUILT)
 def test_prebuilt_scene_equals_the_reference_loaders_output(tool, tmp_path, number, name, fixture):
-    want = (ROOT / "tests" / "golden" / "scenes" / f"{fixture}.cges").read_bytes()
+    folder = "loader" if fixture == "custom" else "scenes"  # (fixtures only this test uses live beside the renderer's scenes)
+    want = (ROOT / "tests" / "golden" / folder / f"{fixture}.cges").read_bytes()
     for what in (str(number), name):  # by SceneType number and by the names src/config.cpp:404-431 accepts
         out = tmp_path / f"{fixture}_{what}.cges"
         r = subprocess.run([str(tool), "prebuilt", what, str(DATA), str(out)], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert out.read_bytes() == want, f"{fixture} via {what}"
+
+
+def test_quad_mesh_equals_the_reference_loaders_output(tool, tmp_path):
+    """monkey-rotated-quad.obj: 468 quads + 32 triangles, centred and normalised (fixture: the reference's loadMesh(file, true))."""
+    out = tmp_path / "mq.cges"
+    r = subprocess.run([str(tool), "obj", str(DATA / "monkey-rotated-quad.obj"), "1", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == (ROOT / "tests" / "golden" / "loader" / "monkey_quad.cges").read_bytes()
 
 
 def test_loader_details(tool, tmp_path):
