@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <ctime>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -42,7 +43,10 @@ using namespace cge_engine;
 
 namespace {
 
-// ---- TOML subset ----------------------------------------------------------------------------------------------------------
+// ---- TOML ------------------------------------------------------------------------------------------------------------------
+// Tables, dotted keys, arrays of tables, inline tables, arrays over several lines, basic / literal / multi-line strings, booleans,
+// integers (decimal, hex, octal, binary, underscores) and floats (exponents, inf, nan), comments.  Not read: dates and times (no
+// key of the reference's config is one).
 struct Value {
     enum Kind { None, Bool, Number, String, Array, Table } kind = None;
     bool b = false;
@@ -134,28 +138,102 @@ struct Parser {
                 } else
                     fail("expected ',' or ']' in array");
             }
-        } else if (t[i] == '"') {
-            v.kind = Value::String;
-            for (i++; i < t.size() && t[i] != '"'; i++) {
-                if (t[i] == '\\' && i + 1 < t.size())
-                    i++;
-                v.str += t[i];
-            }
-            if (i >= t.size())
-                fail("unterminated string");
+        } else if (t[i] == '{') { // inline table: { key = value, dotted.key = value }
+            v.kind = Value::Table;
             i++;
+            for (;;) {
+                skipSpace(false);
+                if (i < t.size() && t[i] == '}') {
+                    i++;
+                    break;
+                }
+                const std::vector<std::string> path = dottedKey();
+                skipSpace(false);
+                if (i >= t.size() || t[i] != '=')
+                    fail("expected '=' in inline table");
+                i++;
+                Value& owner = descend(v, path, path.size() - 1);
+                owner.tab[path.back()] = value();
+                skipSpace(false);
+                if (i < t.size() && t[i] == ',')
+                    i++;
+                else if (i < t.size() && t[i] == '}') {
+                    i++;
+                    break;
+                } else
+                    fail("expected ',' or '}' in inline table");
+            }
+        } else if (t[i] == '"' || t[i] == '\'') {
+            // basic ("...", escapes) and literal ('...', verbatim) strings, single-line or multi-line (three quotes: a newline right
+            // after the opening quotes is dropped, a backslash at the end of a line of a basic string joins the lines)
+            v.kind = Value::String;
+            const char q = t[i];
+            const bool multi = t.compare(i, 3, std::string(3, q)) == 0;
+            i += multi ? 3 : 1;
+            if (multi && i < t.size() && t[i] == '\n')
+                line++, i++;
+            for (;;) {
+                if (i >= t.size() || (!multi && t[i] == '\n'))
+                    fail("unterminated string");
+                if (multi ? t.compare(i, 3, std::string(3, q)) == 0 : t[i] == q) {
+                    i += multi ? 3 : 1;
+                    break;
+                }
+                if (q == '"' && t[i] == '\\' && i + 1 < t.size()) {
+                    const char e = t[++i];
+                    i++;
+                    if (e == 'n')
+                        v.str += '\n';
+                    else if (e == 't')
+                        v.str += '\t';
+                    else if (e == 'r')
+                        v.str += '\r';
+                    else if (e == '\n') { // line-ending backslash: skip the newline and the next line's indentation
+                        line++;
+                        while (i < t.size() && std::isspace(static_cast<unsigned char>(t[i]))) {
+                            if (t[i] == '\n')
+                                line++;
+                            i++;
+                        }
+                    } else
+                        v.str += e; // \" \\ and anything else: the character itself
+                    continue;
+                }
+                if (t[i] == '\n')
+                    line++;
+                v.str += t[i++];
+            }
         } else if (t.compare(i, 4, "true") == 0) {
             v.kind = Value::Bool, v.b = true, i += 4;
         } else if (t.compare(i, 5, "false") == 0) {
             v.kind = Value::Bool, v.b = false, i += 5;
         } else {
-            const char* begin = t.c_str() + i;
-            char* end = nullptr;
-            v.num = std::strtod(begin, &end);
-            if (end == begin)
-                fail("unsupported value");
+            // integers and floats: optional sign, 0x / 0o / 0b prefixes, underscores between digits, exponents, inf, nan
+            std::string tok;
+            size_t j = i;
+            while (j < t.size() && (std::isalnum(static_cast<unsigned char>(t[j])) || t[j] == '+' || t[j] == '-' || t[j] == '.' || t[j] == '_'))
+                if (t[j++] != '_')
+                    tok += t[j - 1];
+            const size_t signLen = !tok.empty() && (tok[0] == '+' || tok[0] == '-') ? 1 : 0;
+            const std::string body = tok.substr(signLen);
+            const double sign = signLen && tok[0] == '-' ? -1.0 : 1.0;
+            if (body == "inf") {
+                v.num = sign * std::numeric_limits<double>::infinity();
+            } else if (body == "nan") {
+                v.num = std::numeric_limits<double>::quiet_NaN();
+            } else if (body.size() > 2 && body[0] == '0' && (body[1] == 'x' || body[1] == 'o' || body[1] == 'b')) {
+                char* end = nullptr;
+                v.num = sign * double(std::strtoull(body.c_str() + 2, &end, body[1] == 'x' ? 16 : body[1] == 'o' ? 8 : 2));
+                if (*end)
+                    fail("unsupported value");
+            } else {
+                char* end = nullptr;
+                v.num = std::strtod(tok.c_str(), &end);
+                if (tok.empty() || *end)
+                    fail("unsupported value");
+            }
             v.kind = Value::Number;
-            i += size_t(end - begin);
+            i = j;
         }
         return v;
     }

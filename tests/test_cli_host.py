@@ -91,3 +91,40 @@ color = [1, 1, 1]
     assert out[7] == "camera fov 45.5 dist 3 look_at 0 0.5 -1 rotation 20 20 0"  # defaults of src/config.cpp:325-330
     assert out[8] == "camera fov 50 dist 2.25 look_at 0 0 0 rotation 10 -20 0"
     assert out[9:] == ["light parallelogram", "light point"]
+
+
+def test_cli_reads_the_other_toml_spellings(tmp_path):
+    """The same config written the other way TOML allows: inline tables, dotted keys, literal and multi-line strings, integers with
+    underscores / in hex / in binary, floats with exponents and signs, arrays over several lines with a trailing comma."""
+    subprocess.run(["bash", str(ROOT / "tests" / "cpp" / "build.sh")], check=True)
+    cfg = tmp_path / "c.toml"
+    cfg.write_text("""window_size = [ 1_280, 0x2D0 ]
+data_path = 'some\\\\where'   # literal string: the backslashes stay
+scene = \"\"\"
+teapot.cges\"\"\"
+features.enable_shading = true
+features.extra = { enable_bloom_effect = true }
+cameras = [
+  { field_of_view = 4.55e1, look_at = [0.0, 0.5, -1], rotation = [1e1, -2_0.0, +0.0] },
+  { distance_from_look_at = 2.25 },
+]
+lights = [ { type = "point", position = [0, 1, 0], color = [1, 1, 1] },
+           { type = "segment", endpoints = [[0, 1, 0], [1, 1, 0]], colors = [[1, 0, 0], [0, 1, 0]] } ]
+[render]
+seed = 0b1001101
+bloom_threshold = 2.5e-1
+""")
+    r = subprocess.run([str(ROOT / "tests" / "cpp" / "cge_cli"), str(cfg), "--print-config"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.splitlines()
+    assert out[0] == "window_size 1280 720" and out[1] == "scene teapot.cges" and out[2] == "data_path some\\\\where"
+    assert out[4] == "features shading 1 recursive 0 hard_shadow 0 soft_shadow 0 normal_interp 0 texture_mapping 0 accel_structure 0"
+    assert out[5] == "extra bits 0x8"
+    assert out[6].endswith("bloom 0.3 0.25 0 seed 77")
+    assert out[7] == "camera fov 45.5 dist 3 look_at 0 0.5 -1 rotation 10 -20 0"
+    assert out[8] == "camera fov 50 dist 2.25 look_at 0 0 0 rotation 20 20 0"
+    assert out[9:] == ["light point", "light segment"]
+    for bad in ("a = { b = 1", "a = 'unterminated", "a = 1__", "a = 0xZZ"):
+        cfg.write_text(bad + "\\n")
+        r = subprocess.run([str(ROOT / "tests" / "cpp" / "cge_cli"), str(cfg), "--print-config"], capture_output=True, text=True)
+        assert r.returncode == 1 and "config line" in r.stderr, bad
