@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "cge_bvh_build_reference_order", "cge_bvh_validate", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
-    "cge_comm_destroy", "cge_comm_host_frame", "cge_comm_peer_frame", "cge_render_distributed", "cge_host_alloc", "cge_host_free",
+    "cge_comm_destroy", "cge_comm_host_frame", "cge_comm_peer_frame", "cge_render_distributed", "cge_hull_clear_host", "cge_host_alloc", "cge_host_free",
 ]
 
 _lib = None
@@ -431,6 +431,16 @@ class Comm:
                 ids = ids_out if ids_out is not None else np.full((H, W), -1, np.int32)
         _check(lib().cge_render_distributed(scene.handle, self.handle, C.byref(cam), C.byref(p), _p(rgb), _p(ids), C.byref(st)))
         return rgb, ids, st.as_dict()
+
+
+def hull_clear_host(o3, light9, tri9) -> np.ndarray:
+    """cge_hull_clear_host: the light-hull pre-pass's "no ray of the hull can hit this triangle" test, on the host (tests)."""
+    o3, light9, tri9 = (np.ascontiguousarray(a, np.float32) for a in (o3, light9, tri9))
+    out = np.zeros(len(o3), np.int32)
+    l = lib()
+    l.cge_hull_clear_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    _check(l.cge_hull_clear_host(o3.ctypes.data, light9.ctypes.data, tri9.ctypes.data, len(o3), out.ctypes.data))
+    return out
 
 
 def device_to_host(ptr: int, shape, dtype=np.float32) -> np.ndarray:

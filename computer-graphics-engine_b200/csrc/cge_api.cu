@@ -1721,6 +1721,36 @@ int cge_bloom_weights(float sigma, float* out9)
     return CGE_OK;
 }
 
+// The light-hull pre-pass's triangle test on the host (the same function the kernel calls, wavefront.cuh cull_triangle_clear, with the
+// kernel's set-up for ONE parallelogram light): per case a hit point o, a light (v0, edge01, edge02) and a triangle.  clear_out = 1
+// means "no ray from o to any point of the light can be accepted by this triangle"; the CPU tests check that against the
+// reference's own intersection routine on sampled rays (tests/test_hull_clear.py).  No GPU involved.
+int cge_hull_clear_host(const float* o3, const float* light9, const float* tri9, uint32_t n, int32_t* clearOut)
+{
+    if (!o3 || !light9 || !tri9 || !clearOut)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    for (uint32_t i = 0; i < n; i++) {
+        const float *po = o3 + 3 * size_t(i), *pl = light9 + 9 * size_t(i), *pt = tri9 + 9 * size_t(i);
+        const vec3 o = v3(po[0], po[1], po[2]);
+        const vec3 v0 = v3(pl[0], pl[1], pl[2]), e01 = v3(pl[3], pl[4], pl[5]), e02 = v3(pl[6], pl[7], pl[8]);
+        const vec3 c[4] = { v0, v0 + e01, (v0 + e01) + e02, v0 + e02 }; // light_corners (wavefront.cuh), evaluated like sample_light
+        vec3 a[4];
+        HullDirs dirs = hull_dirs_empty();
+        float lightMag = 0.0f;
+        for (int j = 0; j < 4; j++) {
+            a[j] = c[j] - o;
+            hull_dirs_add(dirs, a[j]);
+            lightMag = fmaxf(lightMag, max_abs3(c[j]));
+        }
+        const vec3 t0 = v3(pt[0], pt[1], pt[2]), t1 = v3(pt[3], pt[4], pt[5]), t2 = v3(pt[6], pt[7], pt[8]);
+        const TriPre t = triangle_precompute(t0, t1, t2);
+        const float4 rows[kTriRows] = { f4(t.n.x, t.n.y, t.n.z, t.D), f4(t0.x, t0.y, t0.z, t.e0.x), f4(t.e0.y, t.e0.z, t1.x, t1.y),
+            f4(t1.z, t.e1.x, t.e1.y, t.e1.z), f4(t2.x, t2.y, t2.z, t.e2.x), f4(t.e2.y, t.e2.z, 0.0f, 0.0f) };
+        clearOut[i] = cull_triangle_clear(rows, o, dirs.dmin, dirs.dmax, hull_dirs_length(dirs), true, a, max_abs3(o) + lightMag) ? 1 : 0;
+    }
+    return CGE_OK;
+}
+
 // The FAST traversal tree alone, by either builder (parity test of the GPU builder against the host builder).
 int cge_fast_bvh_build(const cge_scene_desc* d, int onGpu, int device, cge_fast_node* nodesOut, uint32_t* nNodesInOut, uint32_t* orderOut,
     uint32_t* rootOut, uint32_t* depthOut, uint32_t* nLeavesOut, float* buildMsOut)

@@ -513,13 +513,44 @@ __device__ __forceinline__ unsigned light_corners(const float* __restrict__ L, c
     return 4;
 }
 
+// a row of a triangle record: read-only cache path on the device, a plain load in the host-side test entry (cge_hull_clear_host)
+CGE_HD float4 hull_row(const float4* p)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// per-axis bounds of the hull's ray directions (corner - o over all corners of all lights) and what the clear test derives from them
+struct HullDirs {
+    vec3 dmin, dmax;
+};
+CGE_HD HullDirs hull_dirs_empty()
+{
+    const float inf = __builtin_huge_valf();
+    return HullDirs { v3(inf), v3(-inf) };
+}
+CGE_HD void hull_dirs_add(HullDirs& h, const vec3 d)
+{
+    h.dmin = v3(fminf(h.dmin.x, d.x), fminf(h.dmin.y, d.y), fminf(h.dmin.z, d.z));
+    h.dmax = v3(fmaxf(h.dmax.x, d.x), fmaxf(h.dmax.y, d.y), fmaxf(h.dmax.z, d.z));
+}
+// an upper bound of |d| over the hull
+CGE_HD float hull_dirs_length(const HullDirs& h)
+{
+    const float mx = fmaxf(fabsf(h.dmin.x), fabsf(h.dmax.x)), my = fmaxf(fabsf(h.dmin.y), fabsf(h.dmax.y)), mz = fmaxf(fabsf(h.dmin.z), fabsf(h.dmax.z));
+    return fsqrt(mx * mx + my * my + mz * mz) * 1.0001f;
+}
+CGE_HD float max_abs3(const vec3 v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fabsf(v.z)); }
+
 // Can NO ray o + t * d, t in [0, 1], d inside the hull, be accepted by triangle tr?  (true = certainly not)
 //   a[4] = light corners - o (pyramid edges; used when `pyramid`), dmin / dmax = their per-axis bounds, dLen >= |d| of every ray,
 //   mag = coordinate magnitude of the configuration (sets the absolute rounding scale)
-__device__ __forceinline__ bool cull_triangle_clear(const float4* __restrict__ tr, const vec3 o, const vec3 dmin, const vec3 dmax, float dLen,
+CGE_HD bool cull_triangle_clear(const float4* __restrict__ tr, const vec3 o, const vec3 dmin, const vec3 dmax, float dLen,
     bool pyramid, const vec3* a, float mag)
 {
-    const float4 r0 = ldg4(tr);
+    const float4 r0 = hull_row(tr);
     const vec3 n = v3(r0.x, r0.y, r0.z);
     const float num = fsub(r0.w, dot(o, n)); // I2's numerator, the archive's own operations: its sign is the archive's sign
     // range of the denominators dot(d, n) over the hull, widened by the rounding of a three-term product sum
@@ -542,10 +573,12 @@ __device__ __forceinline__ bool cull_triangle_clear(const float4* __restrict__ t
     if (!(cosMin > 1e-3f))
         return false;
     const float margin = mag * 4e-6f / fminf(cosMin, 1.0f);
-    const float4 r1 = ldg4(tr + 1), r2 = ldg4(tr + 2), r3 = ldg4(tr + 3), r4 = ldg4(tr + 4);
+    const float4 r1 = hull_row(tr + 1), r2 = hull_row(tr + 2), r3 = hull_row(tr + 3), r4 = hull_row(tr + 4);
     const vec3 w0 = v3(r1.x, r1.y, r1.z) - o, w1 = v3(r2.z, r2.w, r3.x) - o, w2 = v3(r4.x, r4.y, r4.z) - o;
     const vec3 m = (a[0] + a[1]) + (a[2] + a[3]); // a direction inside the pyramid
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int i = 0; i < 4; i++) {
         vec3 pn = cross(a[i], a[(i + 1) & 3]);
         const float inside = dot(pn, m), len = fsqrt(dot(pn, pn));
@@ -583,7 +616,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
         vec3 c[4];
         const unsigned nc = light_corners(s.lights + size_t(li) * kLightFloats, p, c);
         for (unsigned j = 0; j < nc; j++)
-            lightMag = fmaxf(lightMag, fmaxf(fmaxf(fabsf(c[j].x), fabsf(c[j].y)), fabsf(c[j].z)));
+            lightMag = fmaxf(lightMag, max_abs3(c[j]));
     }
     constexpr unsigned kDone = 0x7fffffffu;
     constexpr float kInf = __builtin_huge_valf();
@@ -607,7 +640,7 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
             const vec3 o = v3(b[0], b[wb.cap], b[2 * size_t(wb.cap)]);
             // the hull: per-axis bounds of (corner - o) over all lights; for the single parallelogram also the four edges
             vec3 a[4];
-            vec3 dmin = v3(kInf), dmax = v3(-kInf);
+            HullDirs dirs = hull_dirs_empty();
             unsigned corners = 0;
             for (unsigned li = 0; li < s.n_lights; li++) {
                 vec3 c[4];
@@ -616,11 +649,11 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
                     const vec3 d = c[j] - o;
                     if (pyramid)
                         a[j] = d;
-                    dmin = v3(fminf(dmin.x, d.x), fminf(dmin.y, d.y), fminf(dmin.z, d.z));
-                    dmax = v3(fmaxf(dmax.x, d.x), fmaxf(dmax.y, d.y), fmaxf(dmax.z, d.z));
+                    hull_dirs_add(dirs, d);
                 }
                 corners += nc;
             }
+            const vec3 dmin = dirs.dmin, dmax = dirs.dmax;
             const bool finite = fabsf(dmin.x) <= 3e38f && fabsf(dmin.y) <= 3e38f && fabsf(dmin.z) <= 3e38f && fabsf(dmax.x) <= 3e38f
                 && fabsf(dmax.y) <= 3e38f && fabsf(dmax.z) <= 3e38f;
             if (corners == 0 || s.n_ftris == 0) {
@@ -630,9 +663,8 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
             } else {
                 const HullAxis hx = hull_axis(o.x, dmin.x, dmax.x), hy = hull_axis(o.y, dmin.y, dmax.y), hz = hull_axis(o.z, dmin.z, dmax.z);
                 const bool anyMixed = hx.mixed || hy.mixed || hz.mixed;
-                const float mx = fmaxf(fabsf(dmin.x), fabsf(dmax.x)), my = fmaxf(fabsf(dmin.y), fabsf(dmax.y)), mz = fmaxf(fabsf(dmin.z), fabsf(dmax.z));
-                const float dLen = fsqrt(mx * mx + my * my + mz * mz) * 1.0001f;
-                const float mag = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + lightMag;
+                const float dLen = hull_dirs_length(dirs);
+                const float mag = max_abs3(o) + lightMag;
                 auto hull_box = [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float& ent, float& ext) {
                     const float ax = __fmaf_rn(hx.sel ? hix : lox, hx.k1, hx.c1), bx = __fmaf_rn(hx.sel ? lox : hix, hx.k2, hx.c2);
                     const float ay = __fmaf_rn(hy.sel ? hiy : loy, hy.k1, hy.c1), by = __fmaf_rn(hy.sel ? loy : hiy, hy.k2, hy.c2);

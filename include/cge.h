@@ -300,6 +300,11 @@ int cge_fast_bvh_build(const cge_scene_desc* desc, int on_gpu, int device, cge_f
 int cge_ray_sample_positions(int32_t width, int32_t height, int32_t x, int32_t y, int32_t rays_per_pixel_side, uint32_t seed,
                              float* ndc_out);
 int cge_bloom_weights(float sigma, float* weights9_out);
+/* cge_hull_clear_host: the triangle test of the light-hull pre-pass (the function the shadow stage's pre-pass kernel calls), evaluated on the
+ * host for n cases of (hit point o[3], parallelogram light v0 / edge01 / edge02 [9], triangle [9]); clear_out[i] = 1 claims that no ray from
+ * o to any point of the light is accepted by the triangle.  Parity-test entry: the CPU suite checks the claim against the reference's
+ * own intersectRayWithTriangle on sampled rays. */
+int cge_hull_clear_host(const float* o3, const float* light9, const float* tri9, uint32_t n, int32_t* clear_out);
 /* Copy out the BVH the library built (for parity tests against the reference's tree). Either pointer may be NULL. */
 int cge_scene_bvh_export(const cge_scene* scene, cge_bvh_node* nodes_out, uint32_t* prim_order_out);
 
