@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "cge_bvh_build_reference_order", "cge_bvh_validate", "cge_fast_bvh_build", "cge_ray_sample_positions", "cge_bloom_weights",
     "cge_trace_rays", "cge_kat_triangle", "cge_kat_triangle_precomputed", "cge_kat_aabb", "cge_kat_sphere",
     "cge_kat_plane", "cge_kat_triangle_plane", "cge_kat_point_in_triangle", "cge_comm_unique_id", "cge_comm_create",
-    "cge_comm_destroy", "cge_comm_host_frame", "cge_comm_peer_frame", "cge_render_distributed", "cge_hull_clear_host", "cge_host_alloc", "cge_host_free",
+    "cge_comm_destroy", "cge_comm_host_frame", "cge_comm_peer_frame", "cge_render_distributed", "cge_hull_clear_host", "cge_hull_box_host", "cge_host_alloc", "cge_host_free",
 ]
 
 _lib = None
@@ -440,6 +440,16 @@ def hull_clear_host(o3, light9, tri9) -> np.ndarray:
     l = lib()
     l.cge_hull_clear_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     _check(l.cge_hull_clear_host(o3.ctypes.data, light9.ctypes.data, tri9.ctypes.data, len(o3), out.ctypes.data))
+    return out
+
+
+def hull_box_host(o3, light9, box6) -> np.ndarray:
+    """cge_hull_box_host: the light-hull pre-pass's box test on the host (tests): 0 = no ray of the hull passes through the box."""
+    o3, light9, box6 = (np.ascontiguousarray(a, np.float32) for a in (o3, light9, box6))
+    out = np.zeros(len(o3), np.int32)
+    l = lib()
+    l.cge_hull_box_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    _check(l.cge_hull_box_host(o3.ctypes.data, light9.ctypes.data, box6.ctypes.data, len(o3), out.ctypes.data))
     return out
 
 

@@ -1751,6 +1751,28 @@ int cge_hull_clear_host(const float* o3, const float* light9, const float* tri9,
     return CGE_OK;
 }
 
+// ... and its box test (wavefront.cuh hull_box / hull_box_hit, with the kernel's set-up): hit_out = 0 claims that no ray from o to any
+// point of the light passes through the box [lo, hi] within its length.
+int cge_hull_box_host(const float* o3, const float* light9, const float* box6, uint32_t n, int32_t* hitOut)
+{
+    if (!o3 || !light9 || !box6 || !hitOut)
+        return fail(CGE_ERR_INVALID_ARG, "null argument");
+    for (uint32_t i = 0; i < n; i++) {
+        const float *po = o3 + 3 * size_t(i), *pl = light9 + 9 * size_t(i), *pb = box6 + 6 * size_t(i);
+        const vec3 o = v3(po[0], po[1], po[2]);
+        const vec3 v0 = v3(pl[0], pl[1], pl[2]), e01 = v3(pl[3], pl[4], pl[5]), e02 = v3(pl[6], pl[7], pl[8]);
+        const vec3 c[4] = { v0, v0 + e01, (v0 + e01) + e02, v0 + e02 };
+        HullDirs dirs = hull_dirs_empty();
+        for (int j = 0; j < 4; j++)
+            hull_dirs_add(dirs, c[j] - o);
+        const HullWalk walk = hull_walk(o, dirs.dmin, dirs.dmax);
+        float ent, ext;
+        hull_box(walk, pb[0], pb[1], pb[2], pb[3], pb[4], pb[5], ent, ext);
+        hitOut[i] = hull_box_hit(ent, ext) ? 1 : 0;
+    }
+    return CGE_OK;
+}
+
 // The FAST traversal tree alone, by either builder (parity test of the GPU builder against the host builder).
 int cge_fast_bvh_build(const cge_scene_desc* d, int onGpu, int device, cge_fast_node* nodesOut, uint32_t* nNodesInOut, uint32_t* orderOut,
     uint32_t* rootOut, uint32_t* depthOut, uint32_t* nLeavesOut, float* buildMsOut)

@@ -465,7 +465,7 @@ struct HullAxis {
     float k1, c1, k2, c2;
     bool sel, mixed;
 };
-__device__ __forceinline__ HullAxis hull_axis(float o, float dmin, float dmax)
+CGE_HD HullAxis hull_axis(float o, float dmin, float dmax)
 {
     auto recip = [](float v, float tiny) { return fabsf(v) > 1e-18f ? fdiv(1.0f, v) : tiny; };
     HullAxis h;
@@ -485,6 +485,61 @@ __device__ __forceinline__ HullAxis hull_axis(float o, float dmin, float dmax)
     }
     return h;
 }
+
+// The hull against one box: entry / exit parameter of the set { o + t * d : d in the hull's direction box } (entry clamped to 0); some
+// ray of the hull may pass through the box within t in [0, 1] iff hull_box_hit(ent, ext).  Host + device: the CPU suite checks the
+// test's conservativeness through cge_hull_box_host (tests/test_hull_clear.py).
+struct HullWalk {
+    HullAxis hx, hy, hz;
+    bool anyMixed;
+};
+CGE_HD HullWalk hull_walk(const vec3 o, const vec3 dmin, const vec3 dmax)
+{
+    HullWalk w;
+    w.hx = hull_axis(o.x, dmin.x, dmax.x), w.hy = hull_axis(o.y, dmin.y, dmax.y), w.hz = hull_axis(o.z, dmin.z, dmax.z);
+    w.anyMixed = w.hx.mixed || w.hy.mixed || w.hz.mixed;
+    return w;
+}
+CGE_HD float hull_fma(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+CGE_HD float hull_max3(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    return max3(a, b, c);
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+CGE_HD float hull_min3(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    return min3(a, b, c);
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+CGE_HD void hull_box(const HullWalk& w, float lox, float loy, float loz, float hix, float hiy, float hiz, float& ent, float& ext)
+{
+    const float kInf = __builtin_huge_valf();
+    const HullAxis &hx = w.hx, &hy = w.hy, &hz = w.hz;
+    const float ax = hull_fma(hx.sel ? hix : lox, hx.k1, hx.c1), bx = hull_fma(hx.sel ? lox : hix, hx.k2, hx.c2);
+    const float ay = hull_fma(hy.sel ? hiy : loy, hy.k1, hy.c1), by = hull_fma(hy.sel ? loy : hiy, hy.k2, hy.c2);
+    const float az = hull_fma(hz.sel ? hiz : loz, hz.k1, hz.c1), bz = hull_fma(hz.sel ? loz : hiz, hz.k2, hz.c2);
+    ent = fmaxf(hull_max3(ax, ay, az), 0.0f);
+    if (!w.anyMixed) {
+        ext = hull_min3(bx, by, bz);
+    } else {
+        ent = fmaxf(ent, hull_max3(hx.mixed ? bx : 0.0f, hy.mixed ? by : 0.0f, hz.mixed ? bz : 0.0f));
+        ext = hull_min3(hx.mixed ? kInf : bx, hy.mixed ? kInf : by, hz.mixed ? kInf : bz);
+    }
+}
+CGE_HD bool hull_box_hit(float ent, float ext) { return ent <= ext * 1.000008f && ent <= 1.0001f; }
 
 // The points between which every shadowed sample of light L lies (n = 1, 2 or 4; 0: the light casts no shadow ray)
 __device__ __forceinline__ unsigned light_corners(const float* __restrict__ L, const DevParams& p, vec3 c[4])
@@ -619,7 +674,6 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
             lightMag = fmaxf(lightMag, max_abs3(c[j]));
     }
     constexpr unsigned kDone = 0x7fffffffu;
-    constexpr float kInf = __builtin_huge_valf();
     unsigned long long nResolved = 0;
     for (;;) {
         unsigned chunk = 0;
@@ -661,22 +715,9 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
             } else if (!finite) {
                 hardHit = true;
             } else {
-                const HullAxis hx = hull_axis(o.x, dmin.x, dmax.x), hy = hull_axis(o.y, dmin.y, dmax.y), hz = hull_axis(o.z, dmin.z, dmax.z);
-                const bool anyMixed = hx.mixed || hy.mixed || hz.mixed;
+                const HullWalk walk = hull_walk(o, dmin, dmax);
                 const float dLen = hull_dirs_length(dirs);
                 const float mag = max_abs3(o) + lightMag;
-                auto hull_box = [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float& ent, float& ext) {
-                    const float ax = __fmaf_rn(hx.sel ? hix : lox, hx.k1, hx.c1), bx = __fmaf_rn(hx.sel ? lox : hix, hx.k2, hx.c2);
-                    const float ay = __fmaf_rn(hy.sel ? hiy : loy, hy.k1, hy.c1), by = __fmaf_rn(hy.sel ? loy : hiy, hy.k2, hy.c2);
-                    const float az = __fmaf_rn(hz.sel ? hiz : loz, hz.k1, hz.c1), bz = __fmaf_rn(hz.sel ? loz : hiz, hz.k2, hz.c2);
-                    ent = fmaxf(max3(ax, ay, az), 0.0f);
-                    if (!anyMixed) {
-                        ext = min3(bx, by, bz);
-                    } else {
-                        ent = fmaxf(ent, max3(hx.mixed ? bx : 0.0f, hy.mixed ? by : 0.0f, hz.mixed ? bz : 0.0f));
-                        ext = min3(hx.mixed ? kInf : bx, hy.mixed ? kInf : by, hz.mixed ? kInf : bz);
-                    }
-                };
                 unsigned stack[kFastStackSize];
                 int sp = 0;
                 unsigned cur = s.froot;
@@ -696,11 +737,10 @@ __global__ void __launch_bounds__(128, CGE_MINB_CULL) wf_vis_cull_kernel(DevScen
                         q3 = ldg4(nd + 3), q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2);
 #endif
                         float entL, extL, entR, extR;
-                        hull_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
-                        hull_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
+                        hull_box(walk, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, entL, extL);
+                        hull_box(walk, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, entR, extR);
                         const unsigned cl = __float_as_uint(q3.x), cr = __float_as_uint(q3.y);
-                        const bool hitL = entL <= extL * 1.000008f && entL <= 1.0001f;
-                        const bool hitR = entR <= extR * 1.000008f && entR <= 1.0001f;
+                        const bool hitL = hull_box_hit(entL, extL), hitR = hull_box_hit(entR, extR);
                         const bool leftFirst = hitL && (!hitR || entL <= entR);
                         if (hitL && hitR)
                             stack[sp++] = leftFirst ? cr : cl;

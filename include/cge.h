@@ -305,6 +305,9 @@ int cge_bloom_weights(float sigma, float* weights9_out);
  * o to any point of the light is accepted by the triangle.  Parity-test entry: the CPU suite checks the claim against the reference's
  * own intersectRayWithTriangle on sampled rays. */
 int cge_hull_clear_host(const float* o3, const float* light9, const float* tri9, uint32_t n, int32_t* clear_out);
+/* ... and the pre-pass's box test, same set-up: box6 = lower.xyz, upper.xyz; hit_out[i] = 0 claims that no ray from o to any point of
+ * the light passes through the box within its length. */
+int cge_hull_box_host(const float* o3, const float* light9, const float* box6, uint32_t n, int32_t* hit_out);
 /* Copy out the BVH the library built (for parity tests against the reference's tree). Either pointer may be NULL. */
 int cge_scene_bvh_export(const cge_scene* scene, cge_bvh_node* nodes_out, uint32_t* prim_order_out);
 

@@ -103,3 +103,38 @@ def test_degenerate_inputs(libs):
         ray = np.concatenate([np.tile(o[i], (9, 1)), pos - o[i], np.ones((9, 1), F)], 1)
         hit, _ = ref.kat_triangle(np.tile(tri[i], (9, 1)), ray)
         assert not (clear[i] and hit.any())
+
+
+def segment_box_overlap(o, d, lo, hi):
+    """Does the segment o + t d, t in [0, 1], meet the closed box [lo, hi]?  Exact slab arithmetic in float64."""
+    o, d, lo, hi = (np.asarray(a, np.float64) for a in (o, d, lo, hi))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0, t1 = (lo - o) / d, (hi - o) / d
+    tn, tf = np.minimum(t0, t1), np.maximum(t0, t1)
+    par = d == 0  # parallel to the slab: inside it or never
+    inside = (o >= lo) & (o <= hi)
+    tn = np.where(par, np.where(inside, -np.inf, np.inf), tn)
+    tf = np.where(par, np.where(inside, np.inf, -np.inf), tf)
+    return np.maximum(tn.max(-1), 0.0) <= np.minimum(tf.min(-1), 1.0)
+
+
+@pytest.mark.parametrize("kind", ["between", "beside_hit", "grazing", "behind", "at_light"])
+def test_a_box_the_hull_misses_is_met_by_no_ray_to_the_light(libs, kind):
+    """The pre-pass walks the tree with the hull of the light: a subtree is skipped when hull_box says no ray of the hull can pass
+    through its box.  Checked against exact segment / box arithmetic on sampled rays, for boxes from leaf size to scene size."""
+    cge, _ = libs
+    rng = np.random.default_rng({"between": 11, "beside_hit": 12, "grazing": 13, "behind": 14, "at_light": 15}[kind])
+    n, k = 150000, 40
+    o, v0, e01, e02, tri = cases(rng, n, kind)
+    pts = tri.reshape(n, 3, 3)
+    grow = (10.0 ** rng.uniform(-4.0, 0.3, size=(n, 1))).astype(F)  # from a sliver around the triangle to a box holding the scene
+    lo, hi = (pts.min(1) - grow * rng.random((n, 3))).astype(F), (pts.max(1) + grow * rng.random((n, 3))).astype(F)
+    hit = cge.hull_box_host(o, np.concatenate([v0, e01, e02], 1), np.concatenate([lo, hi], 1)).astype(bool)
+    pos = light_points(rng, n, k, v0, e01, e02)
+    d = (pos - o[:, None, :]).astype(F)
+    met = segment_box_overlap(o[:, None, :], d, lo[:, None, :], hi[:, None, :]).any(1)
+    wrong = ~hit & met
+    assert not wrong.any(), f"{kind}: {int(wrong.sum())} boxes called missed are met by a ray, first case {int(np.flatnonzero(wrong)[0])}"
+    rejected = float((~hit & ~met).sum()) / max(int((~met).sum()), 1)
+    assert rejected >= 0.25, f"{kind}: only {rejected:.2f} of the boxes no sampled ray meets are rejected"
+    print(f"{kind}: met {met.mean():.3f}, hull says hit {hit.mean():.3f}, rejected among unmet {rejected:.3f}")
