@@ -430,18 +430,24 @@ inline vec3 getFinalColor(const Scene& scene, const BvhInterface& bvh, Ray ray, 
 // PNG parsing is host I/O outside the hot path).
 inline Scene loadFlatScene(const std::string& path)
 {
-    FILE* fp = std::fopen(path.c_str(), "rb");
+    // the file is user input: it is closed on every path, every section must be there in full, and every offset / count / id that
+    // is used as an index below is checked against the header's counts first
+    std::unique_ptr<FILE, int (*)(FILE*)> file(std::fopen(path.c_str(), "rb"), &std::fclose);
+    FILE* fp = file.get();
     if (!fp)
         throw std::runtime_error("File " + path + " does not exist.");
     cge_scene_file_header h;
-    if (std::fread(&h, sizeof(h), 1, fp) != 1 || std::memcmp(h.magic, CGE_SCENE_FILE_MAGIC, 8) != 0) {
-        std::fclose(fp);
-        throw std::runtime_error("Failed to load scene " + path);
-    }
+    if (std::fread(&h, sizeof(h), 1, fp) != 1 || std::memcmp(h.magic, CGE_SCENE_FILE_MAGIC, 8) != 0)
+        throw std::runtime_error("Failed to load scene " + path + ": not a flat scene file");
+    std::fseek(fp, 0, SEEK_END);
+    const size_t fileBytes = size_t(std::ftell(fp));
+    std::fseek(fp, long(sizeof(h)), SEEK_SET);
     auto rd = [&](auto& vec, size_t count) {
+        if (count > fileBytes / sizeof(vec[0])) // (before resize: a corrupt count must not become a huge allocation)
+            throw std::runtime_error("Failed to load scene " + path + ": truncated scene file");
         vec.resize(count);
         if (count && std::fread(vec.data(), sizeof(vec[0]), count, fp) != count)
-            throw std::runtime_error("Failed to load scene " + path);
+            throw std::runtime_error("Failed to load scene " + path + ": truncated scene file");
     };
     std::vector<cge_mesh_desc> meshes;
     std::vector<cge_vertex> vertices;
@@ -452,7 +458,27 @@ inline Scene loadFlatScene(const std::string& path)
     std::vector<float> texels;
     rd(meshes, h.n_meshes), rd(vertices, h.n_vertices), rd(tris, size_t(h.n_triangles) * 3), rd(spheres, h.n_spheres);
     rd(lights, h.n_lights), rd(textures, h.n_textures), rd(texels, size_t(h.n_texels) * 3);
-    std::fclose(fp);
+    auto bad = [&](const char* what) { return std::runtime_error("Failed to load scene " + path + ": " + what + " out of range"); };
+    for (const auto& td : textures)
+        if (td.width < 0 || td.height < 0 || td.texel_offset > h.n_texels || uint64_t(td.width) * uint64_t(td.height) > h.n_texels - td.texel_offset)
+            throw bad("texture");
+    for (const auto& md : meshes) {
+        if (md.vertex_offset > h.n_vertices || md.vertex_count > h.n_vertices - md.vertex_offset)
+            throw bad("mesh vertices");
+        if (md.triangle_offset > h.n_triangles || md.triangle_count > h.n_triangles - md.triangle_offset)
+            throw bad("mesh triangles");
+        if (md.texture_id >= int32_t(h.n_textures))
+            throw bad("mesh texture id");
+        for (uint32_t t = 0; t < md.triangle_count * 3; t++)
+            if (tris[3 * size_t(md.triangle_offset) + t] >= md.vertex_count)
+                throw bad("triangle index");
+    }
+    for (const auto& sd : spheres)
+        if (sd.texture_id >= int32_t(h.n_textures))
+            throw bad("sphere texture id");
+    for (const auto& ld : lights)
+        if (ld.type != CGE_LIGHT_POINT && ld.type != CGE_LIGHT_SEGMENT && ld.type != CGE_LIGHT_PARALLELOGRAM)
+            throw bad("light type");
     Scene sc;
     std::vector<std::shared_ptr<Image>> images;
     for (const auto& td : textures) {

@@ -121,6 +121,8 @@ def parallelogram_light(v0, edge01, edge02, c0, c1, c2, c3):
 
 def load(path) -> FlatScene:
     buf = np.fromfile(str(path), dtype=np.uint8)
+    if len(buf) < HEADER_DT.itemsize:
+        raise ValueError(f"{path}: not a flat scene file")
     h = buf[: HEADER_DT.itemsize].view(HEADER_DT)[0]
     if bytes(h["magic"]) != MAGIC:
         raise ValueError(f"{path}: not a flat scene file")
@@ -130,6 +132,8 @@ def load(path) -> FlatScene:
         nonlocal off
         dt = np.dtype(dt)
         nbytes = dt.itemsize * int(count)
+        if off + nbytes > len(buf):
+            raise ValueError(f"{path}: truncated scene file")
         a = buf[off: off + nbytes].view(dt).copy()
         off += nbytes
         return a.reshape(shape) if shape is not None else a

@@ -36,7 +36,12 @@ int main(int argc, char** argv)
             saveFlatScene(flatten(scene), argv[4]);
             return 0;
         }
-        std::fprintf(stderr, "usage: scene_export prebuilt <type> <dataDir> <out> | obj <file> <0|1> <out>\n");
+        if (argc == 3 && std::string(argv[1]) == "check") { // loadFlatScene on a (possibly corrupt) flat scene file
+            const Scene s = loadFlatScene(argv[2]);
+            std::printf("ok %zu meshes %zu spheres %zu lights\n", s.meshes.size(), s.spheres.size(), s.lights.size());
+            return 0;
+        }
+        std::fprintf(stderr, "usage: scene_export prebuilt <type> <dataDir> <out> | obj <file> <0|1> <out> | check <file.cges>\n");
         return 2;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "scene_export: %s\n", e.what());

@@ -92,3 +92,52 @@ def test_cli_resolves_the_reference_scene_names(tool, tmp_path):
         r = subprocess.run([str(cli), str(cfg), "--print-config"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert r.stdout.splitlines()[1] == f"scene {shown}"
+
+
+def test_flat_scene_files_are_untrusted_input(tool, tmp_path):
+    """loadFlatScene (C++ host mirror) and scenefile.load (Python glue): a truncated file, counts larger than the file, offsets and
+    ids that point outside their arrays are refused with a clear error instead of being copied or indexed."""
+    import importlib
+    import sys
+    import numpy as np
+    sys.path.insert(0, str(ROOT))
+    sf = importlib.import_module("computer-graphics-engine_b200.scenefile")
+    good = (ROOT / "tests" / "golden" / "scenes" / "cube_textured.cges").read_bytes()
+
+    def check(data):
+        f = tmp_path / "x.cges"
+        f.write_bytes(data)
+        return subprocess.run([str(tool), "check", str(f)], capture_output=True, text=True)
+
+    assert check(good).returncode == 0
+    r = check(good[: len(good) // 2])
+    assert r.returncode == 1 and "truncated" in r.stderr
+    with pytest.raises(ValueError, match="truncated"):
+        f = tmp_path / "t.cges"
+        f.write_bytes(good[: len(good) // 2])
+        sf.load(f)
+    with pytest.raises(ValueError, match="not a flat scene file"):
+        f.write_bytes(b"short")
+        sf.load(f)
+    s = sf.load(ROOT / "tests" / "golden" / "scenes" / "cube_textured.cges")
+    for field, value, what in (("vertex_offset", 10**6, "mesh vertices"), ("vertex_count", 10**6, "mesh vertices"),
+                               ("triangle_count", 10**6, "mesh triangles"), ("texture_id", 7, "mesh texture id")):
+        bad = s.copy()
+        bad.meshes[field][0] = value
+        sf.save(bad, tmp_path / "b.cges")
+        r = check((tmp_path / "b.cges").read_bytes())
+        assert r.returncode == 1 and what in r.stderr, (field, r.stderr)
+    bad = s.copy()
+    bad.triangles[0, 1] = 10**6
+    sf.save(bad, tmp_path / "b.cges")
+    r = check((tmp_path / "b.cges").read_bytes())
+    assert r.returncode == 1 and "triangle index" in r.stderr
+    bad = s.copy()
+    bad.textures["width"][0] = 1 << 20
+    sf.save(bad, tmp_path / "b.cges")
+    r = check((tmp_path / "b.cges").read_bytes())
+    assert r.returncode == 1 and "texture" in r.stderr
+    huge = bytearray(good)
+    huge[12:16] = np.uint32(0xFFFFFFF0).tobytes()  # n_vertices far beyond the file: refused before anything is allocated
+    r = check(bytes(huge))
+    assert r.returncode == 1 and "truncated" in r.stderr
